@@ -1,0 +1,224 @@
+// TEST INFRASTRUCTURE ONLY — CPU oracle, whole-frame pipeline.
+// Restates ElasticFusion::processFrame / predict / filterDepth / metriciseDepth (Core/ElasticFusion.cpp:270-673)
+// for the open-loop configuration (closeLoops == false, reloc == false): Ferns, deformation graphs and the
+// INACTIVE model-to-model branch are out of scope.
+#include "ef_oracle.h"
+#include "efo_common.h"
+#include "efo_linalg.h"
+
+#include <chrono>
+#include <cstdio>
+#include <vector>
+
+namespace {
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+struct EfoFusion {
+  EfoConfig cfg;
+  EfoOdometry* frameToModel;
+  int rows, cols;
+  float cam4[4];
+  int tick;
+  double T_wc[16];
+  float maxDepthProcessed;
+
+  std::vector<uint8_t> rgb, rgba;
+  std::vector<uint16_t> depthRaw, depthFiltered;
+  std::vector<float> depthMetric, depthMetricFiltered;
+
+  std::vector<float> map, mapTmp, newUnstable, rawFb, filtFb;
+  int count;
+
+  std::vector<uint32_t> indexTex;
+  std::vector<float> vertConf, colorTime, normRad;
+
+  std::vector<uint8_t> imageTex, fillImage;
+  std::vector<float> vertexTex, normalTex, fillVertex, fillNormal;
+  std::vector<uint16_t> timeTex;
+
+  double timers[4];
+  float lastWeighting;
+};
+
+extern "C" EfoFusion* efo_fusion_create(const EfoConfig* cfg) {
+  EfoFusion* f = new EfoFusion();
+  f->cfg = *cfg;
+  f->rows = cfg->height;
+  f->cols = cfg->width;
+  f->cam4[0] = cfg->cx;
+  f->cam4[1] = cfg->cy;
+  f->cam4[2] = cfg->fx;
+  f->cam4[3] = cfg->fy;
+  // RGBDOdometry defaults: distThresh 0.10, angleThresh sin(20*3.14159254/180) (RGBDOdometry.h:41-42)
+  f->frameToModel = efo_odom_create(cfg->width, cfg->height, cfg->cx, cfg->cy, cfg->fx, cfg->fy, 0.10f,
+                                    sinf(20.f * 3.14159254f / 180.f));
+  f->tick = 1;
+  for (int i = 0; i < 16; ++i) f->T_wc[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  f->maxDepthProcessed = 20.0f;
+  const size_t n = (size_t)f->rows * f->cols;
+  f->rgb.assign(n * 3, 0);
+  f->rgba.assign(n * 4, 0);
+  f->depthRaw.assign(n, 0);
+  f->depthFiltered.assign(n, 0);
+  f->depthMetric.assign(n, 0.f);
+  f->depthMetricFiltered.assign(n, 0.f);
+  f->map.assign((size_t)cfg->capacity * 12, 0.f);
+  f->mapTmp.assign((size_t)cfg->capacity * 12, 0.f);
+  f->newUnstable.assign(n * 12, 0.f);
+  f->rawFb.assign(n * 12, 0.f);
+  f->filtFb.assign(n * 12, 0.f);
+  f->count = 0;
+  f->indexTex.assign(n, 0);
+  f->vertConf.assign(n * 4, 0.f);
+  f->colorTime.assign(n * 4, 0.f);
+  f->normRad.assign(n * 4, 0.f);
+  f->imageTex.assign(n * 4, 0);
+  f->fillImage.assign(n * 4, 0);
+  f->vertexTex.assign(n * 4, 0.f);
+  f->normalTex.assign(n * 4, 0.f);
+  f->fillVertex.assign(n * 4, 0.f);
+  f->fillNormal.assign(n * 4, 0.f);
+  f->timeTex.assign(n, 0);
+  for (int i = 0; i < 4; ++i) f->timers[i] = 0;
+  f->lastWeighting = 0;
+  return f;
+}
+
+extern "C" void efo_fusion_destroy(EfoFusion* f) {
+  efo_odom_destroy(f->frameToModel);
+  delete f;
+}
+
+// ElasticFusion::predict, ElasticFusion.cpp:621-653 (lastFrameRecovery == false, lost == false)
+static void predict(EfoFusion* f) {
+  efo_combined_predict(f->map.data(), f->count, f->T_wc, f->maxDepthProcessed, f->cfg.confidence, f->tick, f->tick,
+                       f->cfg.time_delta, f->rows, f->cols, f->cam4, f->imageTex.data(), f->vertexTex.data(),
+                       f->normalTex.data(), f->timeTex.data(), nullptr, 0);
+  efo_fill_vertex(f->vertexTex.data(), f->depthFiltered.data(), 0, f->rows, f->cols, f->cam4, f->fillVertex.data());
+  efo_fill_normal(f->normalTex.data(), f->depthFiltered.data(), 0, f->rows, f->cols, f->cam4, f->fillNormal.data());
+  efo_fill_image(f->imageTex.data(), f->rgb.data(), f->cfg.frame_to_frame_rgb ? 1 : 0, f->rows, f->cols,
+                 f->fillImage.data());
+}
+
+extern "C" void efo_fusion_process_frame(EfoFusion* f, const uint8_t* rgb, const uint16_t* depth, int64_t timestamp,
+                                         float weightMultiplier, const double* in_T_wc) {
+  (void)timestamp;
+  const size_t n = (size_t)f->rows * f->cols;
+  double t0 = now_s();
+  memcpy(f->rgb.data(), rgb, n * 3);
+  memcpy(f->depthRaw.data(), depth, n * 2);
+  for (size_t i = 0; i < n; ++i) {  // GL_RGB upload into an RGBA8 texture: alpha = 255
+    f->rgba[i * 4 + 0] = rgb[i * 3 + 0];
+    f->rgba[i * 4 + 1] = rgb[i * 3 + 1];
+    f->rgba[i * 4 + 2] = rgb[i * 3 + 2];
+    f->rgba[i * 4 + 3] = 255;
+  }
+  // filterDepth + metriciseDepth, ElasticFusion.cpp:284-285,655-673
+  efo_bilateral(f->depthRaw.data(), f->rows, f->cols, f->cfg.depth_cutoff, f->depthFiltered.data());
+  efo_metric(f->depthRaw.data(), f->rows, f->cols, f->cfg.depth_cutoff, f->depthMetric.data());
+  efo_metric(f->depthFiltered.data(), f->rows, f->cols, f->cfg.depth_cutoff, f->depthMetricFiltered.data());
+  double t1 = now_s();
+  f->timers[0] += t1 - t0;
+
+  if (f->tick == 1) {
+    // ElasticFusion.cpp:290-296
+    int rawN = efo_feedback_buffer(f->rgb.data(), f->depthMetric.data(), f->rows, f->cols, f->cam4, f->tick,
+                                   f->maxDepthProcessed, f->rawFb.data());
+    int filtN = efo_feedback_buffer(f->rgb.data(), f->depthMetricFiltered.data(), f->rows, f->cols, f->cam4, f->tick,
+                                    f->maxDepthProcessed, f->filtFb.data());
+    f->count = efo_map_initialise(f->rawFb.data(), rawN, f->filtFb.data(), filtN, (int)n, f->map.data());
+    efo_odom_init_first_rgb(f->frameToModel, f->rgba.data());
+    f->timers[2] += now_s() - t1;
+  } else {
+    double T_prev[16];
+    memcpy(T_prev, f->T_wc, sizeof(T_prev));
+    if (!in_T_wc) {
+      // ElasticFusion.cpp:302-323
+      bool shouldFillIn = !efo_dense_enough(f->imageTex.data(), f->rows, f->cols, 20);
+      efo_odom_init_icp_model(f->frameToModel, shouldFillIn ? f->fillVertex.data() : f->vertexTex.data(),
+                              shouldFillIn ? f->fillNormal.data() : f->normalTex.data(), f->T_wc);
+      efo_odom_init_rgb_model(f->frameToModel,
+                              (shouldFillIn || f->cfg.frame_to_frame_rgb) ? f->fillImage.data() : f->imageTex.data());
+      efo_odom_init_icp_depth(f->frameToModel, f->depthFiltered.data(), f->maxDepthProcessed);
+      efo_odom_init_rgb(f->frameToModel, f->rgba.data());
+      efo_odom_track(f->frameToModel, f->T_wc, f->cfg.rgb_only, f->cfg.icp_weight, f->cfg.pyramid, f->cfg.fast_odom,
+                     f->cfg.so3, nullptr, 0);
+    } else {
+      memcpy(f->T_wc, in_T_wc, sizeof(f->T_wc));
+    }
+    double t2 = now_s();
+    f->timers[1] += t2 - t1;
+
+    // velocity weighting, ElasticFusion.cpp:369-383
+    double inv[16], T_curr_prev[16];
+    la::se3_inverse(f->T_wc, inv);
+    la::mul4(inv, T_prev, T_curr_prev);
+    double tn = std::sqrt(T_curr_prev[3] * T_curr_prev[3] + T_curr_prev[7] * T_curr_prev[7] + T_curr_prev[11] * T_curr_prev[11]);
+    double ln = la::se3_log_norm(T_curr_prev);
+    float weighting = (float)std::max(tn, ln);
+    float largest = 0.01f, minWeight = 0.5f;
+    if (weighting > largest) weighting = largest;
+    weighting = std::max(1.0f - (weighting / largest), minWeight) * weightMultiplier;
+    f->lastWeighting = weighting;
+
+    // ElasticFusion.cpp:387 — the mid-frame predict(): its outputs are only consumed by loop closure and are
+    // overwritten by the predict() at :599, but the reference pays for it, so the timed baseline does too.
+    predict(f);
+    double t3 = now_s();
+    f->timers[3] += t3 - t2;
+
+    if (!f->cfg.rgb_only) {
+      // ElasticFusion.cpp:536-585
+      efo_predict_indices(f->map.data(), f->count, f->T_wc, f->tick, f->maxDepthProcessed, f->cfg.time_delta, f->rows,
+                          f->cols, f->cam4, f->indexTex.data(), f->vertConf.data(), f->colorTime.data(),
+                          f->normRad.data());
+      int newN = efo_fuse(f->map.data(), f->count, f->T_wc, f->tick, f->rgb.data(), f->depthMetric.data(),
+                          f->depthMetricFiltered.data(), f->indexTex.data(), f->vertConf.data(), f->colorTime.data(),
+                          f->normRad.data(), f->maxDepthProcessed, weighting, f->rows, f->cols, f->cam4,
+                          f->newUnstable.data());
+      efo_predict_indices(f->map.data(), f->count, f->T_wc, f->tick, f->maxDepthProcessed, f->cfg.time_delta, f->rows,
+                          f->cols, f->cam4, f->indexTex.data(), f->vertConf.data(), f->colorTime.data(),
+                          f->normRad.data());
+      if (f->count + newN > f->cfg.capacity) newN = f->cfg.capacity - f->count;
+      f->count = efo_clean(f->map.data(), f->count, f->newUnstable.data(), newN, f->T_wc, f->tick, f->indexTex.data(),
+                           f->vertConf.data(), f->colorTime.data(), f->normRad.data(), f->cfg.confidence,
+                           f->cfg.time_delta, f->maxDepthProcessed, f->rows, f->cols, f->cam4, f->mapTmp.data());
+      f->map.swap(f->mapTmp);
+    }
+    f->timers[2] += now_s() - t3;
+  }
+
+  double t4 = now_s();
+  predict(f);  // ElasticFusion.cpp:599
+  f->timers[3] += now_s() - t4;
+  f->tick++;
+}
+
+extern "C" void efo_fusion_pose(const EfoFusion* f, double* T) { memcpy(T, f->T_wc, sizeof(f->T_wc)); }
+extern "C" int efo_fusion_count(const EfoFusion* f) { return f->count; }
+extern "C" int efo_fusion_tick(const EfoFusion* f) { return f->tick; }
+extern "C" const float* efo_fusion_map(const EfoFusion* f) { return f->map.data(); }
+extern "C" EfoOdometry* efo_fusion_odometry(EfoFusion* f) { return f->frameToModel; }
+extern "C" const void* efo_fusion_buffer(const EfoFusion* f, int which) {
+  switch (which) {
+    case 0: return f->imageTex.data();
+    case 1: return f->vertexTex.data();
+    case 2: return f->normalTex.data();
+    case 3: return f->timeTex.data();
+    case 4: return f->fillImage.data();
+    case 5: return f->fillVertex.data();
+    case 6: return f->fillNormal.data();
+    case 7: return f->depthFiltered.data();
+    case 8: return f->depthMetric.data();
+    case 9: return f->depthMetricFiltered.data();
+    case 10: return f->indexTex.data();
+    case 11: return f->vertConf.data();
+    case 12: return f->colorTime.data();
+    case 13: return f->normRad.data();
+  }
+  return nullptr;
+}
+extern "C" void efo_fusion_timers(const EfoFusion* f, double* out4) { memcpy(out4, f->timers, sizeof(f->timers)); }
