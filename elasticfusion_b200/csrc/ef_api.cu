@@ -1,0 +1,833 @@
+// C ABI of libefusion.so (include/efusion_b200.h): context management, named buffers, the RGBDOdometry stage API and
+// the whole-frame orchestration that mirrors ElasticFusion::processFrame (reference Core/ElasticFusion.cpp:270-607).
+#include <math.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "ef_internal.h"
+
+using namespace ef;
+
+// ---- kernels' host entry points (ef_track.cu, ef_preprocess.cu, ef_map.cu) --------------------------------------
+namespace ef {
+int odom_init_icp_depth(EfContext* ctx, int which, const uint16_t* depth_dev, float cutoff);
+int odom_init_icp_pred(EfContext* ctx, int which, const float* vtx4, const float* nrm4);
+int odom_init_icp_model(EfContext* ctx, int which, const float* vtx4, const float* nrm4, const float* vtxB = nullptr,
+                        const float* nrmB = nullptr, const int* flag = nullptr);
+int odom_populate(EfContext* ctx, int which, const uint8_t* rgba, float** destDepths, uint8_t** destImages, bool with_depth,
+                  const uint8_t* rgbaB = nullptr, const int* flag = nullptr, bool forceB = false);
+int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom, bool so3);
+int odom_finish_async(EfContext* ctx, int which, float weightMultiplier, bool have_track);
+int odom_set_pose_async(EfContext* ctx, int which, const double* T_dev);
+int launch_se3_step_raw(EfContext* ctx, int which, int level, bool do_icp, bool do_rgb);
+int launch_rgb_residual_raw(EfContext* ctx, int which, int level);
+int launch_so3_raw(EfContext* ctx, int which);
+int launch_sobel(EfContext* ctx, int which);
+int preprocess_depth(EfContext* ctx, const uint16_t* raw, float cutoff, uint16_t* filtered, float* metric, float* metric_filtered);
+int rgb_to_rgba(EfContext* ctx, const uint8_t* rgb, uint8_t* rgba);
+
+int map_initialise_async(EfContext* ctx);
+int map_update_pose_async(EfContext* ctx, const double* T_host_or_null);
+int map_predict_indices_async(EfContext* ctx, int time_or_neg, float max_depth, int time_delta);
+int map_fuse_async(EfContext* ctx, int time_or_neg, float max_depth, float weighting_or_neg);
+int map_clean_async(EfContext* ctx, int time_or_neg, float conf_threshold, int time_delta, float max_depth);
+int map_raycast_async(EfContext* ctx, float max_depth, float conf_threshold, int time, int max_time, int time_delta, int mode,
+                      bool use_device_tick);
+int map_fill_in_async(EfContext* ctx, bool passthrough_geometry, bool passthrough_image);
+int map_dense_enough_async(EfContext* ctx);
+int map_tick_increment_async(EfContext* ctx);
+int map_select_model_inputs(EfContext* ctx, const float** vtx, const float** nrm, const uint8_t** img);
+void map_free_host(EfContext* ctx);
+}  // namespace ef
+
+#define CU(x)                                  \
+  do {                                         \
+    cudaError_t e__ = (x);                     \
+    if (e__ != cudaSuccess) return (int)e__;   \
+  } while (0)
+#define RC(x)              \
+  do {                     \
+    int rc__ = (x);        \
+    if (rc__) return rc__; \
+  } while (0)
+
+namespace {
+
+struct Arena {
+  std::vector<void*> blocks;
+  template <typename T>
+  cudaError_t alloc(T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T) + 256);
+    if (e != cudaSuccess) return e;
+    blocks.push_back(q);
+    *p = (T*)q;
+    return cudaSuccess;
+  }
+};
+
+Arena* arena_of(EfContext* ctx);
+
+struct CtxExtra {
+  Arena arena;
+  std::vector<EfSolveTrace> trace_host;
+};
+
+}  // namespace
+
+struct EfContextFull : EfContext {
+  CtxExtra extra;
+};
+
+static Arena* arena(EfContext* ctx) { return &static_cast<EfContextFull*>(ctx)->extra.arena; }
+
+extern "C" void ef_default_config(EfConfig* c, int width, int height, float fx, float fy, float cx, float cy) {
+  memset(c, 0, sizeof(*c));
+  c->width = width;
+  c->height = height;
+  c->fx = fx;
+  c->fy = fy;
+  c->cx = cx;
+  c->cy = cy;
+  // ElasticFusion ctor defaults, reference Core/ElasticFusion.h:42-58
+  c->time_delta = 200;
+  c->count_thresh = 35000;
+  c->err_thresh = 5e-05f;
+  c->cov_thresh = 1e-05f;
+  c->close_loops = 0;
+  c->iclnuim = 0;
+  c->reloc = 0;
+  c->photo_thresh = 115;
+  c->confidence = 10;
+  c->depth_cutoff = 3;
+  c->icp_weight = 10;
+  c->fast_odom = 0;
+  c->fern_thresh = 0.3095f;
+  c->so3 = 1;
+  c->frame_to_frame_rgb = 0;
+  c->capacity = 3072 * 3072;  // GlobalModel::MAX_VERTICES, reference Core/GlobalModel.cpp:22-24
+  c->device = 0;
+  c->skip_mid_predict = 1;
+}
+
+extern "C" const char* ef_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code == EF_EINVAL) return "invalid argument";
+  if (code == EF_ENOMEM) return "out of memory";
+  if (code == EF_ESTATE) return "invalid state";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "unknown error";
+}
+
+static int alloc_odom(EfContext* ctx, OdomDev& od) {
+  Arena* A = arena(ctx);
+  const EfConfig& c = ctx->cfg;
+  memset(&od, 0, sizeof(od));
+  od.width = c.width;
+  od.height = c.height;
+  // RGBDOdometry ctor, reference Core/Utils/RGBDOdometry.cpp:22-117 and RGBDOdometry.h:41-42
+  od.distThres = 0.10f;
+  od.angleThres = sinf(20.f * 3.14159254f / 180.f);
+  od.sobelScale = (float)(1.0 / pow(2.0, 3));
+  od.maxDepthDeltaRGB = 0.07f;
+  od.maxDepthRGB = 6.0f;
+  od.minGrad[0] = 5;
+  od.minGrad[1] = 3;
+  od.minGrad[2] = 1;
+  for (int i = 0; i < NUM_PYRS; ++i) {
+    od.minScale[i] = (float)(pow((double)od.minGrad[i], 2.0) / pow((double)od.sobelScale, 2.0));
+    od.rows[i] = c.height >> i;
+    od.cols[i] = c.width >> i;
+    const size_t n = (size_t)od.rows[i] * od.cols[i];
+    CU(A->alloc(&od.depth_tmp[i], n));
+    CU(A->alloc(&od.vmap_g_prev[i], 3 * n));
+    CU(A->alloc(&od.nmap_g_prev[i], 3 * n));
+    CU(A->alloc(&od.vmap_curr[i], 3 * n));
+    CU(A->alloc(&od.nmap_curr[i], 3 * n));
+    CU(A->alloc(&od.lastDepth[i], n));
+    CU(A->alloc(&od.nextDepth[i], n));
+    CU(A->alloc(&od.lastImage[i], n));
+    CU(A->alloc(&od.nextImage[i], n));
+    CU(A->alloc(&od.lastNextImage[i], n));
+    CU(A->alloc(&od.dIdx[i], n));
+    CU(A->alloc(&od.dIdy[i], n));
+    CU(A->alloc(&od.corres[i], n));
+    // the reference's cudaMalloc'd maps start uninitialised; NaN / zero fill keeps every first read defined
+    CU(cudaMemsetAsync(od.vmap_g_prev[i], 0xff, 3 * n * sizeof(float), ctx->stream));
+    CU(cudaMemsetAsync(od.nmap_g_prev[i], 0xff, 3 * n * sizeof(float), ctx->stream));
+    CU(cudaMemsetAsync(od.vmap_curr[i], 0xff, 3 * n * sizeof(float), ctx->stream));
+    CU(cudaMemsetAsync(od.nmap_curr[i], 0xff, 3 * n * sizeof(float), ctx->stream));
+    CU(cudaMemsetAsync(od.lastDepth[i], 0xff, n * sizeof(float), ctx->stream));
+    CU(cudaMemsetAsync(od.nextDepth[i], 0xff, n * sizeof(float), ctx->stream));
+    CU(cudaMemsetAsync(od.lastImage[i], 0, n, ctx->stream));
+    CU(cudaMemsetAsync(od.nextImage[i], 0, n, ctx->stream));
+    CU(cudaMemsetAsync(od.lastNextImage[i], 0, n, ctx->stream));
+    CU(cudaMemsetAsync(od.dIdx[i], 0, n * 2, ctx->stream));
+    CU(cudaMemsetAsync(od.dIdy[i], 0, n * 2, ctx->stream));
+    CU(cudaMemsetAsync(od.corres[i], 0, n * sizeof(DataTerm), ctx->stream));
+    CU(cudaMemsetAsync(od.depth_tmp[i], 0, n * 2, ctx->stream));
+  }
+  const size_t n0 = (size_t)c.width * c.height;
+  CU(A->alloc(&od.vmaps_tmp, 4 * n0));
+  CU(cudaMemsetAsync(od.vmaps_tmp, 0, 4 * n0 * sizeof(float), ctx->stream));
+  CU(A->alloc(&od.gn, 1));
+  CU(A->alloc(&od.partials, (size_t)MAX_RED_BLOCKS * PARTIAL_STRIDE));
+  CU(A->alloc(&od.partials_i, (size_t)MAX_RED_BLOCKS * 2));
+  CU(A->alloc(&od.counter, 4));
+  CU(A->alloc(&od.trace, MAX_TRACE));
+  CU(cudaMemsetAsync(od.counter, 0, 16, ctx->stream));
+  CU(cudaMemsetAsync(od.trace, 0, sizeof(EfSolveTrace) * MAX_TRACE, ctx->stream));
+  GNState g;
+  memset(&g, 0, sizeof(g));
+  for (int k = 0; k < 16; ++k) g.T_wc[k] = (k % 5 == 0) ? 1.0 : 0.0;
+  g.lastICPCount = g.lastRGBCount = g.lastSO3Count = (float)(c.width * c.height);
+  g.fx = c.fx;
+  g.fy = c.fy;
+  g.cx = c.cx;
+  g.cy = c.cy;
+  g.break_level = -1;
+  g.weighting = 1.0f;
+  CU(cudaMemcpyAsync(od.gn, &g, sizeof(g), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+namespace ef {
+int alloc_map(EfContext* ctx);  // ef_map.cu
+}
+namespace ef {
+template <typename T>
+cudaError_t ctx_alloc(EfContext* ctx, T** p, size_t n) {
+  return arena(ctx)->alloc(p, n);
+}
+template cudaError_t ctx_alloc<float4>(EfContext*, float4**, size_t);
+template cudaError_t ctx_alloc<float>(EfContext*, float**, size_t);
+template cudaError_t ctx_alloc<int>(EfContext*, int**, size_t);
+template cudaError_t ctx_alloc<unsigned int>(EfContext*, unsigned int**, size_t);
+template cudaError_t ctx_alloc<unsigned long long>(EfContext*, unsigned long long**, size_t);
+template cudaError_t ctx_alloc<uint8_t>(EfContext*, uint8_t**, size_t);
+template cudaError_t ctx_alloc<uint16_t>(EfContext*, uint16_t**, size_t);
+template cudaError_t ctx_alloc<uchar4>(EfContext*, uchar4**, size_t);
+template cudaError_t ctx_alloc<MapPose>(EfContext*, MapPose**, size_t);
+}  // namespace ef
+
+extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
+  if (!cfg || !out || cfg->width <= 0 || cfg->height <= 0 || cfg->capacity <= 0) return EF_EINVAL;
+  if (cfg->close_loops || cfg->reloc) return EF_EINVAL;  // loop closure is outside the hot path
+  if ((cfg->width >> 2) < 8 || (cfg->height >> 2) < 8) return EF_EINVAL;
+  CU(cudaSetDevice(cfg->device));
+  EfContextFull* full = new (std::nothrow) EfContextFull();
+  if (!full) return EF_ENOMEM;
+  EfContext* ctx = full;
+  ctx->cfg = *cfg;
+  ctx->device = cfg->device;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  ctx->num_sms = prop.multiProcessorCount;
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+    ctx->own_stream = false;
+  } else {
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  ctx->launches = 0;
+  ctx->tick = 1;
+  for (int k = 0; k < 16; ++k) ctx->T_wc[k] = (k % 5 == 0) ? 1.0 : 0.0;
+  ctx->rgb_only = false;
+  ctx->icp_weight = cfg->icp_weight;
+  ctx->pyramid = true;
+  ctx->fast_odom = cfg->fast_odom != 0;
+  ctx->so3 = cfg->so3 != 0;
+  ctx->frame_to_frame_rgb = cfg->frame_to_frame_rgb != 0;
+  ctx->confidence = cfg->confidence;
+  ctx->depth_cutoff = cfg->depth_cutoff;
+  ctx->max_depth_processed = 20.0f;  // reference Core/ElasticFusion.cpp:83
+  ctx->host_count = 0;
+
+  int rc = alloc_odom(ctx, ctx->odom[0]);
+  if (!rc) rc = alloc_odom(ctx, ctx->odom[1]);
+  const size_t n = (size_t)cfg->width * cfg->height;
+  Arena* A = arena(ctx);
+  Textures& t = ctx->tex;
+  memset(&t, 0, sizeof(t));
+#define TA(p, cnt)                               \
+  if (!rc) {                                     \
+    cudaError_t e_ = A->alloc(&(p), (cnt));      \
+    if (e_ != cudaSuccess) rc = (int)e_;         \
+    else cudaMemsetAsync((p), 0, (cnt) * sizeof(*(p)), ctx->stream); \
+  }
+  TA(t.rgb, n * 3);
+  TA(t.rgba, n * 4);
+  TA(t.depth_raw, n);
+  TA(t.depth_filtered, n);
+  TA(t.depth_metric, n);
+  TA(t.depth_metric_filtered, n);
+  TA(t.index, n);
+  TA(t.vert_conf, n);
+  TA(t.color_time, n);
+  TA(t.norm_rad, n);
+  TA(t.image, n);
+  TA(t.old_image, n);
+  TA(t.fill_image, n);
+  TA(t.vertex, n);
+  TA(t.normal, n);
+  TA(t.old_vertex, n);
+  TA(t.old_normal, n);
+  TA(t.fill_vertex, n);
+  TA(t.fill_normal, n);
+  TA(t.time, n);
+  TA(t.old_time, n);
+  TA(t.synth_depth, n);
+#undef TA
+  if (!rc) rc = alloc_map(ctx);
+  if (!rc) {
+    cudaError_t e = cudaMallocHost((void**)&ctx->pin_rgb, n * 3);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->pin_depth, n * 2);
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->pin_small, 65536);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->dev_small, 65536);
+    if (e != cudaSuccess) rc = (int)e;
+  }
+  if (!rc) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = (int)e;
+  }
+  if (rc) {
+    ef_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return 0;
+}
+
+extern "C" int ef_destroy(EfContext* ctx) {
+  if (!ctx) return EF_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  map_free_host(ctx);
+  for (void* p : arena(ctx)->blocks) cudaFree(p);
+  if (ctx->pin_rgb) cudaFreeHost(ctx->pin_rgb);
+  if (ctx->pin_depth) cudaFreeHost(ctx->pin_depth);
+  if (ctx->pin_small) cudaFreeHost(ctx->pin_small);
+  if (ctx->dev_small) cudaFree(ctx->dev_small);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete static_cast<EfContextFull*>(ctx);
+  return 0;
+}
+
+extern "C" void* ef_stream(EfContext* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int ef_sync(EfContext* ctx) {
+  if (!ctx) return EF_EINVAL;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int ef_launch_count(EfContext* ctx, int64_t* n) {
+  if (!ctx || !n) return EF_EINVAL;
+  *n = ctx->launches;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// named buffers
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int ef_buffer(EfContext* ctx, int32_t id, int32_t level, void** dev_ptr, size_t* bytes) {
+  if (!ctx) return EF_EINVAL;
+  const size_t n = (size_t)ctx->cfg.width * ctx->cfg.height;
+  void* p = nullptr;
+  size_t b = 0;
+  Textures& t = ctx->tex;
+  if (id < 40) {
+    switch (id) {
+      case EF_BUF_RGB: p = t.rgb; b = n * 3; break;
+      case EF_BUF_RGBA: p = t.rgba; b = n * 4; break;
+      case EF_BUF_DEPTH_RAW: p = t.depth_raw; b = n * 2; break;
+      case EF_BUF_DEPTH_FILTERED: p = t.depth_filtered; b = n * 2; break;
+      case EF_BUF_DEPTH_METRIC: p = t.depth_metric; b = n * 4; break;
+      case EF_BUF_DEPTH_METRIC_FILTERED: p = t.depth_metric_filtered; b = n * 4; break;
+      case EF_BUF_INDEX: p = t.index; b = n * 4; break;
+      case EF_BUF_VERT_CONF: p = t.vert_conf; b = n * 16; break;
+      case EF_BUF_COLOR_TIME: p = t.color_time; b = n * 16; break;
+      case EF_BUF_NORM_RAD: p = t.norm_rad; b = n * 16; break;
+      case EF_BUF_IMAGE: p = t.image; b = n * 4; break;
+      case EF_BUF_VERTEX: p = t.vertex; b = n * 16; break;
+      case EF_BUF_NORMAL: p = t.normal; b = n * 16; break;
+      case EF_BUF_TIME: p = t.time; b = n * 2; break;
+      case EF_BUF_OLD_IMAGE: p = t.old_image; b = n * 4; break;
+      case EF_BUF_OLD_VERTEX: p = t.old_vertex; b = n * 16; break;
+      case EF_BUF_OLD_NORMAL: p = t.old_normal; b = n * 16; break;
+      case EF_BUF_OLD_TIME: p = t.old_time; b = n * 2; break;
+      case EF_BUF_SYNTH_DEPTH: p = t.synth_depth; b = n * 4; break;
+      case EF_BUF_FILL_IMAGE: p = t.fill_image; b = n * 4; break;
+      case EF_BUF_FILL_VERTEX: p = t.fill_vertex; b = n * 16; break;
+      case EF_BUF_FILL_NORMAL: p = t.fill_normal; b = n * 16; break;
+      default: return EF_EINVAL;
+    }
+  } else {
+    const int which = id / 100, base = id % 100;
+    if (which < 0 || which > 1 || level < 0 || level >= NUM_PYRS) return EF_EINVAL;
+    OdomDev& od = ctx->odom[which];
+    const size_t nl = (size_t)od.rows[level] * od.cols[level];
+    switch (base) {
+      case EF_BUF_VMAP_CURR: p = od.vmap_curr[level]; b = nl * 12; break;
+      case EF_BUF_NMAP_CURR: p = od.nmap_curr[level]; b = nl * 12; break;
+      case EF_BUF_VMAP_G_PREV: p = od.vmap_g_prev[level]; b = nl * 12; break;
+      case EF_BUF_NMAP_G_PREV: p = od.nmap_g_prev[level]; b = nl * 12; break;
+      case EF_BUF_LAST_DEPTH: p = od.lastDepth[level]; b = nl * 4; break;
+      case EF_BUF_NEXT_DEPTH: p = od.nextDepth[level]; b = nl * 4; break;
+      case EF_BUF_LAST_IMAGE: p = od.lastImage[level]; b = nl; break;
+      case EF_BUF_NEXT_IMAGE: p = od.nextImage[level]; b = nl; break;
+      case EF_BUF_LAST_NEXT_IMAGE: p = od.lastNextImage[level]; b = nl; break;
+      case EF_BUF_DIDX: p = od.dIdx[level]; b = nl * 2; break;
+      case EF_BUF_DIDY: p = od.dIdy[level]; b = nl * 2; break;
+      case EF_BUF_DEPTH_TMP: p = od.depth_tmp[level]; b = nl * 2; break;
+      case EF_BUF_CORRES: p = od.corres[level]; b = nl * 16; break;
+      case EF_BUF_VMAPS_TMP: p = od.vmaps_tmp; b = n * 16; break;
+      default: return EF_EINVAL;
+    }
+  }
+  if (dev_ptr) *dev_ptr = p;
+  if (bytes) *bytes = b;
+  return 0;
+}
+
+extern "C" int ef_upload(EfContext* ctx, int32_t id, int32_t level, const void* host, size_t bytes) {
+  void* p;
+  size_t b;
+  RC(ef_buffer(ctx, id, level, &p, &b));
+  if (bytes > b || !host) return EF_EINVAL;
+  CU(cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int ef_download(EfContext* ctx, int32_t id, int32_t level, void* host, size_t bytes) {
+  void* p;
+  size_t b;
+  RC(ef_buffer(ctx, id, level, &p, &b));
+  if (bytes > b || !host) return EF_EINVAL;
+  CU(cudaMemcpyAsync(host, p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tracker stage API
+// ---------------------------------------------------------------------------------------------------------------
+static int upload_gn(EfContext* ctx, int which, size_t offset, const void* src, size_t bytes) {
+  CU(cudaMemcpyAsync((char*)ctx->odom[which].gn + offset, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+static int download_gn(EfContext* ctx, int which, GNState* g) {
+  CU(cudaMemcpyAsync(g, ctx->odom[which].gn, sizeof(GNState), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+#define WHICH_OK(w) ((w) == 0 || (w) == 1)
+
+extern "C" int ef_odom_init_icp_depth(EfContext* ctx, int which, const uint16_t* depth_dev, float cutoff) {
+  if (!ctx || !WHICH_OK(which) || !depth_dev) return EF_EINVAL;
+  return odom_init_icp_depth(ctx, which, depth_dev, cutoff);
+}
+extern "C" int ef_odom_init_icp_pred(EfContext* ctx, int which, const float* vtx4, const float* nrm4) {
+  if (!ctx || !WHICH_OK(which) || !vtx4 || !nrm4) return EF_EINVAL;
+  return odom_init_icp_pred(ctx, which, vtx4, nrm4);
+}
+extern "C" int ef_odom_init_icp_model(EfContext* ctx, int which, const float* vtx4, const float* nrm4, const double* T) {
+  if (!ctx || !WHICH_OK(which) || !vtx4 || !nrm4) return EF_EINVAL;
+  if (T) {
+    RC(upload_gn(ctx, which, offsetof(GNState, T_wc), T, sizeof(double) * 16));
+    CU(cudaStreamSynchronize(ctx->stream));  // T is caller memory
+  }
+  return odom_init_icp_model(ctx, which, vtx4, nrm4);
+}
+extern "C" int ef_odom_init_rgb(EfContext* ctx, int which, const uint8_t* rgba) {
+  if (!ctx || !WHICH_OK(which) || !rgba) return EF_EINVAL;
+  OdomDev& od = ctx->odom[which];
+  return odom_populate(ctx, which, rgba, od.nextDepth, od.nextImage, true);
+}
+extern "C" int ef_odom_init_rgb_model(EfContext* ctx, int which, const uint8_t* rgba) {
+  if (!ctx || !WHICH_OK(which) || !rgba) return EF_EINVAL;
+  OdomDev& od = ctx->odom[which];
+  return odom_populate(ctx, which, rgba, od.lastDepth, od.lastImage, true);
+}
+extern "C" int ef_odom_init_first_rgb(EfContext* ctx, int which, const uint8_t* rgba) {
+  if (!ctx || !WHICH_OK(which) || !rgba) return EF_EINVAL;
+  OdomDev& od = ctx->odom[which];
+  return odom_populate(ctx, which, rgba, nullptr, od.lastNextImage, false);
+}
+
+extern "C" int ef_odom_track(EfContext* ctx, int which, double* T_wc, int32_t rgb_only, float icp_weight, int32_t pyramid,
+                             int32_t fast_odom, int32_t so3, EfSolveTrace* trace, int32_t max_trace, int32_t* n_trace) {
+  if (!ctx || !WHICH_OK(which) || !T_wc) return EF_EINVAL;
+  RC(upload_gn(ctx, which, offsetof(GNState, T_wc), T_wc, sizeof(double) * 16));
+  CU(cudaStreamSynchronize(ctx->stream));
+  RC(odom_track_async(ctx, which, rgb_only != 0, icp_weight, pyramid != 0, fast_odom != 0, so3 != 0));
+  RC(odom_finish_async(ctx, which, 1.0f, true));
+  GNState g;
+  RC(download_gn(ctx, which, &g));
+  memcpy(T_wc, g.T_wc, sizeof(double) * 16);
+  if (n_trace) *n_trace = g.trace_n < max_trace ? g.trace_n : max_trace;
+  if (trace && max_trace > 0) {
+    const int n = g.trace_n < max_trace ? g.trace_n : max_trace;
+    CU(cudaMemcpyAsync(trace, ctx->odom[which].trace, sizeof(EfSolveTrace) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+extern "C" int ef_odom_stats(EfContext* ctx, int which, EfOdomStats* out) {
+  if (!ctx || !WHICH_OK(which) || !out) return EF_EINVAL;
+  GNState g;
+  RC(download_gn(ctx, which, &g));
+  out->lastICPError = g.lastICPError;
+  out->lastICPCount = g.lastICPCount;
+  out->lastRGBError = g.lastRGBError;
+  out->lastRGBCount = g.lastRGBCount;
+  out->lastSO3Error = g.lastSO3Error;
+  out->lastSO3Count = g.lastSO3Count;
+  memcpy(out->lastA, g.lastA, sizeof(g.lastA));
+  memcpy(out->lastb, g.lastb, sizeof(g.lastb));
+  return 0;
+}
+
+static void inv6_host(const double* m, double* o) {
+  double a[6][12];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      a[i][j] = m[i * 6 + j];
+      a[i][6 + j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < 6; ++c) {
+    int p = c;
+    for (int r = c + 1; r < 6; ++r)
+      if (fabs(a[r][c]) > fabs(a[p][c])) p = r;
+    if (p != c)
+      for (int j = 0; j < 12; ++j) {
+        double t = a[c][j];
+        a[c][j] = a[p][j];
+        a[p][j] = t;
+      }
+    double d = a[c][c];
+    for (int j = 0; j < 12; ++j) a[c][j] /= d;
+    for (int r = 0; r < 6; ++r)
+      if (r != c) {
+        double f = a[r][c];
+        if (f != 0)
+          for (int j = 0; j < 12; ++j) a[r][j] -= f * a[c][j];
+      }
+  }
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) o[i * 6 + j] = a[i][6 + j];
+}
+
+extern "C" int ef_odom_covariance(EfContext* ctx, int which, double* cov36) {
+  if (!ctx || !WHICH_OK(which) || !cov36) return EF_EINVAL;
+  GNState g;
+  RC(download_gn(ctx, which, &g));
+  inv6_host(g.lastA, cov36);  // lastA.lu().inverse(), reference RGBDOdometry.cpp:573-575
+  return 0;
+}
+
+static void unpack_se3_host(const float* h, float* A, float* b) {
+  int shift = 0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 7; ++j) {
+      float value = h[shift++];
+      if (j == 6)
+        b[i] = value;
+      else
+        A[j * 6 + i] = A[i * 6 + j] = value;
+    }
+}
+
+extern "C" int ef_icp_step_async(EfContext* ctx, int which, int level, const float* Rcurr, const float* tcurr, const float* Rprev_inv,
+                                 const float* tprev) {
+  if (!ctx || !WHICH_OK(which) || level < 0 || level >= NUM_PYRS) return EF_EINVAL;
+  if (Rcurr) {
+    float* s = (float*)ctx->pin_small;
+    memcpy(s, Rcurr, 36);
+    memcpy(s + 9, tcurr, 12);
+    memcpy(s + 12, Rprev_inv, 36);
+    memcpy(s + 21, tprev, 12);
+    CU(cudaStreamSynchronize(ctx->stream));  // staging buffer reuse
+    RC(upload_gn(ctx, which, offsetof(GNState, Rcurr), s, 36));
+    RC(upload_gn(ctx, which, offsetof(GNState, tcurr), s + 9, 12));
+    RC(upload_gn(ctx, which, offsetof(GNState, Rprev_inv), s + 12, 36));
+    RC(upload_gn(ctx, which, offsetof(GNState, tprev), s + 21, 12));
+  }
+  return launch_se3_step_raw(ctx, which, level, true, false);
+}
+
+extern "C" int ef_icp_step(EfContext* ctx, int which, int level, const float* Rcurr, const float* tcurr, const float* Rprev_inv,
+                           const float* tprev, float* A36, float* b6, float* residual2) {
+  if (!Rcurr || !tcurr || !Rprev_inv || !tprev || !A36 || !b6 || !residual2) return EF_EINVAL;
+  RC(ef_icp_step_async(ctx, which, level, Rcurr, tcurr, Rprev_inv, tprev));
+  GNState g;
+  RC(download_gn(ctx, which, &g));
+  unpack_se3_host(g.sum_icp, A36, b6);
+  residual2[0] = g.sum_icp[27];
+  residual2[1] = g.sum_icp[28];
+  return 0;
+}
+
+extern "C" int ef_rgb_residual(EfContext* ctx, int which, int level, const float* krkinv, const float* kt, int32_t* sigma_sum,
+                               int32_t* count) {
+  if (!ctx || !WHICH_OK(which) || level < 0 || level >= NUM_PYRS || !krkinv || !kt) return EF_EINVAL;
+  RC(upload_gn(ctx, which, offsetof(GNState, krkinv), krkinv, 36));
+  RC(upload_gn(ctx, which, offsetof(GNState, kt), kt, 12));
+  CU(cudaStreamSynchronize(ctx->stream));
+  RC(launch_sobel(ctx, which));
+  RC(launch_rgb_residual_raw(ctx, which, level));
+  GNState g;
+  RC(download_gn(ctx, which, &g));
+  if (count) *count = g.sum_res[0];
+  if (sigma_sum) *sigma_sum = g.sum_res[1];
+  return 0;
+}
+
+extern "C" int ef_rgb_step(EfContext* ctx, int which, int level, float sigma, float* A36, float* b6) {
+  if (!ctx || !WHICH_OK(which) || level < 0 || level >= NUM_PYRS || !A36 || !b6) return EF_EINVAL;
+  RC(upload_gn(ctx, which, offsetof(GNState, sigmaVal), &sigma, 4));
+  CU(cudaStreamSynchronize(ctx->stream));
+  RC(launch_se3_step_raw(ctx, which, level, false, true));
+  GNState g;
+  RC(download_gn(ctx, which, &g));
+  unpack_se3_host(g.sum_rgb, A36, b6);
+  return 0;
+}
+
+extern "C" int ef_so3_step(EfContext* ctx, int which, const float* image_basis, const float* kinv, const float* krlr, float* A9, float* b3,
+                           float* residual2) {
+  if (!ctx || !WHICH_OK(which) || !image_basis || !kinv || !krlr || !A9 || !b3 || !residual2) return EF_EINVAL;
+  RC(upload_gn(ctx, which, offsetof(GNState, imageBasis), image_basis, 36));
+  RC(upload_gn(ctx, which, offsetof(GNState, kinv), kinv, 36));
+  RC(upload_gn(ctx, which, offsetof(GNState, krlr), krlr, 36));
+  CU(cudaStreamSynchronize(ctx->stream));
+  RC(launch_so3_raw(ctx, which));
+  GNState g;
+  RC(download_gn(ctx, which, &g));
+  int shift = 0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = i; j < 4; ++j) {
+      float value = g.sum_so3[shift++];
+      if (j == 3)
+        b3[i] = value;
+      else
+        A9[j * 3 + i] = A9[i * 3 + j] = value;
+    }
+  residual2[0] = g.sum_so3[9];
+  residual2[1] = g.sum_so3[10];
+  return 0;
+}
+
+extern "C" int ef_preprocess_depth(EfContext* ctx, const uint16_t* raw, float cutoff, uint16_t* filtered, float* metric,
+                                   float* metric_filtered) {
+  if (!ctx || !raw) return EF_EINVAL;
+  return preprocess_depth(ctx, raw, cutoff, filtered, metric, metric_filtered);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// setters / getters
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int ef_get_pose(EfContext* ctx, double* T) {
+  if (!ctx || !T) return EF_EINVAL;
+  CU(cudaMemcpyAsync(T, (char*)ctx->odom[0].gn + offsetof(GNState, T_wc), sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(ctx->T_wc, T, sizeof(double) * 16);
+  return 0;
+}
+extern "C" int ef_set_pose(EfContext* ctx, const double* T) {
+  if (!ctx || !T) return EF_EINVAL;
+  RC(upload_gn(ctx, 0, offsetof(GNState, T_wc), T, sizeof(double) * 16));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(ctx->T_wc, T, sizeof(double) * 16);
+  return 0;
+}
+extern "C" int ef_get_tick(EfContext* ctx, int32_t* tick) {
+  if (!ctx || !tick) return EF_EINVAL;
+  *tick = ctx->tick;
+  return 0;
+}
+extern "C" int ef_set_tick(EfContext* ctx, int32_t tick) {
+  if (!ctx) return EF_EINVAL;
+  ctx->tick = tick;
+  CU(cudaMemcpyAsync(ctx->map.tick, &ctx->tick, 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int ef_set_rgb_only(EfContext* ctx, int32_t v) { if (!ctx) return EF_EINVAL; ctx->rgb_only = v != 0; return 0; }
+extern "C" int ef_set_icp_weight(EfContext* ctx, float v) { if (!ctx) return EF_EINVAL; ctx->icp_weight = v; return 0; }
+extern "C" int ef_set_pyramid(EfContext* ctx, int32_t v) { if (!ctx) return EF_EINVAL; ctx->pyramid = v != 0; return 0; }
+extern "C" int ef_set_fast_odom(EfContext* ctx, int32_t v) { if (!ctx) return EF_EINVAL; ctx->fast_odom = v != 0; return 0; }
+extern "C" int ef_set_so3(EfContext* ctx, int32_t v) { if (!ctx) return EF_EINVAL; ctx->so3 = v != 0; return 0; }
+extern "C" int ef_set_frame_to_frame_rgb(EfContext* ctx, int32_t v) { if (!ctx) return EF_EINVAL; ctx->frame_to_frame_rgb = v != 0; return 0; }
+extern "C" int ef_set_confidence_threshold(EfContext* ctx, float v) { if (!ctx) return EF_EINVAL; ctx->confidence = v; return 0; }
+extern "C" int ef_set_depth_cutoff(EfContext* ctx, float v) { if (!ctx) return EF_EINVAL; ctx->depth_cutoff = v; return 0; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// map stage API
+// ---------------------------------------------------------------------------------------------------------------
+namespace ef {
+int map_download(EfContext* ctx, const float4* a, const float4* b, const float4* c, int n, float* out);
+int map_upload(EfContext* ctx, const float* in, int n);
+void map_free_host(EfContext* ctx);
+}
+
+static int read_count(EfContext* ctx, const int* dev, int* out) {
+  CU(cudaMemcpyAsync(out, dev, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int ef_map_initialise(EfContext* ctx) {
+  if (!ctx) return EF_EINVAL;
+  return map_initialise_async(ctx);
+}
+extern "C" int ef_map_predict_indices(EfContext* ctx, const double* T, int32_t time, float max_depth, int32_t time_delta) {
+  if (!ctx) return EF_EINVAL;
+  RC(map_update_pose_async(ctx, T));
+  return map_predict_indices_async(ctx, time, max_depth, time_delta);
+}
+extern "C" int ef_map_fuse(EfContext* ctx, const double* T, int32_t time, float max_depth, float weighting) {
+  if (!ctx) return EF_EINVAL;
+  RC(map_update_pose_async(ctx, T));
+  return map_fuse_async(ctx, time, max_depth, weighting);
+}
+extern "C" int ef_map_clean(EfContext* ctx, const double* T, int32_t time, float conf_threshold, int32_t time_delta, float max_depth) {
+  if (!ctx) return EF_EINVAL;
+  RC(map_update_pose_async(ctx, T));
+  return map_clean_async(ctx, time, conf_threshold, time_delta, max_depth);
+}
+extern "C" int ef_map_raycast(EfContext* ctx, const double* T, float max_depth, float conf_threshold, int32_t time, int32_t max_time,
+                              int32_t time_delta, int32_t mode) {
+  if (!ctx || mode < 0 || mode > 2) return EF_EINVAL;
+  RC(map_update_pose_async(ctx, T));
+  return map_raycast_async(ctx, max_depth, conf_threshold, time, max_time, time_delta, mode, false);
+}
+extern "C" int ef_map_fill_in(EfContext* ctx, int32_t pass_geom, int32_t pass_img) {
+  if (!ctx) return EF_EINVAL;
+  return map_fill_in_async(ctx, pass_geom != 0, pass_img != 0);
+}
+extern "C" int ef_dense_enough(EfContext* ctx, int32_t* out) {
+  if (!ctx || !out) return EF_EINVAL;
+  RC(map_dense_enough_async(ctx));
+  return read_count(ctx, ctx->map.dense_flag, out);
+}
+extern "C" int ef_map_count(EfContext* ctx, int32_t* count) {
+  if (!ctx || !count) return EF_EINVAL;
+  RC(read_count(ctx, ctx->map.count, count));
+  ctx->host_count = *count;
+  return 0;
+}
+extern "C" int ef_map_download(EfContext* ctx, float* out12, int32_t max_surfels, int32_t* count) {
+  if (!ctx || !out12) return EF_EINVAL;
+  int n = 0;
+  RC(read_count(ctx, ctx->map.count, &n));
+  ctx->host_count = n;
+  if (count) *count = n;
+  if (n > max_surfels) n = max_surfels;
+  return map_download(ctx, ctx->map.pos_conf, ctx->map.color_time, ctx->map.norm_rad, n, out12);
+}
+extern "C" int ef_map_download_new(EfContext* ctx, float* out12, int32_t max_surfels, int32_t* count) {
+  if (!ctx || !out12) return EF_EINVAL;
+  int n = 0;
+  RC(read_count(ctx, ctx->map.new_count, &n));
+  if (count) *count = n;
+  if (n > max_surfels) n = max_surfels;
+  return map_download(ctx, ctx->map.new_pos, ctx->map.new_col, ctx->map.new_nr, n, out12);
+}
+extern "C" int ef_map_upload(EfContext* ctx, const float* in12, int32_t count) {
+  if (!ctx || (!in12 && count > 0) || count < 0) return EF_EINVAL;
+  return map_upload(ctx, in12, count);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// whole frame
+// ---------------------------------------------------------------------------------------------------------------
+// ElasticFusion::predict, reference Core/ElasticFusion.cpp:621-653 (lost == false, lastFrameRecovery == false)
+static int predict_async(EfContext* ctx) {
+  RC(map_raycast_async(ctx, ctx->max_depth_processed, ctx->confidence, ctx->tick, ctx->tick, ctx->cfg.time_delta, 0, false));
+  return map_fill_in_async(ctx, false, ctx->frame_to_frame_rgb);
+}
+
+extern "C" int ef_predict(EfContext* ctx) {
+  if (!ctx) return EF_EINVAL;
+  RC(map_update_pose_async(ctx, nullptr));
+  return predict_async(ctx);
+}
+
+extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, const uint16_t* depth_dev, int64_t timestamp,
+                                       float weight_multiplier, const double* in_T_wc) {
+  (void)timestamp;
+  if (!ctx || !rgb_dev || !depth_dev) return EF_EINVAL;
+  const size_t n = (size_t)ctx->cfg.width * ctx->cfg.height;
+  Textures& t = ctx->tex;
+  // texture uploads, reference ElasticFusion.cpp:278-280
+  if (rgb_dev != t.rgb) CU(cudaMemcpyAsync(t.rgb, rgb_dev, n * 3, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (depth_dev != t.depth_raw) CU(cudaMemcpyAsync(t.depth_raw, depth_dev, n * 2, cudaMemcpyDeviceToDevice, ctx->stream));
+  RC(rgb_to_rgba(ctx, t.rgb, t.rgba));
+  // filterDepth + metriciseDepth, ElasticFusion.cpp:284-285
+  RC(preprocess_depth(ctx, t.depth_raw, ctx->depth_cutoff, t.depth_filtered, t.depth_metric, t.depth_metric_filtered));
+
+  if (ctx->tick == 1) {
+    // ElasticFusion.cpp:290-296
+    RC(map_initialise_async(ctx));
+    RC(odom_populate(ctx, 0, t.rgba, nullptr, ctx->odom[0].lastNextImage, false));
+  } else {
+    OdomDev& od = ctx->odom[0];
+    if (!in_T_wc) {
+      // ElasticFusion.cpp:302-323. The fill-in decision stays on the device: both candidate inputs are handed to the
+      // pyramid kernels together with the flag.
+      RC(map_dense_enough_async(ctx));
+      RC(map_select_model_inputs(ctx, nullptr, nullptr, nullptr));
+      RC(odom_init_icp_depth(ctx, 0, t.depth_filtered, ctx->max_depth_processed));
+      RC(odom_populate(ctx, 0, t.rgba, od.nextDepth, od.nextImage, true));
+      RC(odom_track_async(ctx, 0, ctx->rgb_only, ctx->icp_weight, ctx->pyramid, ctx->fast_odom, ctx->so3));
+      RC(odom_finish_async(ctx, 0, weight_multiplier, true));
+    } else {
+      CU(cudaStreamSynchronize(ctx->stream));
+      memcpy((char*)ctx->pin_small + 4096, in_T_wc, sizeof(double) * 16);
+      CU(cudaMemcpyAsync((char*)ctx->dev_small + 4096, (char*)ctx->pin_small + 4096, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
+      RC(odom_set_pose_async(ctx, 0, (const double*)((char*)ctx->dev_small + 4096)));
+      RC(odom_finish_async(ctx, 0, weight_multiplier, false));
+    }
+    RC(map_update_pose_async(ctx, nullptr));
+    if (!ctx->cfg.skip_mid_predict) RC(predict_async(ctx));  // ElasticFusion.cpp:387 (only loop closure reads it)
+    if (!ctx->rgb_only) {
+      // ElasticFusion.cpp:536-585
+      RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta));
+      RC(map_fuse_async(ctx, ctx->tick, ctx->max_depth_processed, -1.0f));
+      RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta));
+      RC(map_clean_async(ctx, ctx->tick, ctx->confidence, ctx->cfg.time_delta, ctx->max_depth_processed));
+    }
+  }
+  RC(map_update_pose_async(ctx, nullptr));
+  RC(predict_async(ctx));  // ElasticFusion.cpp:599
+  ctx->tick++;
+  return 0;
+}
+
+extern "C" int ef_process_frame(EfContext* ctx, const uint8_t* rgb, const uint16_t* depth, int64_t timestamp, float weight_multiplier,
+                                const double* in_T_wc) {
+  if (!ctx || !rgb || !depth) return EF_EINVAL;
+  const size_t n = (size_t)ctx->cfg.width * ctx->cfg.height;
+  // the staging buffers may still be in flight from the previous frame
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(ctx->pin_rgb, rgb, n * 3);
+  memcpy(ctx->pin_depth, depth, n * 2);
+  CU(cudaMemcpyAsync(ctx->tex.rgb, ctx->pin_rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->tex.depth_raw, ctx->pin_depth, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+  RC(ef_process_frame_device(ctx, ctx->tex.rgb, ctx->tex.depth_raw, timestamp, weight_multiplier, in_T_wc));
+  // results the caller can observe (get_T_wc, counts) are final on return
+  char* s = (char*)ctx->pin_small + 8192;
+  CU(cudaMemcpyAsync(s, (char*)ctx->odom[0].gn + offsetof(GNState, T_wc), sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(s + 128, ctx->map.count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(ctx->T_wc, s, sizeof(double) * 16);
+  ctx->host_count = *(int*)(s + 128);
+  return 0;
+}

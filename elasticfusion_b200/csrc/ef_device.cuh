@@ -1,0 +1,104 @@
+// Device-side helpers shared by the tracking / mapping kernels.
+//
+// All translation units are compiled with --fmad=false: every +,-,*,/ and sqrtf below is a single IEEE-754
+// operation in the written order, so per-pixel results are bit-reproducible against a plain C restatement of the
+// same formulas (the parity tests rely on this; the kernels are HBM/latency bound, not FMA bound).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ef {
+
+struct f3 {
+  float x, y, z;
+};
+struct m33 {
+  f3 r[3];
+};
+
+__host__ __device__ __forceinline__ f3 mk3(float x, float y, float z) {
+  f3 v;
+  v.x = x;
+  v.y = y;
+  v.z = z;
+  return v;
+}
+__host__ __device__ __forceinline__ f3 operator-(const f3& a, const f3& b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__host__ __device__ __forceinline__ f3 operator+(const f3& a, const f3& b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__host__ __device__ __forceinline__ f3 operator*(const f3& a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__host__ __device__ __forceinline__ f3 cross(const f3& a, const f3& b) {
+  return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__host__ __device__ __forceinline__ float dot(const f3& a, const f3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float norm(const f3& a) { return sqrtf(dot(a, a)); }
+// IEEE 1/sqrt (the reference's rsqrtf is the 2-ulp MUFU approximation; see DESIGN.md "numerics")
+__device__ __forceinline__ f3 normalized(const f3& a) {
+  const float rn = 1.0f / sqrtf(dot(a, a));
+  return mk3(a.x * rn, a.y * rn, a.z * rn);
+}
+__host__ __device__ __forceinline__ f3 mul(const m33& m, const f3& a) { return mk3(dot(m.r[0], a), dot(m.r[1], a), dot(m.r[2], a)); }
+__host__ __device__ __forceinline__ m33 load_m33(const float* R) {
+  m33 m;
+  m.r[0] = mk3(R[0], R[1], R[2]);
+  m.r[1] = mk3(R[3], R[4], R[5]);
+  m.r[2] = mk3(R[6], R[7], R[8]);
+  return m;
+}
+
+__device__ __forceinline__ float qnan() { return __int_as_float(0x7fffffff); }
+__device__ __forceinline__ float gmin(float x, float y) { return (y < x) ? y : x; }  // GLSL min
+__device__ __forceinline__ float gmax(float x, float y) { return (x < y) ? y : x; }  // GLSL max
+
+// 4x4 row-major float pose applied to a point / a direction, accumulation order ((m0*x + m1*y) + m2*z) + m3
+__device__ __forceinline__ f3 xform(const float* m, const f3& v) {
+  return mk3(((m[0] * v.x + m[1] * v.y) + m[2] * v.z) + m[3], ((m[4] * v.x + m[5] * v.y) + m[6] * v.z) + m[7],
+             ((m[8] * v.x + m[9] * v.y) + m[10] * v.z) + m[11]);
+}
+__device__ __forceinline__ f3 rot(const float* m, const f3& v) {
+  return mk3((m[0] * v.x + m[1] * v.y) + m[2] * v.z, (m[4] * v.x + m[5] * v.y) + m[6] * v.z,
+             (m[8] * v.x + m[9] * v.y) + m[10] * v.z);
+}
+
+// warp / block sum of N floats held per thread; result valid in thread 0 of the block.
+template <int N, int THREADS>
+__device__ __forceinline__ void block_reduce_sum(float (&v)[N], float* smem /* N * (THREADS/32) floats */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    float x = v[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+    v[k] = x;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) smem[wid * N + k] = v[k];
+  }
+  __syncthreads();
+  if (wid == 0) {
+    constexpr int NW = THREADS / 32;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      float x = (lane < NW) ? smem[lane * N + k] : 0.f;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+      v[k] = x;
+    }
+  }
+}
+
+// "last block done" ticket: returns true in every thread of the block that arrives last.
+__device__ __forceinline__ bool last_block_done(unsigned int* counter) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+}  // namespace ef

@@ -1,0 +1,163 @@
+// Internal context layout of libefusion.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/efusion_b200.h"
+
+namespace ef {
+
+constexpr int NUM_PYRS = 3;          // RGBDOdometry::NUM_PYRS (reference Core/Utils/RGBDOdometry.h:114)
+constexpr int RED_THREADS = 256;     // threads per reduction CTA
+constexpr int MAX_RED_BLOCKS = 1184; // 148 SMs x 8 resident 256-thread CTAs
+constexpr int PARTIAL_STRIDE = 64;   // floats per CTA partial: [0,29) geometric system, [32,61) photometric system
+constexpr int MAX_TRACE = 48;
+
+// reference DataTerm (Core/Cuda/types.cuh:79-84): 16 bytes, bool widened to int32
+struct DataTerm {
+  short zero_x, zero_y;
+  short one_x, one_y;
+  float diff;
+  int valid;
+};
+
+// Device-resident state of one getIncrementalTransformation call: everything the reference keeps in host
+// locals between kernel launches (RGBDOdometry.cpp:259-571) lives here so no iteration needs the host.
+struct GNState {
+  double T_wc[16];
+  float lastICPError, lastICPCount, lastRGBError, lastRGBCount, lastSO3Error, lastSO3Count;
+  double lastA[36], lastb[6];
+
+  float Rprev[9], tprev[3], Rprev_inv[9];
+  float Rcurr[9], tcurr[3];
+  double resultRt[16];
+  double resultR[9], lastResultR[9];
+  float R_lr[9];
+  float so3_lastError, so3_lastCount;
+  int so3_done;
+  int break_level;  // rgbOnly early exit of one pyramid level's loop (-1: none)
+
+  float krkinv[9], kt[3];                  // inputs of the next photometric residual pass
+  float imageBasis[9], kinv[9], krlr[9];   // inputs of the next SO3 pass
+  float sigmaVal;
+  int rgbSize, sigma;
+
+  float sum_icp[32], sum_rgb[32], sum_so3[12];  // last reduced systems (reference JtJJtrSE3 / JtJJtrSO3 order)
+  int sum_res[2];                               // last {count, sigma} of the residual pass
+
+  int rgbOnly, icp, rgb, so3;
+  float icpWeight;
+  float fx, fy, cx, cy;
+  int trace_n;
+  float weighting;  // velocity weighting for fusion (ElasticFusion.cpp:369-383)
+};
+
+// pose matrices consumed by the map kernels (float, as the reference's shader uniforms)
+struct MapPose {
+  float pose[16];   // T_wc
+  float t_inv[16];  // T_cw
+};
+
+struct OdomDev {
+  int width, height;
+  int rows[NUM_PYRS], cols[NUM_PYRS];
+  float distThres, angleThres;
+  float sobelScale, maxDepthDeltaRGB, maxDepthRGB;
+  float minGrad[NUM_PYRS];
+  float minScale[NUM_PYRS];  // (minGrad/sobelScale)^2, reference RGBDOdometry.cpp:425
+
+  uint16_t* depth_tmp[NUM_PYRS];
+  float* vmaps_tmp;  // float4 AoS, level 0
+  float *vmap_g_prev[NUM_PYRS], *nmap_g_prev[NUM_PYRS], *vmap_curr[NUM_PYRS], *nmap_curr[NUM_PYRS];
+  float *lastDepth[NUM_PYRS], *nextDepth[NUM_PYRS];
+  uint8_t *lastImage[NUM_PYRS], *nextImage[NUM_PYRS], *lastNextImage[NUM_PYRS];
+  int16_t *dIdx[NUM_PYRS], *dIdy[NUM_PYRS];
+  DataTerm* corres[NUM_PYRS];
+
+  GNState* gn;
+  float* partials;        // MAX_RED_BLOCKS * PARTIAL_STRIDE
+  int* partials_i;        // MAX_RED_BLOCKS * 2
+  unsigned int* counter;  // last-block ticket
+  EfSolveTrace* trace;    // MAX_TRACE records (device)
+};
+
+struct MapDev {
+  int rows, cols;
+  float cx, cy, fx, fy;
+  int capacity;
+  // surfel map, SoA of float4: pos+conf | colour,unused,initTime,lastTime | normal+radius
+  float4 *pos_conf, *color_time, *norm_rad;
+  int* count;             // device-resident surfel count
+  // unstable surfels of the current frame (reference newUnstableVbo)
+  float4 *new_pos, *new_col, *new_nr;
+  int* new_count;
+  // per-pixel association scratch for fuse
+  uint32_t* assoc_id;     // W*H: matched surfel id (or 0xffffffff none / 0xfffffffe new)
+  uint32_t* pending;      // capacity: lowest draw index that chose this surfel (0xffffffff idle)
+  // z-buffers
+  unsigned long long* zbuf;  // W*H
+  // scan scratch
+  int* scan_tile_state;   // decoupled look-back
+  unsigned int* scan_counter;
+  uint8_t* flags;         // capacity + W*H
+  // first-frame feedback buffers
+  float4 *fb_raw[3], *fb_filt[3];
+  int* fb_count;          // [2]
+  MapPose* pose;          // device
+  int* dense_flag;        // device: 1 if the predicted image is dense enough (no fill-in)
+  int* tick;              // device-resident tick
+};
+
+struct Textures {
+  uint8_t* rgb;      // W*H*3
+  uint8_t* rgba;     // W*H*4
+  uint16_t* depth_raw;
+  uint16_t* depth_filtered;
+  float* depth_metric;
+  float* depth_metric_filtered;
+  // IndexMap
+  uint32_t* index;
+  float4 *vert_conf, *color_time, *norm_rad;
+  uchar4 *image, *old_image, *fill_image;
+  float4 *vertex, *normal, *old_vertex, *old_normal, *fill_vertex, *fill_normal;
+  uint16_t *time, *old_time;
+  float* synth_depth;
+};
+
+}  // namespace ef
+
+struct EfContext {
+  EfConfig cfg;
+  int device;
+  int num_sms;
+  cudaStream_t stream;
+  bool own_stream;
+  int64_t launches;
+
+  ef::OdomDev odom[2];
+  ef::MapDev map;
+  ef::Textures tex;
+
+  // host mirrors
+  int tick;
+  double T_wc[16];
+  bool rgb_only;
+  float icp_weight;
+  bool pyramid, fast_odom, so3, frame_to_frame_rgb;
+  float confidence, depth_cutoff, max_depth_processed;
+  int host_count;  // last count read back
+
+  // pinned staging
+  uint8_t* pin_rgb;
+  uint16_t* pin_depth;
+  void* pin_small;   // results read-back
+  void* dev_small;   // upload area for per-call parameters
+  void* map_host;    // host-side bookkeeping of the surfel buffers (ef_map.cu)
+};
+
+// launch bookkeeping
+#define EF_LAUNCH(ctx, kernel, grid, block, smem, ...)                    \
+  do {                                                                     \
+    kernel<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__);             \
+    (ctx)->launches++;                                                     \
+  } while (0)

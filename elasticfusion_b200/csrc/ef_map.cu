@@ -1,0 +1,1065 @@
+// Mapping half of the hot path: the reference's OpenGL/GLSL surfel pipeline (Core/GlobalModel.cpp, Core/IndexMap.cpp,
+// Core/Shaders/*.{vert,geom,frag}) rewritten as CUDA kernels over a device-resident surfel structure-of-arrays.
+// No OpenGL, no interop: rasterisation is an atomicMin z-buffer on packed (depth24 << 32 | primitive id) keys, which
+// reproduces GL_LESS with "earlier primitive wins on ties"; transform feedback is an order-preserving compaction
+// driven by a single-pass decoupled look-back scan; the per-surfel "update map" render target (3 x 3072^2 RGBA32F,
+// cleared every frame, GlobalModel.cpp:375-378) becomes a 4-byte-per-surfel winner slot touched only by matches.
+//
+// GL semantics encoded: nearest sampling texel = clamp(floor(coord*size)); 1-px points at
+// floor(window xy), clipped by centre; point sprites cover pixel centres in [xw - s/2, xw + s/2), size clamped to
+// [1, 2047]; window depth round(z * (2^24-1)); fragments at depth 1.0 fail GL_LESS against the clear value.
+#include <float.h>
+#include <stddef.h>
+
+#include "ef_device.cuh"
+#include "ef_dmath.cuh"
+#include "ef_internal.h"
+
+using namespace ef;
+
+namespace ef {
+template <typename T>
+cudaError_t ctx_alloc(EfContext* ctx, T** p, size_t n);
+}
+
+namespace {
+
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+struct Cam {
+  float cx, cy, fx, fy;
+};
+
+__device__ __forceinline__ int texel(float coord, int n) {
+  int i = (int)floorf(coord * (float)n);
+  return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+// host-side uv buffer value of the reference (GlobalModel.cpp:109-117): (float)i/(float)n + 1.0/(2*(float)n), stored as float
+__device__ __forceinline__ float uv_coord(int i, int n) { return (float)((double)((float)i / (float)n) + 1.0 / (double)(2 * (float)n)); }
+
+// color.glsl:19-34
+__device__ __forceinline__ float encode_color_bytes(unsigned r, unsigned g, unsigned b) {
+  int rgb = (int)r;
+  rgb = (rgb << 8) + (int)g;
+  rgb = (rgb << 8) + (int)b;
+  return (float)rgb;
+}
+__device__ __forceinline__ float encode_color(const f3& c) {
+  int rgb = (int)roundf(c.x * 255.0f);
+  rgb = (rgb << 8) + (int)roundf(c.y * 255.0f);
+  rgb = (rgb << 8) + (int)roundf(c.z * 255.0f);
+  return (float)rgb;
+}
+__device__ __forceinline__ f3 decode_color(float c) {
+  const int ci = (int)c;
+  return mk3((float)(ci >> 16 & 0xFF) / 255.0f, (float)(ci >> 8 & 0xFF) / 255.0f, (float)(ci & 0xFF) / 255.0f);
+}
+// surfels.glsl:19-46
+__device__ __forceinline__ float get_radius(float depth, float norm_z, float inv_fx, float inv_fy) {
+  const float meanFocal = ((1.0f / fabsf(inv_fx)) + (1.0f / fabsf(inv_fy))) / 2.0f;
+  const float sqrt2 = 1.41421356237f;
+  const float radius = (depth / meanFocal) * sqrt2;
+  float radius_n = radius / fabsf(norm_z);
+  radius_n = gmin(2.0f * radius, radius_n);
+  return radius_n;
+}
+__device__ __forceinline__ float confidence(float x, float y, float weighting, float cx, float cy) {
+  const float maxRadDist = 400;
+  const float twoSigmaSquared = 0.72f;
+  const float px = x - cx, py = y - cy;
+  const float radialDist = sqrtf(px * px + py * py) / maxRadDist;
+  return expf((-(radialDist * radialDist) / twoSigmaSquared)) * weighting;
+}
+// geometry.glsl:21-40 (float depth sampler, clamp-to-edge)
+__device__ __forceinline__ f3 vertex_f(const float* depth, int rows, int cols, int ix, int iy, float x, float y, const Cam& c, float ifx,
+                                       float ify) {
+  ix = ix < 0 ? 0 : (ix >= cols ? cols - 1 : ix);
+  iy = iy < 0 ? 0 : (iy >= rows ? rows - 1 : iy);
+  const float z = depth[(size_t)iy * cols + ix];
+  return mk3((x - c.cx) * z * ifx, (y - c.cy) * z * ify, z);
+}
+__device__ __forceinline__ f3 normal_central(const float* depth, int rows, int cols, int ix, int iy, float x, float y, const f3& vPos,
+                                             const Cam& c, float ifx, float ify) {
+  const f3 xf = vertex_f(depth, rows, cols, ix + 1, iy, x + 1, y, c, ifx, ify);
+  const f3 xb = vertex_f(depth, rows, cols, ix - 1, iy, x - 1, y, c, ifx, ify);
+  const f3 yf = vertex_f(depth, rows, cols, ix, iy + 1, x, y + 1, c, ifx, ify);
+  const f3 yb = vertex_f(depth, rows, cols, ix, iy - 1, x, y - 1, c, ifx, ify);
+  const f3 del_x = mk3((xb.x + vPos.x) / 2 - (xf.x + vPos.x) / 2, (xb.y + vPos.y) / 2 - (xf.y + vPos.y) / 2,
+                       (xb.z + vPos.z) / 2 - (xf.z + vPos.z) / 2);
+  const f3 del_y = mk3((yb.x + vPos.x) / 2 - (yf.x + vPos.x) / 2, (yb.y + vPos.y) / 2 - (yf.y + vPos.y) / 2,
+                       (yb.z + vPos.z) / 2 - (yf.z + vPos.z) / 2);
+  return normalized(cross(del_x, del_y));
+}
+// geometry.glsl:42-60 (ushort mm sampler, integer pixel coords)
+__device__ __forceinline__ f3 vertex_u(const uint16_t* depth, int rows, int cols, int ix, int iy, int x, int y, const Cam& c, float ifx,
+                                       float ify) {
+  ix = ix < 0 ? 0 : (ix >= cols ? cols - 1 : ix);
+  iy = iy < 0 ? 0 : (iy >= rows ? rows - 1 : iy);
+  const float z = (float)depth[(size_t)iy * cols + ix] / 1000.0f;
+  return mk3(((float)x - c.cx) * z * ifx, ((float)y - c.cy) * z * ify, z);
+}
+__device__ __forceinline__ unsigned int depth24(float zw) {
+  if (!(zw > 0.f)) zw = 0.f;
+  if (zw > 1.f) zw = 1.f;
+  return (unsigned int)rintf(zw * 16777215.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pose upload: T_wc (double) -> float pose and float inverse, as the shader uniforms (GlobalModel.cpp:405,562)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_update_pose(MapPose* mp, const double* T) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double inv[16];
+  efm::se3_inverse(T, inv);
+  for (int k = 0; k < 16; ++k) {
+    mp->pose[k] = (float)T[k];
+    mp->t_inv[k] = (float)inv[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// single-pass exclusive scan of byte flags (decoupled look-back), persistent CTAs, device-resident length
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_flags(const uint8_t* __restrict__ flags, const int* __restrict__ n_a,
+                                                              const int* __restrict__ n_b, int* __restrict__ offsets,
+                                                              unsigned long long* state, unsigned int* counter, int* total_out) {
+  const int n = (n_a ? *n_a : 0) + (n_b ? *n_b : 0);
+  const int num_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  __shared__ int s_warp[SCAN_THREADS / 32];
+  __shared__ int s_tile, s_prefix;
+  if (num_tiles == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && total_out) *total_out = 0;
+    return;
+  }
+  while (true) {
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(counter, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= num_tiles) return;
+    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+      const int i = base + k;
+      v[k] = (i < n) ? (flags[i] ? 1 : 0) : 0;
+      sum += v[k];
+    }
+    // block exclusive scan of per-thread sums
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int w = (lane < SCAN_THREADS / 32) ? s_warp[lane] : 0;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, off);
+        if (lane >= off) w += t;
+      }
+      if (lane < SCAN_THREADS / 32) s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const int warp_excl = wid ? s_warp[wid - 1] : 0;
+    const int thread_excl = warp_excl + incl - sum;
+    const int aggregate = s_warp[SCAN_THREADS / 32 - 1];
+    // publish aggregate, look back for the exclusive prefix
+    if (threadIdx.x == 0) {
+      int prefix = 0;
+      if (tile == 0) {
+        atomicExch(&state[0], (2ull << 32) | (unsigned int)aggregate);
+      } else {
+        atomicExch(&state[tile], (1ull << 32) | (unsigned int)aggregate);
+        int look = tile - 1;
+        while (true) {
+          const unsigned long long s = atomicAdd(&state[look], 0ull);
+          const unsigned int st = (unsigned int)(s >> 32);
+          if (st == 0) continue;
+          prefix += (int)(unsigned int)(s & 0xffffffffull);
+          if (st == 2) break;
+          --look;
+        }
+        atomicExch(&state[tile], (2ull << 32) | (unsigned int)(prefix + aggregate));
+      }
+      s_prefix = prefix;
+      if (tile == num_tiles - 1 && total_out) *total_out = prefix + aggregate;
+    }
+    __syncthreads();
+    int run = s_prefix + thread_excl;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+      const int i = base + k;
+      if (i < n) offsets[i] = run;
+      run += v[k];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// first frame: vertex_feedback.vert/.geom + init_unstable.vert (FeedbackBuffer.cpp:81-138, GlobalModel.cpp:229-284)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_feedback_flags(const float* __restrict__ depth_raw, const float* __restrict__ depth_filt, int rows, int cols,
+                                 float max_depth, uint8_t* __restrict__ f_raw, uint8_t* __restrict__ f_filt) {
+  const int n = rows * cols;
+  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
+    const int i = d / rows, j = d - i * rows;  // draw order: x-major
+    const float zr = depth_raw[(size_t)j * cols + i], zf = depth_filt[(size_t)j * cols + i];
+    f_raw[d] = !(zr <= 0 || zr > max_depth);
+    f_filt[d] = !(zf <= 0 || zf > max_depth);
+  }
+}
+
+__global__ void k_init_scatter(const uint8_t* __restrict__ rgb, const float* __restrict__ depth_raw, const float* __restrict__ depth_filt,
+                               int rows, int cols, Cam c, int time, const uint8_t* __restrict__ f_raw, const uint8_t* __restrict__ f_filt,
+                               const int* __restrict__ off_raw, const int* __restrict__ off_filt, const int* __restrict__ raw_total,
+                               int capacity, float4* __restrict__ pos_conf, float4* __restrict__ color_time, float4* __restrict__ norm_rad,
+                               int* __restrict__ count) {
+  const float ifx = 1.0f / c.fx, ify = 1.0f / c.fy;
+  const int n = rows * cols;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *count = min(*raw_total, capacity);
+  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
+    const int i = d / rows, j = d - i * rows;
+    const float tcx = uv_coord(i, cols), tcy = uv_coord(j, rows);
+    const float x = tcx * (float)cols, y = tcy * (float)rows;
+    if (f_raw[d]) {
+      const int k = off_raw[d];
+      if (k < capacity) {
+        const f3 v = vertex_f(depth_raw, rows, cols, i, j, x, y, c, ifx, ify);
+        const uint8_t* px = rgb + ((size_t)j * cols + i) * 3;
+        pos_conf[k] = make_float4(v.x, v.y, v.z, confidence(x, y, 1.0f, c.cx, c.cy));
+        // init_unstable.vert: colour.y = 0 (unused), colour.z = 1 (init time); colour.w = time from vertex_feedback.vert
+        color_time[k] = make_float4(encode_color_bytes(px[0], px[1], px[2]), 0.f, 1.f, (float)time);
+      }
+    }
+    if (f_filt[d]) {
+      const int k = off_filt[d];
+      if (k < capacity) {
+        const f3 v = vertex_f(depth_filt, rows, cols, i, j, x, y, c, ifx, ify);
+        const f3 nrm = normal_central(depth_filt, rows, cols, i, j, x, y, v, c, ifx, ify);
+        norm_rad[k] = make_float4(nrm.x, nrm.y, nrm.z, get_radius(v.z, nrm.z, ifx, ify));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// index map: index_map.vert/.frag (IndexMap.cpp:190-258)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_index_scatter(const float4* __restrict__ pos_conf, const float4* __restrict__ color_time, const int* __restrict__ count,
+                                const MapPose* __restrict__ mp, int time, float max_depth, int time_delta, int rows, int cols, Cam c,
+                                unsigned long long* __restrict__ zbuf) {
+  const int n = *count;
+  const float fcols = (float)cols, frows = (float)rows;
+  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+    const float4 pc = pos_conf[id];
+    const f3 h = xform(mp->t_inv, mk3(pc.x, pc.y, pc.z));
+    if (h.z > max_depth || h.z < 0) continue;
+    if ((float)time - color_time[id].w > (float)time_delta) continue;
+    const float xn = ((((c.fx * h.x) / h.z) + c.cx) - (fcols * 0.5f)) / (fcols * 0.5f);
+    const float yn = ((((c.fy * h.y) / h.z) + c.cy) - (frows * 0.5f)) / (frows * 0.5f);
+    const float zn = h.z / max_depth;
+    if (!(xn >= -1.f && xn <= 1.f && yn >= -1.f && yn <= 1.f && zn >= -1.f && zn <= 1.f)) continue;
+    const float xw = (xn + 1.0f) * (fcols * 0.5f);
+    const float yw = (yn + 1.0f) * (frows * 0.5f);
+    const int px = (int)floorf(xw), py = (int)floorf(yw);
+    if (px < 0 || py < 0 || px >= cols || py >= rows) continue;
+    const unsigned int d24 = depth24(0.5f * zn + 0.5f);
+    if (d24 >= 16777215u) continue;
+    atomicMin(&zbuf[(size_t)py * cols + px], ((unsigned long long)d24 << 32) | (unsigned int)id);
+  }
+}
+
+__global__ void k_index_resolve(const float4* __restrict__ pos_conf, const float4* __restrict__ color_time, const float4* __restrict__ norm_rad,
+                                const MapPose* __restrict__ mp, int n_px, const unsigned long long* __restrict__ zbuf,
+                                uint32_t* __restrict__ index, float4* __restrict__ vert_conf, float4* __restrict__ col_time,
+                                float4* __restrict__ nrm_rad) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_px; p += gridDim.x * blockDim.x) {
+    const unsigned long long key = zbuf[p];
+    if (key == kEmptyKey) {
+      index[p] = 0;
+      vert_conf[p] = col_time[p] = nrm_rad[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    const uint32_t id = (uint32_t)(key & 0xffffffffull);
+    const float4 pc = pos_conf[id];
+    const float4 nr = norm_rad[id];
+    const f3 h = xform(mp->t_inv, mk3(pc.x, pc.y, pc.z));
+    const f3 nn = normalized(rot(mp->t_inv, mk3(nr.x, nr.y, nr.z)));
+    index[p] = id;
+    vert_conf[p] = make_float4(h.x, h.y, h.z, pc.w);
+    col_time[p] = color_time[id];
+    nrm_rad[p] = make_float4(nn.x, nn.y, nn.z, nr.w);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fuse: data.vert/.geom/.frag + update.vert (GlobalModel.cpp:356-525)
+// ---------------------------------------------------------------------------------------------------------------
+struct FuseArgs {
+  const uint8_t* rgb;
+  const float* depth_raw;
+  const float* depth_filt;
+  const uint32_t* index;
+  const float4* vert_conf;
+  const float4* norm_rad;
+  int rows, cols;
+  Cam c;
+  int time;
+  float max_depth;
+};
+
+// measurement surfel of pixel (i,j) as data.vert builds it; returns false if the pixel takes no part this frame
+__device__ __forceinline__ bool fuse_active(const FuseArgs& a, int i, int j, float& tcx, float& tcy, float& x, float& y, f3& vPosLocal) {
+  tcx = uv_coord(i, a.cols);
+  tcy = uv_coord(j, a.rows);
+  x = tcx * (float)a.cols;
+  y = tcy * (float)a.rows;
+  const float ftime = (float)a.time;
+  if (!((int)x % 2 == (int)ftime % 2 && (int)y % 2 == (int)ftime % 2)) return false;
+  const float ifx = (float)(1.0 / (double)a.c.fx), ify = (float)(1.0 / (double)a.c.fy);
+  vPosLocal = vertex_f(a.depth_raw, a.rows, a.cols, i, j, x, y, a.c, ifx, ify);
+  const int il = max(i - 1, 0), ir = min(i + 1, a.cols - 1), ju = max(j - 1, 0), jd = min(j + 1, a.rows - 1);
+  if (a.depth_raw[(size_t)j * a.cols + il] == 0 || a.depth_raw[(size_t)ju * a.cols + i] == 0 ||
+      a.depth_raw[(size_t)j * a.cols + ir] == 0 || a.depth_raw[(size_t)jd * a.cols + i] == 0)
+    return false;
+  return (vPosLocal.z > 0 && vPosLocal.z <= a.max_depth);
+}
+
+constexpr uint32_t ASSOC_NONE = 0xffffffffu, ASSOC_NEW = 0xfffffffeu;
+
+__global__ void k_fuse_associate(FuseArgs a, const int* __restrict__ count, uint32_t* __restrict__ assoc, uint32_t* __restrict__ pending,
+                                 uint8_t* __restrict__ new_flags) {
+  const int n = a.rows * a.cols;
+  const int cnt = *count;
+  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
+    const int i = d / a.rows, j = d - i * a.rows;
+    float tcx, tcy, x, y;
+    f3 vPosLocal;
+    uint32_t res = ASSOC_NONE;
+    uint8_t is_new = 0;
+    if (fuse_active(a, i, j, tcx, tcy, x, y, vPosLocal)) {
+      const float ifx = (float)(1.0 / (double)a.c.fx), ify = (float)(1.0 / (double)a.c.fy);
+      const f3 vPos_f = vertex_f(a.depth_filt, a.rows, a.cols, i, j, x, y, a.c, ifx, ify);
+      const f3 vNormLocal = normal_central(a.depth_filt, a.rows, a.cols, i, j, x, y, vPos_f, a.c, ifx, ify);
+      const float fcols = (float)a.cols, frows = (float)a.rows;
+      int counter = 0;
+      uint32_t best = 0;
+      const float scale = 1.0f;  // IndexMap::FACTOR
+      const float indexXStep = (1.0f / (fcols * scale)) * 0.5f;
+      const float indexYStep = (1.0f / (frows * scale)) * 0.5f;
+      float bestDist = 1000;
+      const float windowMultiplier = 2;
+      const float xl = (x - a.c.cx) * ifx;
+      const float yl = (y - a.c.cy) * ify;
+      const float lambda = sqrtf(xl * xl + yl * yl + 1);
+      const f3 ray = mk3(xl, yl, 1);
+      for (float ii = tcx - (scale * indexXStep * windowMultiplier); ii < tcx + (scale * indexXStep * windowMultiplier); ii += indexXStep)
+        for (float jj = tcy - (scale * indexYStep * windowMultiplier); jj < tcy + (scale * indexYStep * windowMultiplier); jj += indexYStep) {
+          const int p = texel(jj, a.rows) * a.cols + texel(ii, a.cols);
+          const uint32_t current = a.index[p];
+          if (current > 0U) {
+            const float4 vc = a.vert_conf[p];
+            if (fabsf((vc.z * lambda) - (vPosLocal.z * lambda)) < 0.05f) {
+              const float dist = norm(cross(ray, mk3(vc.x, vc.y, vc.z))) / norm(ray);
+              const float4 nr = a.norm_rad[p];
+              const f3 nrm = mk3(nr.x, nr.y, nr.z);
+              const float ang = acosf(dot(nrm, vNormLocal) / (norm(nrm) * norm(vNormLocal)));
+              if (dist < bestDist && (fabsf(nr.z) < 0.75f || fabsf(ang) < 0.5f)) {
+                counter++;
+                bestDist = dist;
+                best = current;
+              }
+            }
+          }
+        }
+      if (counter > 0) {
+        res = best;
+        if ((int)best < cnt) atomicMin(&pending[best], (uint32_t)d);  // lowest draw index wins the update-map texel
+      } else {
+        res = ASSOC_NEW;
+        is_new = 1;
+      }
+    }
+    assoc[d] = res;
+    new_flags[d] = is_new;
+  }
+}
+
+__device__ __forceinline__ void fuse_measurement(const FuseArgs& a, const MapPose* mp, float weighting, int i, int j, float4& pos, float4& col,
+                                                 float4& nr) {
+  const float tcx = uv_coord(i, a.cols), tcy = uv_coord(j, a.rows);
+  const float x = tcx * (float)a.cols, y = tcy * (float)a.rows;
+  const float ifx = (float)(1.0 / (double)a.c.fx), ify = (float)(1.0 / (double)a.c.fy);
+  const f3 vPosLocal = vertex_f(a.depth_raw, a.rows, a.cols, i, j, x, y, a.c, ifx, ify);
+  const f3 vg = xform(mp->pose, vPosLocal);
+  const f3 vPos_f = vertex_f(a.depth_filt, a.rows, a.cols, i, j, x, y, a.c, ifx, ify);
+  const f3 vNormLocal = normal_central(a.depth_filt, a.rows, a.cols, i, j, x, y, vPos_f, a.c, ifx, ify);
+  const f3 ng = rot(mp->pose, vNormLocal);
+  const uint8_t* px = a.rgb + ((size_t)j * a.cols + i) * 3;
+  pos = make_float4(vg.x, vg.y, vg.z, confidence(x, y, weighting, a.c.cx, a.c.cy));
+  col = make_float4(encode_color_bytes(px[0], px[1], px[2]), 0.f, (float)a.time, 0.f);
+  nr = make_float4(ng.x, ng.y, ng.z, get_radius(vPos_f.z, vNormLocal.z, ifx, ify));
+}
+
+__global__ void k_fuse_update(FuseArgs a, const MapPose* __restrict__ mp, const GNState* __restrict__ gn, const int* __restrict__ count,
+                              const uint32_t* __restrict__ assoc, uint32_t* __restrict__ pending, const int* __restrict__ new_off,
+                              const int* __restrict__ new_total, float4* __restrict__ pos_conf, float4* __restrict__ color_time,
+                              float4* __restrict__ norm_rad, float4* __restrict__ new_pos, float4* __restrict__ new_col,
+                              float4* __restrict__ new_nr, int* __restrict__ new_count) {
+  const int n = a.rows * a.cols;
+  const int cnt = *count;
+  const float weighting = gn->weighting;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *new_count = *new_total;
+  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
+    const uint32_t as = assoc[d];
+    if (as == ASSOC_NONE) continue;
+    const int i = d / a.rows, j = d - i * a.rows;
+    float4 mpos, mcol, mnr;
+    if (as == ASSOC_NEW) {
+      fuse_measurement(a, mp, weighting, i, j, mpos, mcol, mnr);
+      mcol.w = -2.f;
+      const int k = new_off[d];
+      new_pos[k] = mpos;
+      new_col[k] = mcol;
+      new_nr[k] = mnr;
+      continue;
+    }
+    if ((int)as >= cnt || pending[as] != (uint32_t)d) continue;
+    pending[as] = 0xffffffffu;  // re-arm the slot: exactly one pixel owns it
+    fuse_measurement(a, mp, weighting, i, j, mpos, mcol, mnr);
+    // update.vert:49-84
+    const float4 s_pos = pos_conf[as], s_col = color_time[as], s_nr = norm_rad[as];
+    const float c_k = s_pos.w, aw = mpos.w;
+    if (mnr.w < (1.0f + 0.5f) * s_nr.w) {
+      const float ck_a = c_k + aw;
+      pos_conf[as] = make_float4(((c_k * s_pos.x) + (aw * mpos.x)) / ck_a, ((c_k * s_pos.y) + (aw * mpos.y)) / ck_a,
+                                 ((c_k * s_pos.z) + (aw * mpos.z)) / ck_a, ck_a);
+      const f3 oldCol = decode_color(s_col.x), newCol = decode_color(mcol.x);
+      const f3 avg = mk3(((c_k * oldCol.x) + (aw * newCol.x)) / ck_a, ((c_k * oldCol.y) + (aw * newCol.y)) / ck_a,
+                         ((c_k * oldCol.z) + (aw * newCol.z)) / ck_a);
+      color_time[as] = make_float4(encode_color(avg), s_col.y, s_col.z, (float)a.time);
+      f3 nn = mk3(((c_k * s_nr.x) + (aw * mnr.x)) / ck_a, ((c_k * s_nr.y) + (aw * mnr.y)) / ck_a, ((c_k * s_nr.z) + (aw * mnr.z)) / ck_a);
+      const float rr = ((c_k * s_nr.w) + (aw * mnr.w)) / ck_a;
+      nn = normalized(nn);
+      norm_rad[as] = make_float4(nn.x, nn.y, nn.z, rr);
+    } else {
+      pos_conf[as] = make_float4(s_pos.x, s_pos.y, s_pos.z, c_k + aw);
+      color_time[as] = make_float4(s_col.x, s_col.y, s_col.z, (float)a.time);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// clean: copy_unstable.vert/.geom without deformation graph (GlobalModel.cpp:527-671)
+// ---------------------------------------------------------------------------------------------------------------
+struct CleanArgs {
+  const uint32_t* index;
+  const float4* vert_conf;
+  const float4* col_time;
+  int rows, cols;
+  Cam c;
+  int time;
+  float conf_threshold;
+  int time_delta;
+};
+
+__device__ __forceinline__ bool clean_test(const CleanArgs& a, const MapPose* mp, const float4& pos, float4& col, const float4& nr) {
+  const float fcols = (float)a.cols, frows = (float)a.rows;
+  int test = 1;
+  const f3 localPos = xform(mp->t_inv, mk3(pos.x, pos.y, pos.z));
+  const float x = ((a.c.fx * localPos.x) / localPos.z) + a.c.cx;
+  const float y = ((a.c.fy * localPos.y) / localPos.z) + a.c.cy;
+  const float scale = 1.0f;
+  const float indexXStep = (1.0f / (fcols * scale)) * 0.5f;
+  const float indexYStep = (1.0f / (frows * scale)) * 0.5f;
+  const float windowMultiplier = 2;
+  int count = 0, zCount = 0;
+  if ((float)a.time - col.w < (float)a.time_delta && localPos.z > 0 && x > 0 && y > 0 && x < fcols && y < frows) {
+    const f3 localNorm = normalized(rot(mp->t_inv, mk3(nr.x, nr.y, nr.z)));
+    for (float i = x / fcols - (scale * indexXStep * windowMultiplier); i < x / fcols + (scale * indexXStep * windowMultiplier); i += indexXStep)
+      for (float j = y / frows - (scale * indexYStep * windowMultiplier); j < y / frows + (scale * indexYStep * windowMultiplier); j += indexYStep) {
+        const int p = texel(j, a.rows) * a.cols + texel(i, a.cols);
+        const uint32_t current = a.index[p];
+        if (current > 0U) {
+          const float4 vc = a.vert_conf[p];
+          const float4 ct = a.col_time[p];
+          const float dx = vc.x - localPos.x, dy = vc.y - localPos.y;
+          if (ct.z < col.z && vc.w > a.conf_threshold && vc.z > localPos.z && vc.z - localPos.z < 0.01f &&
+              sqrtf(dx * dx + dy * dy) < nr.w * 1.4f)
+            count++;
+          if (ct.w == (float)a.time && vc.w > a.conf_threshold && vc.z > localPos.z && vc.z - localPos.z > 0.01f &&
+              fabsf(localNorm.z) > 0.85f)
+            zCount++;
+        }
+      }
+  }
+  if (count > 8 || zCount > 4) test = 0;
+  if (col.w == -2) col.w = (float)a.time;
+  if (col.w == -1 || (((float)a.time - col.w) > 20 && pos.w < a.conf_threshold)) test = 0;
+  if (col.w > 0 && (float)a.time - col.w > (float)a.time_delta) test = 1;
+  return test > 0;
+}
+
+__global__ void k_clean_flags(CleanArgs a, const MapPose* __restrict__ mp, const float4* __restrict__ pos_conf,
+                              const float4* __restrict__ color_time, const float4* __restrict__ norm_rad, const int* __restrict__ count,
+                              const float4* __restrict__ new_pos, const float4* __restrict__ new_col, const float4* __restrict__ new_nr,
+                              const int* __restrict__ new_count, uint8_t* __restrict__ flags) {
+  const int n_old = *count, total = n_old + *new_count;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+    float4 pos, col, nr;
+    if (k < n_old) {
+      pos = pos_conf[k];
+      col = color_time[k];
+      nr = norm_rad[k];
+    } else {
+      pos = new_pos[k - n_old];
+      col = new_col[k - n_old];
+      nr = new_nr[k - n_old];
+    }
+    flags[k] = clean_test(a, mp, pos, col, nr) ? 1 : 0;
+  }
+}
+
+__global__ void k_clean_scatter(int time, const float4* __restrict__ pos_conf, const float4* __restrict__ color_time,
+                                const float4* __restrict__ norm_rad, const int* __restrict__ count, const float4* __restrict__ new_pos,
+                                const float4* __restrict__ new_col, const float4* __restrict__ new_nr, const int* __restrict__ new_count,
+                                const uint8_t* __restrict__ flags, const int* __restrict__ offsets, const int* __restrict__ total_kept,
+                                int capacity, float4* __restrict__ out_pos, float4* __restrict__ out_col, float4* __restrict__ out_nr,
+                                int* __restrict__ out_count) {
+  const int n_old = *count, total = n_old + *new_count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = min(*total_kept, capacity);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+    if (!flags[k]) continue;
+    const int o = offsets[k];
+    if (o >= capacity) continue;
+    if (k < n_old) {
+      out_pos[o] = pos_conf[k];
+      out_col[o] = color_time[k];
+      out_nr[o] = norm_rad[k];
+    } else {
+      float4 col = new_col[k - n_old];
+      if (col.w == -2) col.w = (float)time;  // copy_unstable.vert:114-117
+      out_pos[o] = new_pos[k - n_old];
+      out_col[o] = col;
+      out_nr[o] = new_nr[k - n_old];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// model raycast: splat.vert + combo_splat.frag / depth_splat.frag (IndexMap.cpp:293-476)
+// ---------------------------------------------------------------------------------------------------------------
+struct Splat {
+  f3 pos;
+  float conf;
+  f3 nrm;
+  float rad;
+  float xw, yw, size;
+};
+struct RayArgs {
+  int rows, cols;
+  Cam c;
+  float max_depth, conf_threshold;
+  int time, max_time, time_delta;
+};
+
+__device__ __forceinline__ f3 project_image(const Cam& c, const f3& p) { return mk3(((c.fx * p.x) / p.z) + c.cx, ((c.fy * p.y) / p.z) + c.cy, p.z); }
+
+__device__ __forceinline__ bool splat_vertex(const RayArgs& a, const MapPose* mp, const float4& pc, const float4& ct, const float4* norm_rad,
+                                             int id, Splat& sp) {
+  const float fcols = (float)a.cols, frows = (float)a.rows;
+  const f3 h = xform(mp->t_inv, mk3(pc.x, pc.y, pc.z));
+  if (h.z > a.max_depth || h.z < 0 || pc.w < a.conf_threshold || (float)a.time - ct.w > (float)a.time_delta || ct.w > (float)a.max_time)
+    return false;
+  const float xn = ((((a.c.fx * h.x) / h.z) + a.c.cx) - (fcols * 0.5f)) / (fcols * 0.5f);
+  const float yn = ((((a.c.fy * h.y) / h.z) + a.c.cy) - (frows * 0.5f)) / (frows * 0.5f);
+  const float zn = h.z / a.max_depth;
+  if (!(xn >= -1.f && xn <= 1.f && yn >= -1.f && yn <= 1.f && zn >= -1.f && zn <= 1.f)) return false;
+  const float4 nr = norm_rad[id];
+  sp.pos = h;
+  sp.conf = pc.w;
+  sp.nrm = normalized(rot(mp->t_inv, mk3(nr.x, nr.y, nr.z)));
+  sp.rad = nr.w;
+  const f3 x1 = normalized(mk3((sp.nrm.y - sp.nrm.z), -sp.nrm.x, sp.nrm.x)) * sp.rad * 1.41421356f;
+  const f3 y1 = cross(sp.nrm, x1);
+  const f3 p1 = project_image(a.c, h + x1), p2 = project_image(a.c, h + y1), p3 = project_image(a.c, h - y1), p4 = project_image(a.c, h - x1);
+  const float xs0 = gmin(p1.x, gmin(p2.x, gmin(p3.x, p4.x))), xs1 = gmax(p1.x, gmax(p2.x, gmax(p3.x, p4.x)));
+  const float ys0 = gmin(p1.y, gmin(p2.y, gmin(p3.y, p4.y))), ys1 = gmax(p1.y, gmax(p2.y, gmax(p3.y, p4.y)));
+  const float xDiff = fabsf(xs1 - xs0), yDiff = fabsf(ys1 - ys0);
+  float size = gmax(0.f, gmax(xDiff, yDiff));
+  if (!(size >= 1.0f)) size = 1.0f;
+  if (size > 2047.0f) size = 2047.0f;
+  sp.size = size;
+  sp.xw = (xn + 1.0f) * (fcols * 0.5f);
+  sp.yw = (yn + 1.0f) * (frows * 0.5f);
+  return true;
+}
+
+__device__ __forceinline__ bool splat_fragment(const Splat& sp, const Cam& c, int px, int py, f3& corrected) {
+  const float fxc = (float)px + 0.5f, fyc = (float)py + 0.5f;
+  const f3 l = normalized(mk3((fxc - c.cx) / c.fx, (fyc - c.cy) / c.fy, 1.0f));
+  corrected = l * (dot(sp.pos, sp.nrm) / dot(l, sp.nrm));
+  const float sqrRad = sp.rad * sp.rad;
+  const f3 diff = corrected - sp.pos;
+  return !(dot(diff, diff) > sqrRad);
+}
+
+__global__ void k_splat_scatter(RayArgs a, const MapPose* __restrict__ mp, const float4* __restrict__ pos_conf,
+                                const float4* __restrict__ color_time, const float4* __restrict__ norm_rad, const int* __restrict__ count,
+                                unsigned long long* __restrict__ zbuf) {
+  const int n = *count;
+  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+    Splat sp;
+    if (!splat_vertex(a, mp, pos_conf[id], color_time[id], norm_rad, id, sp)) continue;
+    const float half = sp.size * 0.5f;
+    int x0 = (int)ceilf((sp.xw - half) - 0.5f), x1 = (int)ceilf((sp.xw + half) - 0.5f) - 1;
+    int y0 = (int)ceilf((sp.yw - half) - 0.5f), y1 = (int)ceilf((sp.yw + half) - 0.5f) - 1;
+    x0 = max(x0, 0);
+    y0 = max(y0, 0);
+    x1 = min(x1, a.cols - 1);
+    y1 = min(y1, a.rows - 1);
+    for (int py = y0; py <= y1; ++py)
+      for (int px = x0; px <= x1; ++px) {
+        f3 cp;
+        if (!splat_fragment(sp, a.c, px, py, cp)) continue;
+        const unsigned int d24 = depth24((cp.z / (2 * a.max_depth)) + 0.5f);
+        if (d24 >= 16777215u) continue;
+        atomicMin(&zbuf[(size_t)py * a.cols + px], ((unsigned long long)d24 << 32) | (unsigned int)id);
+      }
+  }
+}
+
+__global__ void k_splat_resolve(RayArgs a, const MapPose* __restrict__ mp, const float4* __restrict__ pos_conf,
+                                const float4* __restrict__ color_time, const float4* __restrict__ norm_rad,
+                                const unsigned long long* __restrict__ zbuf, uchar4* __restrict__ image, float4* __restrict__ vertex,
+                                float4* __restrict__ normal, uint16_t* __restrict__ time_out, float* __restrict__ depth_out) {
+  const int n_px = a.rows * a.cols;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_px; p += gridDim.x * blockDim.x) {
+    const unsigned long long key = zbuf[p];
+    if (key == kEmptyKey) {
+      if (depth_out) {
+        depth_out[p] = 0.f;
+      } else {
+        image[p] = make_uchar4(0, 0, 0, 0);
+        vertex[p] = normal[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        time_out[p] = 0;
+      }
+      continue;
+    }
+    const int py = p / a.cols, px = p - py * a.cols;
+    const uint32_t id = (uint32_t)(key & 0xffffffffull);
+    const float4 ct = color_time[id];
+    Splat sp;
+    splat_vertex(a, mp, pos_conf[id], ct, norm_rad, id, sp);
+    f3 cp;
+    splat_fragment(sp, a.c, px, py, cp);
+    if (depth_out) {
+      depth_out[p] = cp.z;
+      continue;
+    }
+    const f3 col = decode_color(ct.x);
+    image[p] = make_uchar4((unsigned char)(int)rintf(col.x * 255.0f), (unsigned char)(int)rintf(col.y * 255.0f),
+                           (unsigned char)(int)rintf(col.z * 255.0f), 255);
+    const float z = cp.z;
+    const float fxc = (float)px + 0.5f, fyc = (float)py + 0.5f;
+    vertex[p] = make_float4((fxc - a.c.cx) * z * (1.f / a.c.fx), (fyc - a.c.cy) * z * (1.f / a.c.fy), z, sp.conf);
+    normal[p] = make_float4(sp.nrm.x, sp.nrm.y, sp.nrm.z, sp.rad);
+    time_out[p] = (uint16_t)(unsigned int)ct.z;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fill-in (fill_vertex/normal/rgb.frag, FillIn.cpp:62-191) in one launch, and the density test
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_fill_in(const float4* __restrict__ vertex, const float4* __restrict__ normal, const uchar4* __restrict__ image,
+                          const uint16_t* __restrict__ raw_depth, const uint8_t* __restrict__ rgb, int rows, int cols, Cam c,
+                          int pass_geom, int pass_img, float4* __restrict__ fvertex, float4* __restrict__ fnormal,
+                          uchar4* __restrict__ fimage) {
+  const float ifx = 1.0f / c.fx, ify = 1.0f / c.fy;
+  const int n = rows * cols;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const int y = p / cols, x = p - y * cols;
+    const float4 sv = vertex[p];
+    if (sv.z == 0 || pass_geom == 1) {
+      const f3 v = vertex_u(raw_depth, rows, cols, x, y, x, y, c, ifx, ify);
+      fvertex[p] = make_float4(v.x, v.y, v.z, 1.f);
+    } else {
+      fvertex[p] = sv;
+    }
+    const float4 sn = normal[p];
+    if (sn.z == 0 || pass_geom == 1) {
+      const f3 v = vertex_u(raw_depth, rows, cols, x, y, x, y, c, ifx, ify);
+      const f3 vx = vertex_u(raw_depth, rows, cols, x + 1, y, x + 1, y, c, ifx, ify);
+      const f3 vy = vertex_u(raw_depth, rows, cols, x, y + 1, x, y + 1, c, ifx, ify);
+      const f3 nn = normalized(cross(vx - v, vy - v));
+      fnormal[p] = make_float4(nn.x, nn.y, nn.z, 1.f);
+    } else {
+      fnormal[p] = sn;
+    }
+    const uchar4 si = image[p];
+    if (((int)si.x + (int)si.y + (int)si.z == 0) || pass_img == 1)
+      fimage[p] = make_uchar4(rgb[(size_t)p * 3 + 0], rgb[(size_t)p * 3 + 1], rgb[(size_t)p * 3 + 2], 255);
+    else
+      fimage[p] = si;
+  }
+}
+
+// Resize::image (nearest decimation by 20) + ElasticFusion::denseEnough (Resize.cpp:50-79, ElasticFusion.cpp:256-268)
+__global__ void k_dense_enough(const uchar4* __restrict__ image, int rows, int cols, int factor, int* __restrict__ flag) {
+  const int drows = rows / factor, dcols = cols / factor;
+  __shared__ int s_sum;
+  if (threadIdx.x == 0) s_sum = 0;
+  __syncthreads();
+  int local = 0;
+  for (int q = threadIdx.x; q < drows * dcols; q += blockDim.x) {
+    const int j = q / dcols, i = q - j * dcols;
+    const int sx = texel(((float)i + 0.5f) / (float)dcols, cols);
+    const int sy = texel(((float)j + 0.5f) / (float)drows, rows);
+    const uchar4 s = image[(size_t)sy * cols + sx];
+    local += (s.x > 0 && s.y > 0 && s.z > 0) ? 1 : 0;
+  }
+  atomicAdd(&s_sum, local);
+  __syncthreads();
+  if (threadIdx.x == 0) *flag = ((float)s_sum / (float)(drows * dcols) > 0.75f) ? 1 : 0;
+}
+
+__global__ void k_set_int(int* p, int v) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *p = v;
+}
+
+// AoS (reference Vertex layout) <-> SoA repack for downloadMap / upload
+__global__ void k_pack_aos(const float4* __restrict__ a, const float4* __restrict__ b, const float4* __restrict__ c, int n, float4* __restrict__ out) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    out[(size_t)k * 3 + 0] = a[k];
+    out[(size_t)k * 3 + 1] = b[k];
+    out[(size_t)k * 3 + 2] = c[k];
+  }
+}
+__global__ void k_unpack_aos(const float4* __restrict__ in, int n, float4* __restrict__ a, float4* __restrict__ b, float4* __restrict__ c) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    a[k] = in[(size_t)k * 3 + 0];
+    b[k] = in[(size_t)k * 3 + 1];
+    c[k] = in[(size_t)k * 3 + 2];
+  }
+}
+
+inline int sblocks(const EfContext* ctx, size_t n, int per_sm = 8) {
+  size_t b = (n + 255) / 256, cap = (size_t)ctx->num_sms * per_sm;
+  return (int)(b < cap ? (b ? b : 1) : cap);
+}
+inline Cam cam_of(const EfContext* ctx) { return Cam{ctx->cfg.cx, ctx->cfg.cy, ctx->cfg.fx, ctx->cfg.fy}; }
+
+}  // namespace
+
+#define CU(x)                                \
+  do {                                       \
+    cudaError_t e__ = (x);                   \
+    if (e__ != cudaSuccess) return (int)e__; \
+  } while (0)
+#define LAST()                                \
+  do {                                        \
+    cudaError_t e__ = cudaGetLastError();     \
+    if (e__ != cudaSuccess) return (int)e__;  \
+  } while (0)
+
+// surfel buffers are ping-ponged by clean (the reference's two VBOs, GlobalModel.cpp:71-87)
+struct MapBuffers {
+  float4 *pos[2], *col[2], *nr[2];
+  int cur;
+  int *offsets;
+  int *totals;  // [4] scan totals
+  int *fb_off_raw, *fb_off_filt;
+  uint8_t *fb_flag_raw, *fb_flag_filt;
+  float4* aos;  // staging for download/upload
+  size_t aos_cap;
+};
+
+namespace ef {
+
+static MapBuffers& mb(EfContext* ctx) { return *reinterpret_cast<MapBuffers*>(ctx->map_host); }
+
+int alloc_map(EfContext* ctx) {
+  MapDev& m = ctx->map;
+  memset(&m, 0, sizeof(m));
+  const EfConfig& c = ctx->cfg;
+  m.rows = c.height;
+  m.cols = c.width;
+  m.cx = c.cx;
+  m.cy = c.cy;
+  m.fx = c.fx;
+  m.fy = c.fy;
+  m.capacity = c.capacity;
+  const size_t n = (size_t)c.width * c.height, cap = (size_t)c.capacity;
+  MapBuffers* B = new MapBuffers();
+  memset(B, 0, sizeof(*B));
+  ctx->map_host = B;
+  for (int s = 0; s < 2; ++s) {
+    CU(ctx_alloc(ctx, &B->pos[s], cap));
+    CU(ctx_alloc(ctx, &B->col[s], cap));
+    CU(ctx_alloc(ctx, &B->nr[s], cap));
+  }
+  B->cur = 0;
+  m.pos_conf = B->pos[0];
+  m.color_time = B->col[0];
+  m.norm_rad = B->nr[0];
+  CU(ctx_alloc(ctx, &m.count, 4));
+  CU(ctx_alloc(ctx, &m.new_pos, n));
+  CU(ctx_alloc(ctx, &m.new_col, n));
+  CU(ctx_alloc(ctx, &m.new_nr, n));
+  CU(ctx_alloc(ctx, &m.new_count, 4));
+  CU(ctx_alloc(ctx, &m.assoc_id, n));
+  CU(ctx_alloc(ctx, &m.pending, cap));
+  CU(ctx_alloc(ctx, &m.zbuf, n));
+  const size_t max_items = cap + n;
+  const size_t tiles = (max_items + SCAN_TILE - 1) / SCAN_TILE + 1;
+  unsigned long long* st = nullptr;
+  CU(ctx_alloc(ctx, &st, tiles));
+  m.scan_tile_state = reinterpret_cast<int*>(st);
+  CU(ctx_alloc(ctx, &m.scan_counter, 4));
+  CU(ctx_alloc(ctx, &m.flags, max_items));
+  CU(ctx_alloc(ctx, &B->offsets, max_items));
+  CU(ctx_alloc(ctx, &B->totals, 4));
+  CU(ctx_alloc(ctx, &B->fb_off_raw, n));
+  CU(ctx_alloc(ctx, &B->fb_off_filt, n));
+  CU(ctx_alloc(ctx, &B->fb_flag_raw, n));
+  CU(ctx_alloc(ctx, &B->fb_flag_filt, n));
+  CU(ctx_alloc(ctx, &m.pose, 1));
+  CU(ctx_alloc(ctx, &m.dense_flag, 4));
+  CU(ctx_alloc(ctx, &m.tick, 4));
+  CU(cudaMemsetAsync(m.count, 0, 16, ctx->stream));
+  CU(cudaMemsetAsync(m.new_count, 0, 16, ctx->stream));
+  CU(cudaMemsetAsync(m.pending, 0xff, cap * 4, ctx->stream));
+  CU(cudaMemsetAsync(m.dense_flag, 0, 16, ctx->stream));
+  CU(cudaMemsetAsync(B->totals, 0, 16, ctx->stream));
+  const int one = 1;
+  CU(cudaMemcpyAsync(m.tick, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static int run_scan(EfContext* ctx, const uint8_t* flags, const int* n_a, const int* n_b, size_t max_items, int* offsets, int* total) {
+  MapDev& m = ctx->map;
+  const size_t tiles = (max_items + SCAN_TILE - 1) / SCAN_TILE + 1;
+  CU(cudaMemsetAsync(m.scan_tile_state, 0, tiles * 8, ctx->stream));
+  CU(cudaMemsetAsync(m.scan_counter, 0, 4, ctx->stream));
+  size_t nb = tiles < (size_t)ctx->num_sms * 4 ? tiles : (size_t)ctx->num_sms * 4;
+  EF_LAUNCH(ctx, k_scan_flags, (int)nb, SCAN_THREADS, 0, flags, n_a, n_b, offsets, (unsigned long long*)m.scan_tile_state, m.scan_counter, total);
+  LAST();
+  return 0;
+}
+
+// T == nullptr: use the tracker's device-resident pose
+int map_update_pose_async(EfContext* ctx, const double* T_host) {
+  const double* src = ctx->odom[0].gn->T_wc;
+  if (T_host) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy((char*)ctx->pin_small + 1024, T_host, sizeof(double) * 16);
+    CU(cudaMemcpyAsync((char*)ctx->dev_small + 1024, (char*)ctx->pin_small + 1024, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
+    src = (const double*)((char*)ctx->dev_small + 1024);
+  }
+  EF_LAUNCH(ctx, k_update_pose, 1, 32, 0, ctx->map.pose, src);
+  LAST();
+  return 0;
+}
+
+int map_initialise_async(EfContext* ctx) {
+  MapDev& m = ctx->map;
+  MapBuffers& B = mb(ctx);
+  const int n = m.rows * m.cols;
+  EF_LAUNCH(ctx, k_feedback_flags, sblocks(ctx, n), 256, 0, ctx->tex.depth_metric, ctx->tex.depth_metric_filtered, m.rows, m.cols,
+            ctx->max_depth_processed, B.fb_flag_raw, B.fb_flag_filt);
+  // device-resident element count for the scans: reuse new_count as "n pixels"
+  EF_LAUNCH(ctx, k_set_int, 1, 32, 0, m.new_count, n);
+  int rc = run_scan(ctx, B.fb_flag_raw, m.new_count, nullptr, n, B.fb_off_raw, B.totals + 0);
+  if (rc) return rc;
+  rc = run_scan(ctx, B.fb_flag_filt, m.new_count, nullptr, n, B.fb_off_filt, B.totals + 1);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(m.norm_rad, 0, (size_t)(n < m.capacity ? n : m.capacity) * sizeof(float4), ctx->stream));
+  EF_LAUNCH(ctx, k_init_scatter, sblocks(ctx, n), 256, 0, ctx->tex.rgb, ctx->tex.depth_metric, ctx->tex.depth_metric_filtered, m.rows, m.cols,
+            cam_of(ctx), ctx->tick, B.fb_flag_raw, B.fb_flag_filt, B.fb_off_raw, B.fb_off_filt, B.totals + 0, m.capacity, m.pos_conf,
+            m.color_time, m.norm_rad, m.count);
+  EF_LAUNCH(ctx, k_set_int, 1, 32, 0, m.new_count, 0);
+  LAST();
+  return 0;
+}
+
+int map_predict_indices_async(EfContext* ctx, int time, float max_depth, int time_delta) {
+  MapDev& m = ctx->map;
+  const int n = m.rows * m.cols;
+  CU(cudaMemsetAsync(m.zbuf, 0xff, (size_t)n * 8, ctx->stream));
+  const int cap_guess = ctx->host_count > 0 ? ctx->host_count : m.capacity;
+  (void)cap_guess;
+  EF_LAUNCH(ctx, k_index_scatter, ctx->num_sms * 8, 256, 0, m.pos_conf, m.color_time, m.count, m.pose, time, max_depth, time_delta, m.rows,
+            m.cols, cam_of(ctx), m.zbuf);
+  EF_LAUNCH(ctx, k_index_resolve, sblocks(ctx, n), 256, 0, m.pos_conf, m.color_time, m.norm_rad, m.pose, n, m.zbuf, ctx->tex.index,
+            ctx->tex.vert_conf, ctx->tex.color_time, ctx->tex.norm_rad);
+  LAST();
+  return 0;
+}
+
+static FuseArgs fuse_args(EfContext* ctx, int time, float max_depth) {
+  FuseArgs a;
+  a.rgb = ctx->tex.rgb;
+  a.depth_raw = ctx->tex.depth_metric;
+  a.depth_filt = ctx->tex.depth_metric_filtered;
+  a.index = ctx->tex.index;
+  a.vert_conf = ctx->tex.vert_conf;
+  a.norm_rad = ctx->tex.norm_rad;
+  a.rows = ctx->map.rows;
+  a.cols = ctx->map.cols;
+  a.c = cam_of(ctx);
+  a.time = time;
+  a.max_depth = max_depth;
+  return a;
+}
+
+// weighting < 0: use the device-resident velocity weighting computed by the tracker
+int map_fuse_async(EfContext* ctx, int time, float max_depth, float weighting) {
+  MapDev& m = ctx->map;
+  MapBuffers& B = mb(ctx);
+  const int n = m.rows * m.cols;
+  if (weighting >= 0) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    *(float*)((char*)ctx->pin_small + 2048) = weighting;
+    CU(cudaMemcpyAsync((char*)ctx->odom[0].gn + offsetof(GNState, weighting), (char*)ctx->pin_small + 2048, 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  FuseArgs a = fuse_args(ctx, time, max_depth);
+  EF_LAUNCH(ctx, k_fuse_associate, sblocks(ctx, n), 256, 0, a, m.count, m.assoc_id, m.pending, m.flags);
+  EF_LAUNCH(ctx, k_set_int, 1, 32, 0, m.new_count, n);
+  int rc = run_scan(ctx, m.flags, m.new_count, nullptr, n, B.offsets, B.totals + 2);
+  if (rc) return rc;
+  EF_LAUNCH(ctx, k_fuse_update, sblocks(ctx, n), 256, 0, a, m.pose, (const GNState*)ctx->odom[0].gn, m.count, m.assoc_id, m.pending, B.offsets,
+            B.totals + 2, m.pos_conf, m.color_time, m.norm_rad, m.new_pos, m.new_col, m.new_nr, m.new_count);
+  LAST();
+  return 0;
+}
+
+int map_clean_async(EfContext* ctx, int time, float conf_threshold, int time_delta, float max_depth) {
+  (void)max_depth;
+  MapDev& m = ctx->map;
+  MapBuffers& B = mb(ctx);
+  CleanArgs a;
+  a.index = ctx->tex.index;
+  a.vert_conf = ctx->tex.vert_conf;
+  a.col_time = ctx->tex.color_time;
+  a.rows = m.rows;
+  a.cols = m.cols;
+  a.c = cam_of(ctx);
+  a.time = time;
+  a.conf_threshold = conf_threshold;
+  a.time_delta = time_delta;
+  const size_t max_items = (size_t)m.capacity + (size_t)m.rows * m.cols;
+  EF_LAUNCH(ctx, k_clean_flags, ctx->num_sms * 8, 256, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos, m.new_col, m.new_nr,
+            m.new_count, m.flags);
+  int rc = run_scan(ctx, m.flags, m.count, m.new_count, max_items, B.offsets, B.totals + 3);
+  if (rc) return rc;
+  const int other = 1 - B.cur;
+  EF_LAUNCH(ctx, k_clean_scatter, ctx->num_sms * 8, 256, 0, time, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos, m.new_col, m.new_nr,
+            m.new_count, m.flags, B.offsets, B.totals + 3, m.capacity, B.pos[other], B.col[other], B.nr[other], m.new_count + 1);
+  // swap (GlobalModel.cpp:667) and publish the new count
+  B.cur = other;
+  m.pos_conf = B.pos[other];
+  m.color_time = B.col[other];
+  m.norm_rad = B.nr[other];
+  CU(cudaMemcpyAsync(m.count, m.new_count + 1, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  EF_LAUNCH(ctx, k_set_int, 1, 32, 0, m.new_count, 0);
+  LAST();
+  return 0;
+}
+
+int map_raycast_async(EfContext* ctx, float max_depth, float conf_threshold, int time, int max_time, int time_delta, int mode, bool) {
+  MapDev& m = ctx->map;
+  const int n = m.rows * m.cols;
+  RayArgs a;
+  a.rows = m.rows;
+  a.cols = m.cols;
+  a.c = cam_of(ctx);
+  a.max_depth = max_depth;
+  a.conf_threshold = conf_threshold;
+  a.time = time;
+  a.max_time = max_time;
+  a.time_delta = time_delta;
+  CU(cudaMemsetAsync(m.zbuf, 0xff, (size_t)n * 8, ctx->stream));
+  EF_LAUNCH(ctx, k_splat_scatter, ctx->num_sms * 8, 256, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.zbuf);
+  Textures& t = ctx->tex;
+  if (mode == 0)
+    EF_LAUNCH(ctx, k_splat_resolve, sblocks(ctx, n), 256, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.zbuf, t.image, t.vertex, t.normal,
+              t.time, (float*)nullptr);
+  else if (mode == 1)
+    EF_LAUNCH(ctx, k_splat_resolve, sblocks(ctx, n), 256, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.zbuf, t.old_image, t.old_vertex,
+              t.old_normal, t.old_time, (float*)nullptr);
+  else
+    EF_LAUNCH(ctx, k_splat_resolve, sblocks(ctx, n), 256, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.zbuf, (uchar4*)nullptr,
+              (float4*)nullptr, (float4*)nullptr, (uint16_t*)nullptr, t.synth_depth);
+  LAST();
+  return 0;
+}
+
+int map_fill_in_async(EfContext* ctx, bool pass_geom, bool pass_img) {
+  MapDev& m = ctx->map;
+  Textures& t = ctx->tex;
+  const int n = m.rows * m.cols;
+  EF_LAUNCH(ctx, k_fill_in, sblocks(ctx, n), 256, 0, t.vertex, t.normal, t.image, t.depth_filtered, t.rgb, m.rows, m.cols, cam_of(ctx),
+            pass_geom ? 1 : 0, pass_img ? 1 : 0, t.fill_vertex, t.fill_normal, t.fill_image);
+  LAST();
+  return 0;
+}
+
+int map_dense_enough_async(EfContext* ctx) {
+  MapDev& m = ctx->map;
+  EF_LAUNCH(ctx, k_dense_enough, 1, 256, 0, ctx->tex.image, m.rows, m.cols, 20, m.dense_flag);
+  LAST();
+  return 0;
+}
+
+int map_download(EfContext* ctx, const float4* a, const float4* b, const float4* c, int n, float* out) {
+  MapBuffers& B = mb(ctx);
+  if (n <= 0) return 0;
+  if ((size_t)n > B.aos_cap) {
+    if (B.aos) cudaFree(B.aos);
+    B.aos = nullptr;
+    CU(cudaMalloc((void**)&B.aos, (size_t)n * 48));
+    B.aos_cap = n;
+  }
+  EF_LAUNCH(ctx, k_pack_aos, sblocks(ctx, n), 256, 0, a, b, c, n, B.aos);
+  CU(cudaMemcpyAsync(out, B.aos, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int map_upload(EfContext* ctx, const float* in, int n) {
+  MapDev& m = ctx->map;
+  MapBuffers& B = mb(ctx);
+  if (n > m.capacity) return EF_EINVAL;
+  if (n > 0) {
+    if ((size_t)n > B.aos_cap) {
+      if (B.aos) cudaFree(B.aos);
+      B.aos = nullptr;
+      CU(cudaMalloc((void**)&B.aos, (size_t)n * 48));
+      B.aos_cap = n;
+    }
+    CU(cudaMemcpyAsync(B.aos, in, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
+    EF_LAUNCH(ctx, k_unpack_aos, sblocks(ctx, n), 256, 0, (const float4*)B.aos, n, m.pos_conf, m.color_time, m.norm_rad);
+  }
+  EF_LAUNCH(ctx, k_set_int, 1, 32, 0, m.count, n);
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->host_count = n;
+  return 0;
+}
+
+void map_free_host(EfContext* ctx) {
+  MapBuffers* B = reinterpret_cast<MapBuffers*>(ctx->map_host);
+  if (B) {
+    if (B->aos) cudaFree(B->aos);
+    delete B;
+    ctx->map_host = nullptr;
+  }
+}
+
+}  // namespace ef

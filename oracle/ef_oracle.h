@@ -162,6 +162,19 @@ EfoOdometry* efo_fusion_odometry(EfoFusion* f);
 /* which: 0 image4(u8) 1 vertex4 2 normal4 3 time(u16) 4 fill image4 5 fill vertex4 6 fill normal4
  * 7 depth filtered (u16) 8 metric raw 9 metric filtered 10 index (u32) 11 vertConf 12 colorTime 13 normRad */
 const void* efo_fusion_buffer(const EfoFusion* f, int which);
+/* Optional external tracker backend (used by bench.py --impl reference to drive the REFERENCE's own CUDA tracking
+ * kernels from oracle/_ref/libef_ref.so inside this pipeline). All pointers are host memory. */
+typedef struct {
+  void* handle;
+  void (*init_icp_model)(void*, const float* vtx4, const float* nrm4, const double* T_wc16);
+  void (*init_rgb_model)(void*, const uint8_t* rgba);
+  void (*init_icp_depth)(void*, const uint16_t* depth, float cutoff);
+  void (*init_rgb)(void*, const uint8_t* rgba);
+  void (*init_first_rgb)(void*, const uint8_t* rgba);
+  int (*track)(void*, double* T_wc16, int rgb_only, float icp_weight, int pyramid, int fast_odom, int so3, void* trace,
+               int max_trace);
+} EfoTrackerBackend;
+void efo_fusion_set_tracker(EfoFusion* f, const EfoTrackerBackend* backend);
 /* wall-clock seconds spent per stage since creation: preprocess, tracking, mapping(fuse+clean+index), predict */
 void efo_fusion_timers(const EfoFusion* f, double* out4);
 

@@ -41,6 +41,8 @@ struct EfoFusion {
 
   double timers[4];
   float lastWeighting;
+  EfoTrackerBackend ext;
+  bool has_ext;
 };
 
 extern "C" EfoFusion* efo_fusion_create(const EfoConfig* cfg) {
@@ -84,6 +86,7 @@ extern "C" EfoFusion* efo_fusion_create(const EfoConfig* cfg) {
   f->timeTex.assign(n, 0);
   for (int i = 0; i < 4; ++i) f->timers[i] = 0;
   f->lastWeighting = 0;
+  f->has_ext = false;
   return f;
 }
 
@@ -130,7 +133,10 @@ extern "C" void efo_fusion_process_frame(EfoFusion* f, const uint8_t* rgb, const
     int filtN = efo_feedback_buffer(f->rgb.data(), f->depthMetricFiltered.data(), f->rows, f->cols, f->cam4, f->tick,
                                     f->maxDepthProcessed, f->filtFb.data());
     f->count = efo_map_initialise(f->rawFb.data(), rawN, f->filtFb.data(), filtN, (int)n, f->map.data());
-    efo_odom_init_first_rgb(f->frameToModel, f->rgba.data());
+    if (f->has_ext)
+      f->ext.init_first_rgb(f->ext.handle, f->rgba.data());
+    else
+      efo_odom_init_first_rgb(f->frameToModel, f->rgba.data());
     f->timers[2] += now_s() - t1;
   } else {
     double T_prev[16];
@@ -138,14 +144,24 @@ extern "C" void efo_fusion_process_frame(EfoFusion* f, const uint8_t* rgb, const
     if (!in_T_wc) {
       // ElasticFusion.cpp:302-323
       bool shouldFillIn = !efo_dense_enough(f->imageTex.data(), f->rows, f->cols, 20);
-      efo_odom_init_icp_model(f->frameToModel, shouldFillIn ? f->fillVertex.data() : f->vertexTex.data(),
-                              shouldFillIn ? f->fillNormal.data() : f->normalTex.data(), f->T_wc);
-      efo_odom_init_rgb_model(f->frameToModel,
-                              (shouldFillIn || f->cfg.frame_to_frame_rgb) ? f->fillImage.data() : f->imageTex.data());
-      efo_odom_init_icp_depth(f->frameToModel, f->depthFiltered.data(), f->maxDepthProcessed);
-      efo_odom_init_rgb(f->frameToModel, f->rgba.data());
-      efo_odom_track(f->frameToModel, f->T_wc, f->cfg.rgb_only, f->cfg.icp_weight, f->cfg.pyramid, f->cfg.fast_odom,
-                     f->cfg.so3, nullptr, 0);
+      const float* mv = shouldFillIn ? f->fillVertex.data() : f->vertexTex.data();
+      const float* mn = shouldFillIn ? f->fillNormal.data() : f->normalTex.data();
+      const uint8_t* mi = (shouldFillIn || f->cfg.frame_to_frame_rgb) ? f->fillImage.data() : f->imageTex.data();
+      if (f->has_ext) {
+        f->ext.init_icp_model(f->ext.handle, mv, mn, f->T_wc);
+        f->ext.init_rgb_model(f->ext.handle, mi);
+        f->ext.init_icp_depth(f->ext.handle, f->depthFiltered.data(), f->maxDepthProcessed);
+        f->ext.init_rgb(f->ext.handle, f->rgba.data());
+        f->ext.track(f->ext.handle, f->T_wc, f->cfg.rgb_only, f->cfg.icp_weight, f->cfg.pyramid, f->cfg.fast_odom, f->cfg.so3,
+                     nullptr, 0);
+      } else {
+        efo_odom_init_icp_model(f->frameToModel, mv, mn, f->T_wc);
+        efo_odom_init_rgb_model(f->frameToModel, mi);
+        efo_odom_init_icp_depth(f->frameToModel, f->depthFiltered.data(), f->maxDepthProcessed);
+        efo_odom_init_rgb(f->frameToModel, f->rgba.data());
+        efo_odom_track(f->frameToModel, f->T_wc, f->cfg.rgb_only, f->cfg.icp_weight, f->cfg.pyramid, f->cfg.fast_odom,
+                       f->cfg.so3, nullptr, 0);
+      }
     } else {
       memcpy(f->T_wc, in_T_wc, sizeof(f->T_wc));
     }
@@ -197,6 +213,10 @@ extern "C" void efo_fusion_process_frame(EfoFusion* f, const uint8_t* rgb, const
   f->tick++;
 }
 
+extern "C" void efo_fusion_set_tracker(EfoFusion* f, const EfoTrackerBackend* b) {
+  f->has_ext = b != nullptr;
+  if (b) f->ext = *b;
+}
 extern "C" void efo_fusion_pose(const EfoFusion* f, double* T) { memcpy(T, f->T_wc, sizeof(f->T_wc)); }
 extern "C" int efo_fusion_count(const EfoFusion* f) { return f->count; }
 extern "C" int efo_fusion_tick(const EfoFusion* f) { return f->tick; }

@@ -1,0 +1,190 @@
+"""GPU parity tests of the tracking half: libefusion.so (through its C ABI) vs the CPU oracle on identical inputs.
+
+Per-pixel stages are compared bit-exactly (both sides evaluate the reference's formulas with single IEEE ops in the
+same order). Reductions differ only in summation order; tolerance 1e-5 relative per system (BASELINE.json allows 1e-4).
+"""
+import numpy as np
+import pytest
+
+from util import assert_same, assert_same_map, rel_err, rgba_of, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+LEVELS = (0, 1, 2)
+
+
+@pytest.fixture(scope="module")
+def state(frames, K):
+    """Oracle after 3 frames + the inputs of frame 3, and a product context holding the same tracker inputs."""
+    from elasticfusion_b200 import capi
+    from oracle import ef_oracle as eo
+
+    f = run_oracle(frames, K, 3)
+    rgb, depth, _ = frames[3]
+    filt = eo.bilateral(depth, 3.0)
+    od = f.odometry()
+    T_prev = f.pose
+    vtx, nrm, img = f.buffer("fill_vertex"), f.buffer("fill_normal"), f.buffer("fill_image")
+    od.init_icp_model(vtx, nrm, T_prev)
+    od.init_rgb_model(img)
+    od.init_icp_depth(filt, 20.0)
+    od.init_rgb(rgba_of(rgb))
+
+    ctx = capi.Context(capi.default_config(K.width, K.height, K.fx, K.fy, K.cx, K.cy, capacity=400000))
+    ctx.upload("FILL_VERTEX", vtx)
+    ctx.upload("FILL_NORMAL", nrm)
+    ctx.upload("FILL_IMAGE", img)
+    ctx.upload("DEPTH_FILTERED", filt)
+    ctx.upload("RGBA", rgba_of(rgb))
+    # lastNextImage of the oracle tracker = previous live frame pyramid
+    for lv in LEVELS:
+        ctx.upload("LAST_NEXT_IMAGE", od.buffer("lastNextImage", lv), level=lv)
+    ctx.odom_init_icp_model(ctx.buffer_ptr("FILL_VERTEX")[0], ctx.buffer_ptr("FILL_NORMAL")[0], T_prev)
+    ctx.odom_init_rgb_model(ctx.buffer_ptr("FILL_IMAGE")[0])
+    ctx.odom_init_icp_depth(ctx.buffer_ptr("DEPTH_FILTERED")[0], 20.0)
+    ctx.odom_init_rgb(ctx.buffer_ptr("RGBA")[0])
+    yield dict(f=f, od=od, ctx=ctx, T_prev=T_prev, K=K, filt=filt)
+    ctx.close()
+
+
+@pytest.mark.parametrize("lv", LEVELS)
+def test_current_pyramid_bit_exact(state, lv):
+    od, ctx = state["od"], state["ctx"]
+    assert_same(ctx.download("DEPTH_TMP", lv), od.buffer("depth_tmp", lv), f"depth_tmp[{lv}]")
+    assert_same_map(ctx.download("VMAP_CURR", lv), od.buffer("vmap_curr", lv), f"vmap_curr[{lv}]")
+    assert_same_map(ctx.download("NMAP_CURR", lv), od.buffer("nmap_curr", lv), f"nmap_curr[{lv}]")
+
+
+@pytest.mark.parametrize("lv", LEVELS)
+def test_model_pyramid_bit_exact(state, lv):
+    od, ctx = state["od"], state["ctx"]
+    assert_same_map(ctx.download("VMAP_G_PREV", lv), od.buffer("vmap_g_prev", lv), f"vmap_g_prev[{lv}]")
+    assert_same_map(ctx.download("NMAP_G_PREV", lv), od.buffer("nmap_g_prev", lv), f"nmap_g_prev[{lv}]")
+
+
+@pytest.mark.parametrize("lv", LEVELS)
+def test_rgbd_pyramids_bit_exact(state, lv):
+    od, ctx = state["od"], state["ctx"]
+    for name, oname in (("LAST_DEPTH", "lastDepth"), ("NEXT_DEPTH", "nextDepth"), ("LAST_IMAGE", "lastImage"),
+                        ("NEXT_IMAGE", "nextImage")):
+        assert_same(ctx.download(name, lv), od.buffer(oname, lv), f"{oname}[{lv}]")
+
+
+def _level_intr(K, lv):
+    d = 1 << lv
+    f32 = np.float32
+    return f32(K.fx) / f32(d), f32(K.fy) / f32(d), f32(K.cx) / f32(d), f32(K.cy) / f32(d)
+
+
+@pytest.mark.parametrize("lv", LEVELS)
+def test_icp_step_matches_oracle(state, lv):
+    from oracle import ef_oracle as eo
+
+    od, ctx, K, T = state["od"], state["ctx"], state["K"], state["T_prev"]
+    R = T[:3, :3].astype(np.float32)
+    t = T[:3, 3].astype(np.float32)
+    # a small offset so that residuals are non-trivial
+    dR = np.array([[1, -0.002, 0.001], [0.002, 1, -0.003], [-0.001, 0.003, 1]], np.float32)
+    Rcurr, tcurr = (R @ dR).astype(np.float32), (t + np.array([0.004, -0.003, 0.005], np.float32))
+    Rprev_inv = np.linalg.inv(R).astype(np.float32)
+    fx, fy, cx, cy = _level_intr(K, lv)
+    Ao, bo, ro = eo.icp_step(Rcurr, tcurr, od.buffer("vmap_curr", lv), od.buffer("nmap_curr", lv), Rprev_inv, t, fx, fy, cx, cy,
+                             od.buffer("vmap_g_prev", lv), od.buffer("nmap_g_prev", lv), 0.10, float(np.sin(np.float32(20.0) * np.float32(3.14159254) / np.float32(180.0))))
+    Ap, bp, rp = ctx.icp_step(lv, Rcurr, tcurr, Rprev_inv, t)
+    assert rp[1] == ro[1], f"inlier count {rp[1]} vs {ro[1]}"
+    assert ro[1] > 1000
+    assert rel_err(Ap, Ao) < 1e-5 and rel_err(bp, bo) < 1e-5 and abs(rp[0] - ro[0]) <= 1e-5 * abs(ro[0])
+
+
+@pytest.mark.parametrize("lv", LEVELS)
+def test_photometric_residual_and_step(state, lv):
+    from oracle import ef_oracle as eo
+
+    od, ctx, K = state["od"], state["ctx"], state["K"]
+    fx, fy, cx, cy = _level_intr(K, lv)
+    Km = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64)
+    ang = 0.003
+    R = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    krkinv = (Km @ R @ np.linalg.inv(Km)).astype(np.float32)
+    kt = (Km @ np.array([0.004, -0.002, 0.003])).astype(np.float32)
+    dIdx, dIdy = eo.sobel(od.buffer("nextImage", lv))
+    min_scale = np.float32((float(od_min_grad(lv)) ** 2) / (0.125 ** 2))
+    corres, sig_o, cnt_o = eo.rgb_residual(min_scale, dIdx, dIdy, od.buffer("lastDepth", lv), od.buffer("nextDepth", lv),
+                                           od.buffer("lastImage", lv), od.buffer("nextImage", lv), 0.07, kt, krkinv)
+    sig_p, cnt_p = ctx.rgb_residual(lv, krkinv, kt)
+    assert_same(ctx.download("DIDX", lv), dIdx, "dIdx")
+    assert_same(ctx.download("DIDY", lv), dIdy, "dIdy")
+    assert (sig_p, cnt_p) == (sig_o, cnt_o)
+    assert cnt_o > 100
+    cp = ctx.download("CORRES", lv)
+    assert_same(cp["valid"], corres["valid"], "corres.valid")
+    v = corres["valid"] != 0
+    for n in ("zero_x", "zero_y", "one_x", "one_y", "diff"):
+        assert_same(cp[n][v], corres[n][v], f"corres.{n}")
+    sigma = float(np.sqrt(np.float32(cnt_o)))
+    cloud = eo.project_points(od.buffer("lastDepth", lv), fx, fy, cx, cy)
+    Ao, bo = eo.rgb_step(corres, sigma, cloud, fx, fy, dIdx, dIdy, 0.125)
+    Ap, bp = ctx.rgb_step(lv, sigma)
+    assert rel_err(Ap, Ao) < 1e-5 and rel_err(bp, bo) < 1e-5
+
+
+def od_min_grad(lv):
+    return (5, 3, 1)[lv]
+
+
+def test_so3_step_matches_oracle(state):
+    from oracle import ef_oracle as eo
+
+    od, ctx, K = state["od"], state["ctx"], state["K"]
+    fx, fy, cx, cy = _level_intr(K, 2)
+    Km = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64)
+    a = 0.004
+    R = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    H = (Km @ R @ np.linalg.inv(Km)).astype(np.float32)
+    kinv = np.linalg.inv(Km).astype(np.float32)
+    krlr = (Km @ R).astype(np.float32)
+    Ao, bo, ro = eo.so3_step(od.buffer("lastNextImage", 2), od.buffer("nextImage", 2), H, kinv, krlr)
+    Ap, bp, rp = ctx.so3_step(H, kinv, krlr)
+    assert rp[1] == ro[1]
+    assert rel_err(Ap, Ao) < 1e-5 and rel_err(bp, bo) < 1e-5 and abs(rp[0] - ro[0]) <= 1e-5 * abs(ro[0])
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(icp_weight=100.0, so3=False), dict(fast_odom=True), dict(pyramid=False, so3=False),
+                                 dict(rgb_only=True, so3=False)])
+def test_full_track_trace_matches_oracle(state, cfg):
+    """getIncrementalTransformation on the device vs the oracle host loop. Iteration k starts from the pose iteration k-1
+    produced, so the two runs see inputs that differ by summation-order noise; a handful of borderline correspondences
+    (distance / angle gates, nearest-pixel rounding) flip, which moves A by ~1e-4 relative at level 0. Hence: every
+    iteration's system within 5e-4 relative, solve result within 1e-5, final pose within 1e-5. The identical-input
+    steps above hold 1e-5."""
+    import copy
+
+    od, ctx, T_prev = state["od"], state["ctx"], state["T_prev"]
+    # both trackers swap lastNextImage <-> nextImage when so3 is on: re-run the init stages for every case
+    rgb_state = {lv: (od.buffer("nextImage", lv), od.buffer("lastNextImage", lv)) for lv in LEVELS}
+    To, tro = od.track(T_prev, **cfg)
+    Tp, trp = ctx.odom_track(T_prev, **cfg)
+    try:
+        assert len(tro) == len(trp), (len(tro), len(trp))
+        se3 = [t for t in tro if t["kind"] == 0]
+        b_scale = max(np.abs(t["lastb"]).max() for t in se3) if se3 else 1.0
+        for a, b in zip(trp, tro):
+            assert (a["kind"], a["level"], a["iter"]) == (b["kind"], b["level"], b["iter"])
+            if a["kind"] == 1:
+                assert a["so3_residual"][1] == b["so3_residual"][1]
+                assert rel_err(a["A_so3"], b["A_so3"]) < 5e-4 and rel_err(a["b_so3"], b["b_so3"]) < 5e-4
+            else:
+                assert abs(int(a["rgb_count"]) - int(b["rgb_count"])) <= max(3, 1e-3 * b["rgb_count"]), ("rgb_count", a["level"], a["iter"], a["rgb_count"], b["rgb_count"])
+                assert abs(a["icp_residual"][1] - b["icp_residual"][1]) <= max(3, 1e-3 * b["icp_residual"][1]), ("icp_count", a["level"], a["iter"])
+                assert rel_err(a["lastA"], b["lastA"]) < 5e-4, ("lastA", a["level"], a["iter"], rel_err(a["lastA"], b["lastA"]))
+                # b = J^T r cancels towards 0 as the iteration converges: 1e-4 relative to the scale of the system
+                assert np.abs(a["lastb"] - b["lastb"]).max() < 2e-3 * b_scale, ("lastb", a["level"], a["iter"])
+                assert np.abs(a["result"] - b["result"]).max() < (1e-4 if cfg.get("rgb_only") else 1e-5), ("result", a["level"], a["iter"], np.abs(a["result"] - b["result"]).max())
+        pose_tol = 2e-4 if cfg.get("rgb_only") else 1e-5  # photometric-only tracking is poorly conditioned
+        assert np.abs(Tp[:3, 3] - To[:3, 3]).max() < pose_tol
+        assert np.abs(Tp[:3, :3] - To[:3, :3]).max() < pose_tol
+    finally:
+        # undo the so3 handle swap on both sides so the module fixture stays consistent
+        if cfg.get("so3", True):
+            To2, _ = od.track(To, icp_weight=100.0, so3=True, pyramid=False, fast_odom=True)
+            Tp2, _ = ctx.odom_track(Tp, icp_weight=100.0, so3=True, pyramid=False, fast_odom=True)
