@@ -16,7 +16,9 @@ namespace efm {
 
 EFM_HD void mul3(const double* a, const double* b, double* c) {
   double r[9];
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j) r[i * 3 + j] = a[i * 3 + 0] * b[0 * 3 + j] + a[i * 3 + 1] * b[1 * 3 + j] + a[i * 3 + 2] * b[2 * 3 + j];
   for (int i = 0; i < 9; ++i) c[i] = r[i];
 }
@@ -27,9 +29,12 @@ EFM_HD void mulv3(const double* a, const double* v, double* o) {
 }
 EFM_HD void mul4(const double* a, const double* b, double* c) {
   double r[16];
+#pragma unroll
   for (int i = 0; i < 4; ++i)
+#pragma unroll
     for (int j = 0; j < 4; ++j) {
       double s = 0;
+#pragma unroll
       for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
       r[i * 4 + j] = s;
     }
@@ -93,9 +98,11 @@ template <typename T, int N>
 EFM_HD void ldlt_solve(const T* A_, const T* b_, T* x, T tiny) {
   T A[N][N];
   T bb[N];
+  T invd[N];
   int perm[N];
   for (int i = 0; i < N; ++i) {
     perm[i] = i;
+    invd[i] = T(0);
     bb[i] = b_[i];
     for (int j = 0; j < N; ++j) A[i][j] = A_[i * N + j];
   }
@@ -127,7 +134,9 @@ EFM_HD void ldlt_solve(const T* A_, const T* b_, T* x, T tiny) {
     }
     T d = A[k][k];
     if (d == T(0)) continue;
-    for (int i = k + 1; i < N; ++i) A[i][k] /= d;
+    const T rd = T(1) / d;  // one division per pivot (double division is a ~40-instruction dependent sequence on the GPU)
+    invd[k] = (fabs(d) > tiny) ? rd : T(0);
+    for (int i = k + 1; i < N; ++i) A[i][k] *= rd;
     for (int i = k + 1; i < N; ++i)
       for (int j = k + 1; j <= i; ++j) {
         A[i][j] -= A[i][k] * d * A[j][k];
@@ -140,7 +149,7 @@ EFM_HD void ldlt_solve(const T* A_, const T* b_, T* x, T tiny) {
     for (int j = 0; j < i; ++j) s -= A[i][j] * y[j];
     y[i] = s;
   }
-  for (int i = 0; i < N; ++i) y[i] = (fabs(A[i][i]) > tiny) ? y[i] / A[i][i] : T(0);
+  for (int i = 0; i < N; ++i) y[i] = y[i] * invd[i];
   T z[N];
   for (int i = N - 1; i >= 0; --i) {
     T s = y[i];
@@ -150,6 +159,52 @@ EFM_HD void ldlt_solve(const T* A_, const T* b_, T* x, T tiny) {
   for (int i = 0; i < N; ++i) x[perm[i]] = z[i];
 }
 EFM_HD void solve_sym6(const double* A, const double* b, double* x) { ldlt_solve<double, 6>(A, b, x, 1.0 / DBL_MAX); }
+
+// Register-resident L D L^T solve (no pivoting, fully unrolled: every index is a compile-time constant, so nothing goes
+// to local memory). For the symmetric positive-definite normal equations of the tracker this equals the pivoted solve to
+// rounding (~1e-13 relative); a vanishing pivot contributes 0 like Eigen::LDLT does. Used on the device, where a
+// single thread runs the solve and dependent local-memory traffic would dominate.
+template <int N>
+EFM_HD void ldlt_solve_unrolled(const double* A_, const double* b_, double* x) {
+  double L[N][N], D[N], invD[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double d = A_[j * N + j];
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if (k < j) d -= L[j][k] * L[j][k] * D[k];
+    D[j] = d;
+    invD[j] = (fabs(d) > 1.0 / DBL_MAX) ? 1.0 / d : 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (i > j) {
+        double v = A_[i * N + j];
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          if (k < j) v -= L[i][k] * L[j][k] * D[k];
+        L[i][j] = v * invD[j];
+      }
+  }
+  double y[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double v = b_[i];
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if (k < i) v -= L[i][k] * y[k];
+    y[i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] *= invD[i];
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    double v = y[i];
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      if (k > i) v -= L[k][i] * x[k];
+    x[i] = v;
+  }
+}
 EFM_HD void solve_sym3f(const float* A, const float* b, float* x) { ldlt_solve<float, 3>(A, b, x, 1.0f / FLT_MAX); }
 
 EFM_HD void rodrigues(const double* src, double* dst) {

@@ -1,0 +1,997 @@
+// Reductions of the tracking half: the geometric (ICP) and photometric 6x6 systems, the photometric correspondence
+// pass and the SO(3) pre-alignment, each as ONE launch (per-CTA shuffle tree -> partials -> last-CTA final sum in double),
+// plus the device-resident Gauss-Newton state machine that replaces the reference's host loop
+// (Core/Utils/RGBDOdometry.cpp:259-571; kernels Core/Cuda/reduce.cu).
+//
+// This translation unit is compiled WITH fused multiply-add contraction (the reference build has it on as well): the
+// sums are order-dependent anyway, and FMA removes about a third of the instructions of the per-pixel rows. The
+// per-pixel image/pyramid kernels live in ef_track.cu, compiled with --fmad=false for bit-reproducibility.
+#include <float.h>
+#include <stddef.h>
+#include <stdio.h>
+
+#include "ef_device.cuh"
+#include "ef_dmath.cuh"
+#include "ef_internal.h"
+
+using namespace ef;
+
+namespace ef {
+int launch_sobel(EfContext* ctx, int which);
+}
+
+// =============================================================================================
+// Gauss-Newton state machine (device side)
+// =============================================================================================
+
+__device__ __forceinline__ void level_intr(const GNState* gn, int level, float& fx, float& fy, float& cx, float& cy) {
+  const int div = 1 << level;  // CameraModel::operator()(level), reference types.cuh:92-95
+  fx = gn->fx / div;
+  fy = gn->fy / div;
+  cx = gn->cx / div;
+  cy = gn->cy / div;
+}
+
+// K and K^-1 of a pyramid level in double; the pinhole inverse is closed-form (no general 3x3 inverse on the device)
+__device__ __forceinline__ void level_K(const GNState* gn, int level, double* K, double* Kinv) {
+  float lfx, lfy, lcx, lcy;
+  level_intr(gn, level, lfx, lfy, lcx, lcy);
+  const double fx = lfx, fy = lfy, cx = lcx, cy = lcy;
+  K[0] = fx; K[1] = 0; K[2] = cx; K[3] = 0; K[4] = fy; K[5] = cy; K[6] = 0; K[7] = 0; K[8] = 1;
+  const double ifx = 1.0 / fx, ify = 1.0 / fy;
+  Kinv[0] = ifx; Kinv[1] = 0; Kinv[2] = -cx * ifx; Kinv[3] = 0; Kinv[4] = ify; Kinv[5] = -cy * ify; Kinv[6] = 0; Kinv[7] = 0; Kinv[8] = 1;
+}
+
+// warp matrices for the next photometric residual pass (RGBDOdometry.cpp:407-417). resultRt is a rigid transform
+// (products of Rodrigues rotations and translations), so its inverse is [R^T | -R^T t]: no 4x4 elimination.
+__device__ void gn_prepare_warp(GNState* gn, int level) {
+  double K[9], Kinv[9], Rt[16];
+  level_K(gn, level, K, Kinv);
+  efm::se3_inverse(gn->resultRt, Rt);
+  double R[9] = {Rt[0], Rt[1], Rt[2], Rt[4], Rt[5], Rt[6], Rt[8], Rt[9], Rt[10]};
+  double tmp[9], KRK_inv[9];
+  efm::mul3(K, R, tmp);
+  efm::mul3(tmp, Kinv, KRK_inv);
+  for (int k = 0; k < 9; ++k) gn->krkinv[k] = (float)KRK_inv[k];
+  double tv[3] = {Rt[3], Rt[7], Rt[11]}, Kt[3];
+  efm::mulv3(K, tv, Kt);
+  for (int k = 0; k < 3; ++k) gn->kt[k] = (float)Kt[k];
+}
+
+// homography etc. for the next SO3 pass (RGBDOdometry.cpp:309-321)
+__device__ void so3_prepare(GNState* gn) {
+  double K[9], Kinv[9], tmp[9], H[9];
+  level_K(gn, 2, K, Kinv);
+  efm::mul3(K, gn->resultR, tmp);
+  efm::mul3(tmp, Kinv, H);
+  for (int k = 0; k < 9; ++k) {
+    gn->imageBasis[k] = (float)H[k];
+    gn->kinv[k] = (float)Kinv[k];
+    gn->krlr[k] = (float)tmp[k];
+  }
+}
+
+// start of getIncrementalTransformation (RGBDOdometry.cpp:266-273,284-303)
+__global__ void k_gn_begin(GNState* gn, int rgbOnly, float icpWeight, int so3) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  gn->rgbOnly = rgbOnly;
+  gn->icpWeight = icpWeight;
+  gn->icp = (!rgbOnly && icpWeight > 0) ? 1 : 0;
+  gn->rgb = (rgbOnly || icpWeight < 100) ? 1 : 0;
+  gn->so3 = so3;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) gn->Rprev[r * 3 + c] = (float)gn->T_wc[r * 4 + c];
+    gn->tprev[r] = (float)gn->T_wc[r * 4 + 3];
+  }
+  for (int k = 0; k < 9; ++k) gn->Rcurr[k] = gn->Rprev[k];
+  for (int k = 0; k < 3; ++k) gn->tcurr[k] = gn->tprev[k];
+  efm::inv3<float>(gn->Rprev, gn->Rprev_inv);
+  const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int k = 0; k < 9; ++k) {
+    gn->resultR[k] = I3[k];
+    gn->lastResultR[k] = I3[k];
+    gn->R_lr[k] = (float)I3[k];
+  }
+  gn->so3_lastError = FLT_MAX / 2;
+  gn->so3_lastCount = FLT_MAX / 2;
+  gn->so3_done = 0;
+  gn->break_level = -1;
+  gn->trace_n = 0;
+  if (so3) so3_prepare(gn);
+}
+
+// after the SO3 loop: seed resultRt (RGBDOdometry.cpp:379-388) and prepare the first SE3 iteration
+__global__ void k_gn_seed(GNState* gn, int first_level) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int k = 0; k < 16; ++k) gn->resultRt[k] = (k % 5 == 0) ? 1.0 : 0.0;
+  if (gn->so3)
+    for (int x = 0; x < 3; x++)
+      for (int y = 0; y < 3; y++) gn->resultRt[x * 4 + y] = gn->resultR[x * 3 + y];
+  gn->lastRGBError = FLT_MAX;
+  if (!gn->rgb) {
+    gn->rgbSize = 0;
+    gn->sigma = 0;
+    gn->sigmaVal = 0.f;  // sqrt((0.f/0 == 0) ? 1 : 0)
+    gn->lastRGBError = 0.f;
+    gn->lastRGBCount = 0.f;
+  }
+  gn_prepare_warp(gn, first_level);
+}
+
+// end of getIncrementalTransformation (RGBDOdometry.cpp:555-570) + velocity weighting (ElasticFusion.cpp:369-383)
+__global__ void k_gn_finish(GNState* gn, float weightMultiplier, int have_track) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double Tprev[16];
+  for (int k = 0; k < 16; ++k) Tprev[k] = gn->T_wc[k];
+  if (have_track) {
+    if (gn->rgb) {
+      const float dx = gn->tcurr[0] - gn->tprev[0], dy = gn->tcurr[1] - gn->tprev[1], dz = gn->tcurr[2] - gn->tprev[2];
+      if (sqrtf(dx * dx + dy * dy + dz * dz) > 0.3) {
+        for (int k = 0; k < 9; ++k) gn->Rcurr[k] = gn->Rprev[k];
+        for (int k = 0; k < 3; ++k) gn->tcurr[k] = gn->tprev[k];
+      }
+    }
+    double Rc[9], Ro[9];
+    for (int k = 0; k < 9; ++k) Rc[k] = gn->Rcurr[k];
+    efm::polar_orthogonal(Rc, Ro);
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) gn->T_wc[r * 4 + c] = Ro[r * 3 + c];
+      gn->T_wc[r * 4 + 3] = (double)gn->tcurr[r];
+    }
+    gn->T_wc[12] = gn->T_wc[13] = gn->T_wc[14] = 0;
+    gn->T_wc[15] = 1;
+  }
+  // weighting from T_curr_prev = T_wc_curr^-1 * T_wc_prev; Tprev is reconstructed from Rprev/tprev only when tracking
+  // ran — otherwise the caller stored the previous pose in resultRt before overwriting T_wc.
+  double inv[16], Tcp[16];
+  efm::se3_inverse(gn->T_wc, inv);
+  if (!have_track)
+    for (int k = 0; k < 16; ++k) Tprev[k] = gn->resultRt[k];
+  efm::mul4(inv, Tprev, Tcp);
+  const double tn = sqrt(Tcp[3] * Tcp[3] + Tcp[7] * Tcp[7] + Tcp[11] * Tcp[11]);
+  const double ln = efm::se3_log_norm(Tcp);
+  float weighting = (float)fmax(tn, ln);
+  const float largest = 0.01f, minWeight = 0.5f;
+  if (weighting > largest) weighting = largest;
+  gn->weighting = fmaxf(1.0f - (weighting / largest), minWeight) * weightMultiplier;
+}
+
+// k_gn_finish needs the pre-tracking pose; stash it (tracking overwrites T_wc only at the end, so this is only needed
+// for the in_T_wc path where the host replaces the pose).
+__global__ void k_set_pose(GNState* gn, const double* T_new) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int k = 0; k < 16; ++k) {
+    gn->resultRt[k] = gn->T_wc[k];
+    gn->T_wc[k] = T_new[k];
+  }
+}
+
+// unpack the reference's 29-float JtJJtrSE3 into A (6x6, symmetric) and b (reduce.cu:388-400)
+__device__ __forceinline__ void unpack_se3(const float* h, float* A, float* b) {
+  int shift = 0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 7; ++j) {
+      const float value = h[shift++];
+      if (j == 6)
+        b[i] = value;
+      else
+        A[j * 6 + i] = A[i * 6 + j] = value;
+    }
+}
+
+// Shared-memory scratch of the update kernel
+struct GnScratch {
+  double dsm[32][64];  // per-slice partial sums (32 slices x 64 values)
+  float sums[64];      // reduced systems: [0,29) geometric, [32,61) photometric
+  float A_icp[36], b_icp[8], A_rgb[36], b_rgb[8];
+  double lastA[36], lastb[8], result[8];
+  double rRt[16], nrt[16], upd[16];
+  double K[9], Kinv[9], Rt[16], tmp[9];
+  float Rprev[9], tprev[3], iR[9], it[3];
+};
+
+// packed index k (reference JtJJtrSE3 order, types.cuh:98-104) -> (i, j) with j == 6 meaning the b column
+__device__ __forceinline__ void se3_unpack_index(int k, int& i, int& j) {
+  int row = 0, start = 0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const int len = 7 - r;
+    if (row == r && k >= start + len) {
+      start += len;
+      row = r + 1;
+    }
+  }
+  i = row;
+  j = row + (k - start);
+}
+
+// One SE3 Gauss-Newton update (RGBDOdometry.cpp:492-551) executed cooperatively by one warp: the independent pieces
+// (unpacking, lastA/lastb, 4x4 and 3x3 products, trace) are spread over the lanes; only the 6x6 LDL^T and the Rodrigues
+// formula run on lane 0. All operands live in shared memory.
+__device__ void gn_update_warp(const OdomDev& od, GnScratch& S, int level, int iter, int next_level) {
+  GNState* gn = od.gn;
+  const int lane = threadIdx.x;
+  // stage state
+  if (lane < 16) S.rRt[lane] = gn->resultRt[lane];
+  if (lane < 9) S.Rprev[lane] = gn->Rprev[lane];
+  if (lane < 3) S.tprev[lane] = gn->tprev[lane];
+  const int icp = gn->icp, rgb = gn->rgb;
+  const double w = gn->icpWeight;
+  if (lane < 27) {
+    int i, j;
+    se3_unpack_index(lane, i, j);
+    const float vi = S.sums[lane], vr = S.sums[32 + lane];
+    if (j == 6) {
+      S.b_icp[i] = vi;
+      S.b_rgb[i] = vr;
+    } else {
+      S.A_icp[i * 6 + j] = S.A_icp[j * 6 + i] = vi;
+      S.A_rgb[i * 6 + j] = S.A_rgb[j * 6 + i] = vr;
+    }
+  }
+  __syncwarp();
+  for (int k = lane; k < 36; k += 32) {
+    double a;
+    if (icp && rgb)
+      a = (double)S.A_rgb[k] + w * w * (double)S.A_icp[k];
+    else if (icp)
+      a = S.A_icp[k];
+    else
+      a = S.A_rgb[k];
+    S.lastA[k] = a;
+    gn->lastA[k] = a;
+  }
+  if (lane < 6) {
+    double b;
+    if (icp && rgb)
+      b = (double)S.b_rgb[lane] + w * (double)S.b_icp[lane];
+    else if (icp)
+      b = S.b_icp[lane];
+    else
+      b = S.b_rgb[lane];
+    S.lastb[lane] = b;
+    gn->lastb[lane] = b;
+  }
+  __syncwarp();
+  const float res0 = S.sums[27], res1 = S.sums[28];
+  if (lane == 0) {
+    gn->lastICPError = sqrtf(res0) / res1;
+    gn->lastICPCount = res1;
+    double A[36], b[6], x[6];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) A[k] = S.lastA[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) b[k] = S.lastb[k];
+    efm::ldlt_solve_unrolled<6>(A, b, x);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) S.result[k] = x[k];
+    // OdometryProvider::computeUpdateSE3 (OdometryProvider.h:73-96)
+    double rvec[3] = {x[3], x[4], x[5]}, Rd[9];
+    efm::rodrigues(rvec, Rd);
+    const double upd[16] = {Rd[0], Rd[1], Rd[2], x[0], Rd[3], Rd[4], Rd[5], x[1], Rd[6], Rd[7], Rd[8], x[2], 0, 0, 0, 1};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) S.upd[k] = upd[k];
+  }
+  __syncwarp();
+  if (lane < 16) {
+    const int r = lane >> 2, c = lane & 3;
+    double acc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc += S.upd[r * 4 + k] * S.rRt[k * 4 + c];
+    S.nrt[lane] = acc;
+    gn->resultRt[lane] = acc;
+  }
+  // trace (independent of the rest)
+  int slot = -1;
+  if (od.trace) {
+    const int tn = gn->trace_n;
+    if (tn < MAX_TRACE) slot = tn;
+  }
+  __syncwarp();
+  if (slot >= 0) {
+    EfSolveTrace& t = od.trace[slot];
+    for (int k = lane; k < 36; k += 32) {
+      t.A_icp[k] = S.A_icp[k];
+      t.A_rgb[k] = S.A_rgb[k];
+      t.lastA[k] = S.lastA[k];
+    }
+    if (lane < 6) {
+      t.b_icp[lane] = S.b_icp[lane];
+      t.b_rgb[lane] = S.b_rgb[lane];
+      t.lastb[lane] = S.lastb[lane];
+      t.result[lane] = S.result[lane];
+    }
+    if (lane == 0) {
+      t.kind = 0;
+      t.level = level;
+      t.iter = iter;
+      t.rgb_count = gn->rgbSize;
+      t.rgb_sigma = gn->sigma;
+      t.sigma_val = gn->sigmaVal;
+      t.icp_residual[0] = res0;
+      t.icp_residual[1] = res1;
+      gn->trace_n = slot + 1;
+    }
+  }
+  // currentT = T_prev * rgbOdom^-1 in float (RGBDOdometry.cpp:543-551): iR = R^T, it = -(R^T t)
+  if (lane < 9) {
+    const int r = lane / 3, c = lane % 3;
+    S.iR[lane] = (float)S.nrt[c * 4 + r];
+  }
+  __syncwarp();
+  if (lane < 3) {
+    const float ot0 = (float)S.nrt[3], ot1 = (float)S.nrt[7], ot2 = (float)S.nrt[11];
+    S.it[lane] = -(S.iR[lane * 3 + 0] * ot0 + S.iR[lane * 3 + 1] * ot1 + S.iR[lane * 3 + 2] * ot2);
+  }
+  __syncwarp();
+  if (lane < 9) {
+    const int r = lane / 3, c = lane % 3;
+    gn->Rcurr[lane] = S.Rprev[r * 3 + 0] * S.iR[0 * 3 + c] + S.Rprev[r * 3 + 1] * S.iR[1 * 3 + c] + S.Rprev[r * 3 + 2] * S.iR[2 * 3 + c];
+  } else if (lane < 12) {
+    const int r = lane - 9;
+    gn->tcurr[r] = (S.Rprev[r * 3 + 0] * S.it[0] + S.Rprev[r * 3 + 1] * S.it[1] + S.Rprev[r * 3 + 2] * S.it[2]) + S.tprev[r];
+  }
+  // next iteration's warp matrices (RGBDOdometry.cpp:407-417): KRK^-1 and K t of resultRt^-1 = [R^T | -R^T t]
+  if (next_level >= 0) {
+    if (lane == 0) level_K(gn, next_level, S.K, S.Kinv);
+    if (lane < 9) {
+      const int r = lane / 3, c = lane % 3;
+      S.Rt[r * 4 + c] = S.nrt[c * 4 + r];
+    }
+    __syncwarp();
+    if (lane < 3) S.Rt[lane * 4 + 3] = -(S.Rt[lane * 4 + 0] * S.nrt[3] + S.Rt[lane * 4 + 1] * S.nrt[7] + S.Rt[lane * 4 + 2] * S.nrt[11]);
+    __syncwarp();
+    if (lane < 9) {
+      const int r = lane / 3, c = lane % 3;
+      S.tmp[lane] = S.K[r * 3 + 0] * S.Rt[0 * 4 + c] + S.K[r * 3 + 1] * S.Rt[1 * 4 + c] + S.K[r * 3 + 2] * S.Rt[2 * 4 + c];
+    }
+    __syncwarp();
+    if (lane < 9) {
+      const int r = lane / 3, c = lane % 3;
+      gn->krkinv[lane] = (float)(S.tmp[r * 3 + 0] * S.Kinv[0 * 3 + c] + S.tmp[r * 3 + 1] * S.Kinv[1 * 3 + c] + S.tmp[r * 3 + 2] * S.Kinv[2 * 3 + c]);
+    } else if (lane < 12) {
+      const int r = lane - 9;
+      gn->kt[r] = (float)(S.K[r * 3 + 0] * S.Rt[3] + S.K[r * 3 + 1] * S.Rt[7] + S.K[r * 3 + 2] * S.Rt[11]);
+    }
+  }
+}
+
+// =============================================================================================
+// reductions
+// =============================================================================================
+
+constexpr int SE3_THREADS = 128;  // 640x480/4 pixel groups = 600 CTAs of 128: one resident wave at 5 CTAs/SM (<=102 registers)
+constexpr int SE3_CTAS_PER_SM = 5;
+constexpr int RES_THREADS = 256;
+constexpr int RES_CTAS_PER_SM = 3;
+
+// final cross-CTA sum of `nvals` (<=32) floats at `off` inside each CTA's partial; result (float) to dst[0..nvals)
+template <int THREADS>
+__device__ __forceinline__ void final_sum(const float* partials, int nblocks, int off, int nvals, float* dst, double* dsm) {
+  const int v = threadIdx.x & 31, s = threadIdx.x >> 5;
+  double acc = 0;
+  if (v < nvals) {
+    int b = s;
+    // 4 independent loads in flight per step
+    for (; b + 3 * (THREADS / 32) < nblocks; b += 4 * (THREADS / 32)) {
+      const float p0 = partials[(size_t)b * PARTIAL_STRIDE + off + v];
+      const float p1 = partials[(size_t)(b + THREADS / 32) * PARTIAL_STRIDE + off + v];
+      const float p2 = partials[(size_t)(b + 2 * (THREADS / 32)) * PARTIAL_STRIDE + off + v];
+      const float p3 = partials[(size_t)(b + 3 * (THREADS / 32)) * PARTIAL_STRIDE + off + v];
+      acc += ((double)p0 + (double)p1) + ((double)p2 + (double)p3);
+    }
+    for (; b < nblocks; b += THREADS / 32) acc += (double)partials[(size_t)b * PARTIAL_STRIDE + off + v];
+  }
+  dsm[s * 32 + v] = acc;
+  __syncthreads();
+  if (s == 0 && v < nvals) {
+    double t = 0;
+#pragma unroll
+    for (int k = 0; k < THREADS / 32; ++k) t += dsm[k * 32 + v];
+    dst[v] = (float)t;
+  }
+  __syncthreads();
+}
+
+// ---- geometric row: ICPReduction::search/getProducts (reduce.cu:224-331) ------------------------------------
+struct IcpFrame {
+  m33 Rcurr, Rprev_inv;
+  f3 tcurr, tprev;
+  float fx, fy, cx, cy;
+  float distThres, angleThres;
+};
+
+__device__ __forceinline__ void accumulate29(const float row[7], float (&acc)[29]) {
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = i; j < 7; ++j) acc[k++] += row[i] * row[j];
+  acc[27] += row[6] * row[6];
+  acc[28] += 1.0f;
+}
+
+// projective association of one live vertex: returns the model pixel (linear index) or -1
+__device__ __forceinline__ int icp_project(const IcpFrame& F, const f3& vcurr, int rows, int cols, f3& vcurr_g, f3& vcurr_cp) {
+  vcurr_g = mul(F.Rcurr, vcurr) + F.tcurr;
+  vcurr_cp = mul(F.Rprev_inv, vcurr_g - F.tprev);
+  const int ux = __float2int_rn(vcurr_cp.x * F.fx / vcurr_cp.z + F.cx);
+  const int uy = __float2int_rn(vcurr_cp.y * F.fy / vcurr_cp.z + F.cy);
+  if (ux < 0 || uy < 0 || ux >= cols || uy >= rows || vcurr_cp.z < 0) return -1;
+  return uy * cols + ux;
+}
+
+__device__ __forceinline__ void icp_accumulate(const IcpFrame& F, const f3& vcurr_g, const f3& s_cp, const f3& ncurr, const f3& vprev_g,
+                                               const f3& nprev_g, float (&acc)[29]) {
+  const f3 ncurr_g = mul(F.Rcurr, ncurr);
+  const float dist = norm(vprev_g - vcurr_g);
+  const float sine = norm(cross(ncurr_g, nprev_g));
+  if (!(sine < F.angleThres && dist <= F.distThres && !isnan(ncurr.x) && !isnan(nprev_g.x))) return;
+  const f3 d_cp = mul(F.Rprev_inv, vprev_g - F.tprev);
+  const f3 n_cp = mul(F.Rprev_inv, nprev_g);
+  const f3 c = cross(s_cp, n_cp);
+  const float row[7] = {n_cp.x, n_cp.y, n_cp.z, c.x, c.y, c.z, dot(n_cp, s_cp - d_cp)};
+  accumulate29(row, acc);
+}
+
+// ---- photometric row: RGBReduction::getProducts (reduce.cu:419-480); cloud point recomputed from lastDepth
+//      with projectPointsKernel's arithmetic (cudafuncs.cu:670-688) ----------------------------------------
+__device__ __forceinline__ void rgb_accumulate(const DataTerm& corresp, float sigma, float z, float dx_raw, float dy_raw, float fx, float fy,
+                                               float cx, float cy, float sobelScale, float (&acc)[29]) {
+  float w = sigma + fabsf(corresp.diff);
+  w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
+  if (sigma == -1) w = 1;
+  float row[7];
+  row[6] = -w * corresp.diff;
+  const float invFx = 1.0f / fx, invFy = 1.0f / fy;
+  const f3 cp = mk3((float)((corresp.zero_x - cx) * z * invFx), (float)((corresp.zero_y - cy) * z * invFy), z);
+  const float invz = (float)(1.0 / (double)cp.z);
+  const float dI_dx_val = w * sobelScale * dx_raw;
+  const float dI_dy_val = w * sobelScale * dy_raw;
+  const float v0 = dI_dx_val * fx * invz;
+  const float v1 = dI_dy_val * fy * invz;
+  const float v2 = -(v0 * cp.x + v1 * cp.y) * invz;
+  row[0] = v0;
+  row[1] = v1;
+  row[2] = v2;
+  row[3] = -cp.z * v1 + cp.y * v2;
+  row[4] = cp.z * v0 - cp.x * v2;
+  row[5] = -cp.y * v0 + cp.x * v1;
+  accumulate29(row, acc);
+}
+
+// One Gauss-Newton step: geometric and/or photometric 6x6 systems reduced in ONE launch (icpStep + rgbStep,
+// reduce.cu:333-401,502-550). The last CTA sums the per-CTA partials in double; k_gn_update then solves.
+__global__ void __launch_bounds__(SE3_THREADS, SE3_CTAS_PER_SM) k_se3_step(OdomDev od, int level, int next_level, int do_icp, int do_rgb, int solve) {
+  GNState* gn = od.gn;
+  if (solve && gn->break_level == level) return;  // rgbOnly `break`: rest of the level is skipped
+  __shared__ float sred[29 * (SE3_THREADS / 32)];
+  const int rows = od.rows[level], cols = od.cols[level];
+  const int N = rows * cols;
+  const size_t plane = (size_t)N;
+  float lfx, lfy, lcx, lcy;
+  {
+    const int div = 1 << level;
+    lfx = gn->fx / div;
+    lfy = gn->fy / div;
+    lcx = gn->cx / div;
+    lcy = gn->cy / div;
+  }
+  float* my_partial = od.partials + (size_t)blockIdx.x * PARTIAL_STRIDE;
+
+  if (do_icp) {
+    IcpFrame F;
+    F.Rcurr = load_m33(gn->Rcurr);
+    F.Rprev_inv = load_m33(gn->Rprev_inv);
+    F.tcurr = mk3(gn->tcurr[0], gn->tcurr[1], gn->tcurr[2]);
+    F.tprev = mk3(gn->tprev[0], gn->tprev[1], gn->tprev[2]);
+    F.fx = lfx;
+    F.fy = lfy;
+    F.cx = lcx;
+    F.cy = lcy;
+    F.distThres = od.distThres;
+    F.angleThres = od.angleThres;
+    float acc[29];
+#pragma unroll
+    for (int k = 0; k < 29; ++k) acc[k] = 0.f;
+    const float* __restrict__ vc = od.vmap_curr[level];
+    const float* __restrict__ nc = od.nmap_curr[level];
+    const float* __restrict__ vp = od.vmap_g_prev[level];
+    const float* __restrict__ np_ = od.nmap_g_prev[level];
+    if ((cols & 3) == 0) {
+      // 4 consecutive pixels per thread: six 128-bit coalesced loads for the live maps, the model maps gathered in pairs
+      const int ngroups = N >> 2;
+      for (int g = blockIdx.x * SE3_THREADS + threadIdx.x; g < ngroups; g += gridDim.x * SE3_THREADS) {
+        const int i0 = g << 2;
+        const float4 vx4 = *reinterpret_cast<const float4*>(vc + i0);
+        const float4 vy4 = *reinterpret_cast<const float4*>(vc + plane + i0);
+        const float4 vz4 = *reinterpret_cast<const float4*>(vc + 2 * plane + i0);
+        const float4 nx4 = *reinterpret_cast<const float4*>(nc + i0);
+        const float4 ny4 = *reinterpret_cast<const float4*>(nc + plane + i0);
+        const float4 nz4 = *reinterpret_cast<const float4*>(nc + 2 * plane + i0);
+        const float vxs[4] = {vx4.x, vx4.y, vx4.z, vx4.w}, vys[4] = {vy4.x, vy4.y, vy4.z, vy4.w}, vzs[4] = {vz4.x, vz4.y, vz4.z, vz4.w};
+        const float nxs[4] = {nx4.x, nx4.y, nx4.z, nx4.w}, nys[4] = {ny4.x, ny4.y, ny4.z, ny4.w}, nzs[4] = {nz4.x, nz4.y, nz4.z, nz4.w};
+#pragma unroll
+        for (int h = 0; h < 4; h += 2) {
+          f3 vg0, vg1, cp0, cp1;
+          const int q0 = icp_project(F, mk3(vxs[h], vys[h], vzs[h]), rows, cols, vg0, cp0);
+          const int q1 = icp_project(F, mk3(vxs[h + 1], vys[h + 1], vzs[h + 1]), rows, cols, vg1, cp1);
+          const int a0 = q0 < 0 ? 0 : q0, a1 = q1 < 0 ? 0 : q1;
+          const float p00 = __ldg(vp + a0), p01 = __ldg(vp + plane + a0), p02 = __ldg(vp + 2 * plane + a0);
+          const float p03 = __ldg(np_ + a0), p04 = __ldg(np_ + plane + a0), p05 = __ldg(np_ + 2 * plane + a0);
+          const float p10 = __ldg(vp + a1), p11 = __ldg(vp + plane + a1), p12 = __ldg(vp + 2 * plane + a1);
+          const float p13 = __ldg(np_ + a1), p14 = __ldg(np_ + plane + a1), p15 = __ldg(np_ + 2 * plane + a1);
+          if (q0 >= 0) icp_accumulate(F, vg0, cp0, mk3(nxs[h], nys[h], nzs[h]), mk3(p00, p01, p02), mk3(p03, p04, p05), acc);
+          if (q1 >= 0) icp_accumulate(F, vg1, cp1, mk3(nxs[h + 1], nys[h + 1], nzs[h + 1]), mk3(p10, p11, p12), mk3(p13, p14, p15), acc);
+        }
+      }
+    } else {
+      for (int i = blockIdx.x * SE3_THREADS + threadIdx.x; i < N; i += gridDim.x * SE3_THREADS) {
+        f3 vg, cp;
+        const int q = icp_project(F, mk3(vc[i], vc[i + plane], vc[i + 2 * plane]), rows, cols, vg, cp);
+        if (q >= 0)
+          icp_accumulate(F, vg, cp, mk3(nc[i], nc[i + plane], nc[i + 2 * plane]), mk3(vp[q], vp[q + plane], vp[q + 2 * plane]),
+                         mk3(np_[q], np_[q + plane], np_[q + 2 * plane]), acc);
+      }
+    }
+    block_reduce_sum<29, SE3_THREADS>(acc, sred);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < 29; ++k) my_partial[k] = acc[k];
+    }
+    __syncthreads();
+  }
+  if (do_rgb) {
+    const float sigma = gn->sigmaVal;
+    const DataTerm* __restrict__ corres = od.corres[level];
+    const float* __restrict__ lastDepth = od.lastDepth[level];
+    const int16_t* __restrict__ dIdx = od.dIdx[level];
+    const int16_t* __restrict__ dIdy = od.dIdy[level];
+    float acc[29];
+#pragma unroll
+    for (int k = 0; k < 29; ++k) acc[k] = 0.f;
+    // 2 DataTerms (16 B each, one 128-bit load) per thread per iteration, their gathers issued together
+    const int4* __restrict__ c4 = reinterpret_cast<const int4*>(corres);
+    for (int i = (blockIdx.x * SE3_THREADS + threadIdx.x) * 2; i < N; i += gridDim.x * SE3_THREADS * 2) {
+      const int4 r0 = c4[i];
+      const int4 r1 = (i + 1 < N) ? c4[i + 1] : make_int4(0, 0, 0, 0);
+      DataTerm d0, d1;
+      d0.zero_x = (short)(r0.x & 0xffff);
+      d0.zero_y = (short)(r0.x >> 16);
+      d0.one_x = (short)(r0.y & 0xffff);
+      d0.one_y = (short)(r0.y >> 16);
+      d0.diff = __int_as_float(r0.z);
+      d0.valid = r0.w;
+      d1.zero_x = (short)(r1.x & 0xffff);
+      d1.zero_y = (short)(r1.x >> 16);
+      d1.one_x = (short)(r1.y & 0xffff);
+      d1.one_y = (short)(r1.y >> 16);
+      d1.diff = __int_as_float(r1.z);
+      d1.valid = r1.w;
+      const size_t z0 = d0.valid ? (size_t)d0.zero_y * cols + d0.zero_x : 0, o0 = d0.valid ? (size_t)d0.one_y * cols + d0.one_x : 0;
+      const size_t z1 = d1.valid ? (size_t)d1.zero_y * cols + d1.zero_x : 0, o1 = d1.valid ? (size_t)d1.one_y * cols + d1.one_x : 0;
+      const float zz0 = __ldg(lastDepth + z0), zz1 = __ldg(lastDepth + z1);
+      const float gx0 = (float)__ldg(dIdx + o0), gy0 = (float)__ldg(dIdy + o0);
+      const float gx1 = (float)__ldg(dIdx + o1), gy1 = (float)__ldg(dIdy + o1);
+      if (d0.valid) rgb_accumulate(d0, sigma, zz0, gx0, gy0, lfx, lfy, lcx, lcy, od.sobelScale, acc);
+      if (d1.valid) rgb_accumulate(d1, sigma, zz1, gx1, gy1, lfx, lfy, lcx, lcy, od.sobelScale, acc);
+    }
+    block_reduce_sum<29, SE3_THREADS>(acc, sred);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < 29; ++k) my_partial[32 + k] = acc[k];
+    }
+  }
+}
+
+// Final cross-CTA sums of one step (double, fixed order) + the serial part of the Gauss-Newton iteration, as one 1-CTA
+// launch: 32 warps sum 32 interleaved slices of the per-CTA partials with 4 loads in flight each, then warp 0 solves.
+// (The reference does this with reduceSum<<<1,1024>>>, cudaDeviceSynchronize, a blocking D2H and Eigen on the host.)
+__global__ void __launch_bounds__(1024) k_gn_update(OdomDev od, int level, int iter, int next_level, int nblocks, int do_icp, int do_rgb, int solve) {
+  __shared__ GnScratch S;
+  GNState* gn = od.gn;
+  if (solve && gn->break_level == level) {
+    // rgbOnly `break`: the first iteration of the next level still needs its warp matrices
+    if (threadIdx.x == 0 && next_level >= 0 && next_level != level) gn_prepare_warp(gn, next_level);
+    return;
+  }
+  const int v = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  double a0 = 0, a1 = 0;
+  {
+    const float* p = od.partials;
+    int b = sl;
+    for (; b + 96 < nblocks; b += 128) {
+      const float x0 = p[(size_t)b * PARTIAL_STRIDE + v], x1 = p[(size_t)(b + 32) * PARTIAL_STRIDE + v];
+      const float x2 = p[(size_t)(b + 64) * PARTIAL_STRIDE + v], x3 = p[(size_t)(b + 96) * PARTIAL_STRIDE + v];
+      const float y0 = p[(size_t)b * PARTIAL_STRIDE + 32 + v], y1 = p[(size_t)(b + 32) * PARTIAL_STRIDE + 32 + v];
+      const float y2 = p[(size_t)(b + 64) * PARTIAL_STRIDE + 32 + v], y3 = p[(size_t)(b + 96) * PARTIAL_STRIDE + 32 + v];
+      a0 += ((double)x0 + (double)x1) + ((double)x2 + (double)x3);
+      a1 += ((double)y0 + (double)y1) + ((double)y2 + (double)y3);
+    }
+    for (; b < nblocks; b += 32) {
+      a0 += (double)p[(size_t)b * PARTIAL_STRIDE + v];
+      a1 += (double)p[(size_t)b * PARTIAL_STRIDE + 32 + v];
+    }
+  }
+  S.dsm[sl][v] = do_icp ? a0 : 0.0;
+  S.dsm[sl][32 + v] = do_rgb ? a1 : 0.0;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    double t = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += S.dsm[k][threadIdx.x];
+    const float f = (float)t;
+    S.sums[threadIdx.x] = f;
+    if (threadIdx.x < 32)
+      gn->sum_icp[threadIdx.x] = f;
+    else
+      gn->sum_rgb[threadIdx.x - 32] = f;
+  }
+  __syncthreads();
+  if (!solve || threadIdx.x >= 32) return;
+  gn_update_warp(od, S, level, iter, next_level);
+}
+
+// Photometric correspondences + {count, sum diff^2}: RGBResidual / computeRgbResidual (reduce.cu:603-787).
+// The last CTA also derives sigma / rgbError exactly as the host does (RGBDOdometry.cpp:442-455, incl. the
+// operator-precedence quirk) so the following step launch needs nothing from the host.
+__global__ void __launch_bounds__(RES_THREADS, RES_CTAS_PER_SM) k_rgb_residual(OdomDev od, int level, int iter, int finalize) {
+  GNState* gn = od.gn;
+  if (finalize && gn->break_level == level) return;
+  __shared__ int sred_i[2 * (RES_THREADS / 32)];
+  const int rows = od.rows[level], cols = od.cols[level];
+  const int N = rows * cols;
+  const m33 krkinv = load_m33(gn->krkinv);
+  const f3 kt = mk3(gn->kt[0], gn->kt[1], gn->kt[2]);
+  const float minScale = od.minScale[level];
+  const int16_t* __restrict__ dIdx = od.dIdx[level];
+  const int16_t* __restrict__ dIdy = od.dIdy[level];
+  const float* __restrict__ lastDepth = od.lastDepth[level];
+  const float* __restrict__ nextDepth = od.nextDepth[level];
+  const uint8_t* __restrict__ lastImage = od.lastImage[level];
+  const uint8_t* __restrict__ nextImage = od.nextImage[level];
+  int4* __restrict__ corres4 = reinterpret_cast<int4*>(od.corres[level]);
+  unsigned int cnt = 0, sig = 0;
+  for (int k = blockIdx.x * RES_THREADS + threadIdx.x; k < N; k += gridDim.x * RES_THREADS) {
+    const int i = k / cols, j0 = k - i * cols;
+    // everything that does not depend on the warp is loaded up front, branch-free, so the loads overlap
+    const int valx = dIdx[k], valy = dIdy[k];
+    const float d1 = nextDepth[k];
+    const int nI = nextImage[k];
+    bool valid = (j0 < cols - 5 && i < rows - 1);
+    {
+      const int u0 = max(i - 2, 0), u1 = min(i + 2, rows), v0 = max(j0 - 2, 0), v1 = min(j0 + 2, cols);
+      int allpos = 1;
+#pragma unroll
+      for (int du = 0; du < 4; ++du)
+#pragma unroll
+        for (int dv = 0; dv < 4; ++dv) {
+          const int u = u0 + du, v = v0 + dv;
+          const bool in = (u < u1) && (v < v1);
+          const int px = in ? (int)nextImage[(size_t)u * cols + v] : 1;
+          allpos &= (px > 0);
+        }
+      valid = valid && allpos;
+    }
+    int4 out = make_int4(0, 0, 0, 0);  // DataTerm{zero, one, diff, valid} packed
+    if (valid) {
+      const float mTwo = (float)((valx * valx) + (valy * valy));
+      if (mTwo >= minScale && !isnan(d1)) {
+        const int y = i, x = j0;
+        const float transformed_d1 = (float)(d1 * (krkinv.r[2].x * x + krkinv.r[2].y * y + krkinv.r[2].z) + kt.z);
+        const int u0 = __float2int_rn((d1 * (krkinv.r[0].x * x + krkinv.r[0].y * y + krkinv.r[0].z) + kt.x) / transformed_d1);
+        const int v0 = __float2int_rn((d1 * (krkinv.r[1].x * x + krkinv.r[1].y * y + krkinv.r[1].z) + kt.y) / transformed_d1);
+        if (u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows) {
+          const float d0 = lastDepth[(size_t)v0 * cols + u0];
+          const int li = lastImage[(size_t)v0 * cols + u0];
+          if (d0 > 0 && fabsf(transformed_d1 - d0) <= od.maxDepthDeltaRGB && li != 0) {
+            const float diff = (float)nI - (float)li;
+            out.x = (u0 & 0xffff) | (v0 << 16);
+            out.y = (x & 0xffff) | (y << 16);
+            out.z = __float_as_int(diff);
+            out.w = 1;
+            cnt += 1;
+            sig += (unsigned int)__float2int_rz(diff * diff);
+          }
+        }
+      }
+    }
+    corres4[k] = out;
+  }
+  // block reduce two ints (wrapping adds, like the reference's int2 sums)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+    sig += __shfl_down_sync(0xffffffffu, sig, off);
+  }
+  if (lane == 0) {
+    sred_i[wid * 2] = (int)cnt;
+    sred_i[wid * 2 + 1] = (int)sig;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int c = 0, s = 0;
+    for (int w = 0; w < RES_THREADS / 32; ++w) {
+      c += (unsigned int)sred_i[w * 2];
+      s += (unsigned int)sred_i[w * 2 + 1];
+    }
+    od.partials_i[blockIdx.x * 2] = (int)c;
+    od.partials_i[blockIdx.x * 2 + 1] = (int)s;
+  }
+  if (!last_block_done(od.counter)) return;
+  {
+    unsigned int c2 = 0, s2 = 0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += RES_THREADS) {
+      c2 += (unsigned int)od.partials_i[b * 2];
+      s2 += (unsigned int)od.partials_i[b * 2 + 1];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      c2 += __shfl_down_sync(0xffffffffu, c2, off);
+      s2 += __shfl_down_sync(0xffffffffu, s2, off);
+    }
+    __syncthreads();
+    if (lane == 0) {
+      sred_i[wid * 2] = (int)c2;
+      sred_i[wid * 2 + 1] = (int)s2;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    unsigned int c = 0, s = 0;
+    for (int w = 0; w < RES_THREADS / 32; ++w) {
+      c += (unsigned int)sred_i[w * 2];
+      s += (unsigned int)sred_i[w * 2 + 1];
+    }
+    *od.counter = 0;
+    const int rgbSize = (int)c, sigma = (int)s;
+    gn->sum_res[0] = rgbSize;
+    gn->sum_res[1] = sigma;
+    if (finalize) {
+      gn->rgbSize = rgbSize;
+      gn->sigma = sigma;
+      // reference: std::sqrt((float)sigma / rgbSize == 0 ? 1 : rgbSize)  (RGBDOdometry.cpp:442, App. A-1)
+      float sigmaVal = (float)sqrt((double)(((float)sigma / rgbSize == 0) ? 1 : rgbSize));
+      const float rgbError = (float)(sqrt((double)sigma) / (rgbSize == 0 ? 1 : rgbSize));
+      const float prevError = (iter == 0) ? FLT_MAX : gn->lastRGBError;  // RGBDOdometry.cpp:404
+      if (gn->rgbOnly && rgbError > prevError) {
+        gn->break_level = level;
+      } else {
+        gn->lastRGBError = rgbError;
+        gn->lastRGBCount = (float)rgbSize;
+        if (gn->rgbOnly) sigmaVal = -1;
+        gn->sigmaVal = sigmaVal;
+      }
+    }
+  }
+}
+
+// SO3 pre-alignment step: SO3Reduction / so3Step + the host loop body (reduce.cu:789-973, RGBDOdometry.cpp:305-368)
+__device__ __forceinline__ void so3_gradient(const uint8_t* img, int cols, int x, int y, float& gx, float& gy) {
+  const float actu = (float)img[(size_t)y * cols + x];
+  float back = (float)img[(size_t)y * cols + x - 1];
+  float fore = (float)img[(size_t)y * cols + x + 1];
+  gx = ((back + actu) / 2.0f) - ((fore + actu) / 2.0f);
+  back = (float)img[(size_t)(y - 1) * cols + x];
+  fore = (float)img[(size_t)(y + 1) * cols + x];
+  gy = ((back + actu) / 2.0f) - ((fore + actu) / 2.0f);
+}
+
+__global__ void __launch_bounds__(RED_THREADS) k_so3_step(OdomDev od, int iter, int solve) {
+  GNState* gn = od.gn;
+  if (solve && gn->so3_done) return;
+  __shared__ float sred[11 * (RED_THREADS / 32)];
+  __shared__ double dsm[(RED_THREADS / 32) * 32];
+  const int level = 2;
+  const int rows = od.rows[level], cols = od.cols[level];
+  const int N = rows * cols;
+  const m33 imageBasis = load_m33(gn->imageBasis), kinv = load_m33(gn->kinv), krlr = load_m33(gn->krlr);
+  const uint8_t* lastImage = od.lastNextImage[level];
+  const uint8_t* nextImage = od.nextImage[level];
+  float acc[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) acc[k] = 0.f;
+  for (int k = blockIdx.x * RED_THREADS + threadIdx.x; k < N; k += gridDim.x * RED_THREADS) {
+    const int y = k / cols, x = k - y * cols;
+    const f3 unwarped = mk3((float)x, (float)y, 1.0f);
+    const f3 warped = mul(imageBasis, unwarped);
+    const int wx = __float2int_rn(warped.x / warped.z);
+    const int wy = __float2int_rn(warped.y / warped.z);
+    if (wx >= 1 && wx < cols - 1 && wy >= 1 && wy < rows - 1 && x >= 1 && x < cols - 1 && y >= 1 && y < rows - 1) {
+      float gnx, gny, glx, gly;
+      so3_gradient(nextImage, cols, wx, wy, gnx, gny);
+      so3_gradient(lastImage, cols, x, y, glx, gly);
+      const float gx = (gnx + glx) / 2.0f;
+      const float gy = (gny + gly) / 2.0f;
+      const f3 point = mul(kinv, unwarped);
+      const float z2 = point.z * point.z;
+      const float a = krlr.r[0].x, b = krlr.r[0].y, c = krlr.r[0].z;
+      const float d = krlr.r[1].x, e = krlr.r[1].y, f = krlr.r[1].z;
+      const float g = krlr.r[2].x, h = krlr.r[2].y, i = krlr.r[2].z;
+      const f3 leftProduct = mk3(((point.z * (d * gy + a * gx)) - (gy * g * y) - (gx * g * x)) / z2,
+                                 ((point.z * (e * gy + b * gx)) - (gy * h * y) - (gx * h * x)) / z2,
+                                 ((point.z * (f * gy + c * gx)) - (gy * i * y) - (gx * i * x)) / z2);
+      const f3 jacRow = cross(leftProduct, point);
+      float row[4];
+      row[0] = jacRow.x;
+      row[1] = jacRow.y;
+      row[2] = jacRow.z;
+      row[3] = -((float)nextImage[(size_t)wy * cols + wx] - (float)lastImage[k]);
+      int q = 0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = r; s < 4; ++s) acc[q++] += row[r] * row[s];
+      acc[9] += row[3] * row[3];
+      acc[10] += 1.0f;
+    }
+  }
+  block_reduce_sum<11, RED_THREADS>(acc, sred);
+  if (threadIdx.x == 0) {
+    float* my_partial = od.partials + (size_t)blockIdx.x * PARTIAL_STRIDE;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) my_partial[k] = acc[k];
+  }
+  if (!last_block_done(od.counter)) return;
+  final_sum<RED_THREADS>(od.partials, gridDim.x, 0, 11, gn->sum_so3, dsm);
+  if (threadIdx.x != 0) return;
+  *od.counter = 0;
+  if (!solve) return;
+
+  float jtj[9], jtr[3];
+  {
+    int shift = 0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = i; j < 4; ++j) {
+        const float value = gn->sum_so3[shift++];
+        if (j == 3)
+          jtr[i] = value;
+        else
+          jtj[j * 3 + i] = jtj[i * 3 + j] = value;
+      }
+  }
+  const float res0 = gn->sum_so3[9], res1 = gn->sum_so3[10];
+  if (od.trace && gn->trace_n < MAX_TRACE) {
+    EfSolveTrace& t = od.trace[gn->trace_n++];
+    t.kind = 1;
+    t.level = 2;
+    t.iter = iter;
+    for (int k = 0; k < 9; ++k) t.A_so3[k] = jtj[k];
+    for (int k = 0; k < 3; ++k) t.b_so3[k] = jtr[k];
+    t.so3_residual[0] = res0;
+    t.so3_residual[1] = res1;
+  }
+  gn->lastSO3Error = sqrtf(res0) / res1;
+  gn->lastSO3Count = res1;
+  if (gn->lastSO3Error < gn->so3_lastError && gn->so3_lastCount == gn->lastSO3Count) {
+    gn->so3_done = 1;  // converged
+    return;
+  } else if ((double)gn->lastSO3Error > (double)gn->so3_lastError + 0.001) {  // diverging
+    gn->lastSO3Error = gn->so3_lastError;
+    gn->lastSO3Count = gn->so3_lastCount;
+    for (int k = 0; k < 9; ++k) gn->resultR[k] = gn->lastResultR[k];
+    gn->so3_done = 1;
+    return;
+  }
+  gn->so3_lastError = gn->lastSO3Error;
+  gn->so3_lastCount = gn->lastSO3Count;
+  for (int k = 0; k < 9; ++k) gn->lastResultR[k] = gn->resultR[k];
+  float delta[3];
+  efm::solve_sym3f(jtj, jtr, delta);
+  double dd[3] = {delta[0], delta[1], delta[2]}, rotUpdate[9];
+  efm::rodrigues(dd, rotUpdate);
+  float ru[9], nr[9];
+  for (int k = 0; k < 9; ++k) ru[k] = (float)rotUpdate[k];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      nr[r * 3 + c] = ru[r * 3 + 0] * gn->R_lr[0 * 3 + c] + ru[r * 3 + 1] * gn->R_lr[1 * 3 + c] + ru[r * 3 + 2] * gn->R_lr[2 * 3 + c];
+  for (int k = 0; k < 9; ++k) {
+    gn->R_lr[k] = nr[k];
+    gn->resultR[k] = nr[k];
+  }
+  so3_prepare(gn);
+}
+
+namespace {
+
+inline int red_blocks(const EfContext* ctx, int n_items, int per_thread, int threads, int ctas_per_sm) {
+  int b = (n_items + threads * per_thread - 1) / (threads * per_thread);
+  int cap = ctx->num_sms * ctas_per_sm;  // one resident wave
+  if (cap > MAX_RED_BLOCKS) cap = MAX_RED_BLOCKS;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return b;
+}
+
+#define EF_CHECK_LAST()                          \
+  do {                                           \
+    cudaError_t e__ = cudaGetLastError();        \
+    if (e__ != cudaSuccess) return (int)e__;     \
+  } while (0)
+
+}  // namespace
+
+namespace ef {
+
+// the device-resident Gauss-Newton schedule; T_wc in/out lives in gn->T_wc
+int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom, bool so3) {
+  OdomDev& od = ctx->odom[which];
+  const bool icp = !rgbOnly && icpWeight > 0;
+  const bool rgb = rgbOnly || icpWeight < 100;
+  if (rgb) {
+    int rc = launch_sobel(ctx, which);
+    if (rc) return rc;
+  }
+  EF_LAUNCH(ctx, k_gn_begin, 1, 32, 0, od.gn, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0);
+  if (so3) {
+    const int nb = red_blocks(ctx, od.rows[2] * od.cols[2], 1, RED_THREADS, 2);
+    for (int i = 0; i < 10; ++i) EF_LAUNCH(ctx, k_so3_step, nb, RED_THREADS, 0, od, i, 1);
+  }
+  int iterations[NUM_PYRS] = {fastOdom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0};
+  // static schedule of (level, iter)
+  int sched_level[32], sched_iter[32], ns = 0;
+  for (int i = NUM_PYRS - 1; i >= 0; --i)
+    for (int j = 0; j < iterations[i]; ++j) {
+      sched_level[ns] = i;
+      sched_iter[ns] = j;
+      ++ns;
+    }
+  EF_LAUNCH(ctx, k_gn_seed, 1, 32, 0, od.gn, ns ? sched_level[0] : 0);
+  for (int s = 0; s < ns; ++s) {
+    const int lv = sched_level[s];
+    const int npx = od.rows[lv] * od.cols[lv];
+    if (rgb) EF_LAUNCH(ctx, k_rgb_residual, red_blocks(ctx, npx, 4, RES_THREADS, RES_CTAS_PER_SM), RES_THREADS, 0, od, lv, sched_iter[s], 1);
+    const int next_lv = (s + 1 < ns) ? sched_level[s + 1] : -1;
+    const int nbs = red_blocks(ctx, npx, 4, SE3_THREADS, SE3_CTAS_PER_SM);
+    EF_LAUNCH(ctx, k_se3_step, nbs, SE3_THREADS, 0, od, lv, next_lv, icp ? 1 : 0, rgb ? 1 : 0, 1);
+    EF_LAUNCH(ctx, k_gn_update, 1, 1024, 0, od, lv, sched_iter[s], next_lv, nbs, icp ? 1 : 0, rgb ? 1 : 0, 1);
+  }
+  if (so3)
+    for (int i = 0; i < NUM_PYRS; ++i) {  // RGBDOdometry.cpp:560-564: handle swap
+      uint8_t* t = od.lastNextImage[i];
+      od.lastNextImage[i] = od.nextImage[i];
+      od.nextImage[i] = t;
+    }
+  EF_CHECK_LAST();
+  return 0;
+}
+
+int odom_finish_async(EfContext* ctx, int which, float weightMultiplier, bool have_track) {
+  OdomDev& od = ctx->odom[which];
+  EF_LAUNCH(ctx, k_gn_finish, 1, 32, 0, od.gn, weightMultiplier, have_track ? 1 : 0);
+  EF_CHECK_LAST();
+  return 0;
+}
+
+int odom_set_pose_async(EfContext* ctx, int which, const double* T_dev) {
+  OdomDev& od = ctx->odom[which];
+  EF_LAUNCH(ctx, k_set_pose, 1, 32, 0, od.gn, T_dev);
+  EF_CHECK_LAST();
+  return 0;
+}
+
+// stand-alone reduction launches for the stage API
+int launch_se3_step_raw(EfContext* ctx, int which, int level, bool do_icp, bool do_rgb) {
+  OdomDev& od = ctx->odom[which];
+  const int nb = red_blocks(ctx, od.rows[level] * od.cols[level], 4, SE3_THREADS, SE3_CTAS_PER_SM);
+  EF_LAUNCH(ctx, k_se3_step, nb, SE3_THREADS, 0, od, level, -1, do_icp ? 1 : 0, do_rgb ? 1 : 0, 0);
+  EF_LAUNCH(ctx, k_gn_update, 1, 1024, 0, od, level, 0, -1, nb, do_icp ? 1 : 0, do_rgb ? 1 : 0, 0);
+  EF_CHECK_LAST();
+  return 0;
+}
+int launch_rgb_residual_raw(EfContext* ctx, int which, int level) {
+  OdomDev& od = ctx->odom[which];
+  const int nb = red_blocks(ctx, od.rows[level] * od.cols[level], 4, RES_THREADS, RES_CTAS_PER_SM);
+  EF_LAUNCH(ctx, k_rgb_residual, nb, RES_THREADS, 0, od, level, 0, 0);
+  EF_CHECK_LAST();
+  return 0;
+}
+int launch_so3_raw(EfContext* ctx, int which) {
+  OdomDev& od = ctx->odom[which];
+  const int nb = red_blocks(ctx, od.rows[2] * od.cols[2], 1, RED_THREADS, 2);
+  EF_LAUNCH(ctx, k_so3_step, nb, RED_THREADS, 0, od, 0, 0);
+  EF_CHECK_LAST();
+  return 0;
+}
+}  // namespace ef
