@@ -24,7 +24,7 @@ int odom_populate(EfContext* ctx, int which, const uint8_t* rgba, float** destDe
 int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom, bool so3);
 int odom_finish_async(EfContext* ctx, int which, float weightMultiplier, bool have_track);
 int odom_set_pose_async(EfContext* ctx, int which, const double* T_dev);
-int launch_se3_step_raw(EfContext* ctx, int which, int level, bool do_icp, bool do_rgb);
+int launch_se3_step_raw(EfContext* ctx, int which, int level, bool do_icp, bool do_rgb, float sigma);
 int launch_rgb_residual_raw(EfContext* ctx, int which, int level);
 int launch_so3_raw(EfContext* ctx, int which);
 int launch_sobel(EfContext* ctx, int which);
@@ -177,6 +177,20 @@ static int alloc_odom(EfContext* ctx, OdomDev& od) {
   CU(cudaMemsetAsync(od.vmaps_tmp, 0, 4 * n0 * sizeof(float), ctx->stream));
   CU(A->alloc(&od.gn, 1));
   CU(A->alloc(&od.partials, (size_t)MAX_RED_BLOCKS * PARTIAL_STRIDE));
+  CU(A->alloc(&od.partials_rgb, (size_t)MAX_RGB_BLOCKS * 32));
+  CU(A->alloc(&od.partials2, (size_t)MAX_RGB_BLOCKS * 32));
+  {
+    size_t flat = 0;
+    for (int i = 0; i < NUM_PYRS; ++i) {
+      od.level_start[i] = (int)flat;
+      flat += (size_t)od.rows[i] * od.cols[i];
+    }
+    od.level_start[NUM_PYRS] = (int)flat;
+    CU(A->alloc(&od.cand, flat));
+    CU(A->alloc(&od.terms, flat));
+    CU(cudaMemsetAsync(od.cand, 0, flat * sizeof(int4), ctx->stream));
+    CU(cudaMemsetAsync(od.terms, 0, flat * sizeof(int4), ctx->stream));
+  }
   CU(A->alloc(&od.partials_i, (size_t)MAX_RED_BLOCKS * 2));
   CU(A->alloc(&od.counter, 4));
   CU(A->alloc(&od.trace, MAX_TRACE));
@@ -192,6 +206,7 @@ static int alloc_odom(EfContext* ctx, OdomDev& od) {
   g.cy = c.cy;
   g.break_level = -1;
   g.weighting = 1.0f;
+  g.flat_n = od.level_start[NUM_PYRS];
   CU(cudaMemcpyAsync(od.gn, &g, sizeof(g), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -214,6 +229,7 @@ template cudaError_t ctx_alloc<uint8_t>(EfContext*, uint8_t**, size_t);
 template cudaError_t ctx_alloc<uint16_t>(EfContext*, uint16_t**, size_t);
 template cudaError_t ctx_alloc<uchar4>(EfContext*, uchar4**, size_t);
 template cudaError_t ctx_alloc<MapPose>(EfContext*, MapPose**, size_t);
+template cudaError_t ctx_alloc<int4>(EfContext*, int4**, size_t);
 }  // namespace ef
 
 extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
@@ -559,7 +575,7 @@ extern "C" int ef_icp_step_async(EfContext* ctx, int which, int level, const flo
     RC(upload_gn(ctx, which, offsetof(GNState, Rprev_inv), s + 12, 36));
     RC(upload_gn(ctx, which, offsetof(GNState, tprev), s + 21, 12));
   }
-  return launch_se3_step_raw(ctx, which, level, true, false);
+  return launch_se3_step_raw(ctx, which, level, true, false, 0.f);
 }
 
 extern "C" int ef_icp_step(EfContext* ctx, int which, int level, const float* Rcurr, const float* tcurr, const float* Rprev_inv,
@@ -591,9 +607,7 @@ extern "C" int ef_rgb_residual(EfContext* ctx, int which, int level, const float
 
 extern "C" int ef_rgb_step(EfContext* ctx, int which, int level, float sigma, float* A36, float* b6) {
   if (!ctx || !WHICH_OK(which) || level < 0 || level >= NUM_PYRS || !A36 || !b6) return EF_EINVAL;
-  RC(upload_gn(ctx, which, offsetof(GNState, sigmaVal), &sigma, 4));
-  CU(cudaStreamSynchronize(ctx->stream));
-  RC(launch_se3_step_raw(ctx, which, level, false, true));
+  RC(launch_se3_step_raw(ctx, which, level, false, true, sigma));
   GNState g;
   RC(download_gn(ctx, which, &g));
   unpack_se3_host(g.sum_rgb, A36, b6);

@@ -160,12 +160,23 @@ EFM_HD void ldlt_solve(const T* A_, const T* b_, T* x, T tiny) {
 }
 EFM_HD void solve_sym6(const double* A, const double* b, double* x) { ldlt_solve<double, 6>(A, b, x, 1.0 / DBL_MAX); }
 
+// 1/d to full double precision without the ~40-instruction IEEE division sequence: hardware reciprocal seed (rcp.approx.ftz.f64,
+// ~20 good bits) + three Newton steps. Used only where a 1-ulp difference is irrelevant (pivot reciprocals of the solve).
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = r * (2.0 - d * r);
+  r = r * (2.0 - d * r);
+  r = r * (2.0 - d * r);
+  return r;
+}
+
 // Register-resident L D L^T solve (no pivoting, fully unrolled: every index is a compile-time constant, so nothing goes
 // to local memory). For the symmetric positive-definite normal equations of the tracker this equals the pivoted solve to
 // rounding (~1e-13 relative); a vanishing pivot contributes 0 like Eigen::LDLT does. Used on the device, where a
 // single thread runs the solve and dependent local-memory traffic would dominate.
 template <int N>
-EFM_HD void ldlt_solve_unrolled(const double* A_, const double* b_, double* x) {
+__device__ __forceinline__ void ldlt_solve_unrolled(const double* A_, const double* b_, double* x) {
   double L[N][N], D[N], invD[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) {
@@ -174,7 +185,7 @@ EFM_HD void ldlt_solve_unrolled(const double* A_, const double* b_, double* x) {
     for (int k = 0; k < N; ++k)
       if (k < j) d -= L[j][k] * L[j][k] * D[k];
     D[j] = d;
-    invD[j] = (fabs(d) > 1.0 / DBL_MAX) ? 1.0 / d : 0.0;
+    invD[j] = (fabs(d) > 1e-300) ? fast_rcp(d) : 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i)
       if (i > j) {

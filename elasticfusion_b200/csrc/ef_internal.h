@@ -12,6 +12,7 @@ constexpr int RED_THREADS = 256;     // threads per reduction CTA
 constexpr int MAX_RED_BLOCKS = 1184; // 148 SMs x 8 resident 256-thread CTAs
 constexpr int PARTIAL_STRIDE = 64;   // floats per CTA partial: [0,29) geometric system, [32,61) photometric system
 constexpr int MAX_TRACE = 48;
+constexpr int MAX_RGB_BLOCKS = 64;
 
 // reference DataTerm (Core/Cuda/types.cuh:79-84): 16 bytes, bool widened to int32
 struct DataTerm {
@@ -49,6 +50,9 @@ struct GNState {
   float icpWeight;
   float fx, fy, cx, cy;
   int trace_n;
+  int cand_base[NUM_PYRS + 1];  // photometric candidates of level L live in cand[cand_base[L], cand_base[L+1])
+  int flat_n;                   // total pixels over the three levels
+  float rgbErrBuf[2];           // rgbError of the previous / current iteration (double-buffered across CTAs)
   float weighting;  // velocity weighting for fusion (ElasticFusion.cpp:369-383)
 };
 
@@ -73,9 +77,16 @@ struct OdomDev {
   uint8_t *lastImage[NUM_PYRS], *nextImage[NUM_PYRS], *lastNextImage[NUM_PYRS];
   int16_t *dIdx[NUM_PYRS], *dIdy[NUM_PYRS];
   DataTerm* corres[NUM_PYRS];
+  // photometric candidates: pixels that pass every pose-independent gate of computeRgbResidual (reference reduce.cu:641-660),
+  // compacted once per frame; {pixel index, nextDepth bits, dIdx | dIdy << 16, nextImage}
+  int4* cand;
+  int4* terms;            // per candidate and iteration: {zero_x | zero_y << 16 (or -1), diff bits, dIdx | dIdy << 16, lastDepth[zero] bits}
+  int level_start[NUM_PYRS + 1];  // flat pixel offset of each level
 
   GNState* gn;
-  float* partials;        // MAX_RED_BLOCKS * PARTIAL_STRIDE
+  float* partials;        // MAX_RED_BLOCKS * PARTIAL_STRIDE (geometric system, one slot per CTA of the dense pass)
+  double* partials2;      // MAX_RGB_BLOCKS * 32: second-level sums of `partials`, one slot per CTA of the candidate pass
+  float* partials_rgb;    // MAX_RGB_BLOCKS * 32 (photometric system, one slot per CTA of the candidate pass)
   int* partials_i;        // MAX_RED_BLOCKS * 2
   unsigned int* counter;  // last-block ticket
   EfSolveTrace* trace;    // MAX_TRACE records (device)

@@ -816,7 +816,7 @@ int alloc_map(EfContext* ctx) {
   CU(ctx_alloc(ctx, &m.assoc_id, n));
   CU(ctx_alloc(ctx, &m.pending, cap));
   CU(ctx_alloc(ctx, &m.zbuf, n));
-  const size_t max_items = cap + n;
+  const size_t max_items = (cap + n) > 2 * n ? (cap + n) : 2 * n;
   const size_t tiles = (max_items + SCAN_TILE - 1) / SCAN_TILE + 1;
   unsigned long long* st = nullptr;
   CU(ctx_alloc(ctx, &st, tiles));
@@ -843,7 +843,7 @@ int alloc_map(EfContext* ctx) {
   return 0;
 }
 
-static int run_scan(EfContext* ctx, const uint8_t* flags, const int* n_a, const int* n_b, size_t max_items, int* offsets, int* total) {
+int run_scan(EfContext* ctx, const uint8_t* flags, const int* n_a, const int* n_b, size_t max_items, int* offsets, int* total) {
   MapDev& m = ctx->map;
   const size_t tiles = (max_items + SCAN_TILE - 1) / SCAN_TILE + 1;
   CU(cudaMemsetAsync(m.scan_tile_state, 0, tiles * 8, ctx->stream));
@@ -1051,6 +1051,18 @@ int map_upload(EfContext* ctx, const float* in, int n) {
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->host_count = n;
   return 0;
+}
+
+// scan scratch shared with the tracker's per-frame candidate compaction (same stream, never concurrent)
+int scan_flags_shared(EfContext* ctx, const int* n_dev, size_t max_items, uint8_t** flags, int** offsets, int* total_dev) {
+  MapBuffers& B = mb(ctx);
+  *flags = ctx->map.flags;
+  *offsets = B.offsets;
+  return run_scan(ctx, ctx->map.flags, n_dev, nullptr, max_items, B.offsets, total_dev);
+}
+void scan_scratch(EfContext* ctx, uint8_t** flags, int** offsets) {
+  *flags = ctx->map.flags;
+  *offsets = mb(ctx).offsets;
 }
 
 void map_free_host(EfContext* ctx) {

@@ -360,38 +360,9 @@ __device__ void gn_update_warp(const OdomDev& od, GnScratch& S, int level, int i
 // reductions
 // =============================================================================================
 
-constexpr int SE3_THREADS = 128;  // 640x480/4 pixel groups = 600 CTAs of 128: one resident wave at 5 CTAs/SM (<=102 registers)
-constexpr int SE3_CTAS_PER_SM = 5;
-constexpr int RES_THREADS = 256;
-constexpr int RES_CTAS_PER_SM = 3;
-
-// final cross-CTA sum of `nvals` (<=32) floats at `off` inside each CTA's partial; result (float) to dst[0..nvals)
-template <int THREADS>
-__device__ __forceinline__ void final_sum(const float* partials, int nblocks, int off, int nvals, float* dst, double* dsm) {
-  const int v = threadIdx.x & 31, s = threadIdx.x >> 5;
-  double acc = 0;
-  if (v < nvals) {
-    int b = s;
-    // 4 independent loads in flight per step
-    for (; b + 3 * (THREADS / 32) < nblocks; b += 4 * (THREADS / 32)) {
-      const float p0 = partials[(size_t)b * PARTIAL_STRIDE + off + v];
-      const float p1 = partials[(size_t)(b + THREADS / 32) * PARTIAL_STRIDE + off + v];
-      const float p2 = partials[(size_t)(b + 2 * (THREADS / 32)) * PARTIAL_STRIDE + off + v];
-      const float p3 = partials[(size_t)(b + 3 * (THREADS / 32)) * PARTIAL_STRIDE + off + v];
-      acc += ((double)p0 + (double)p1) + ((double)p2 + (double)p3);
-    }
-    for (; b < nblocks; b += THREADS / 32) acc += (double)partials[(size_t)b * PARTIAL_STRIDE + off + v];
-  }
-  dsm[s * 32 + v] = acc;
-  __syncthreads();
-  if (s == 0 && v < nvals) {
-    double t = 0;
-#pragma unroll
-    for (int k = 0; k < THREADS / 32; ++k) t += dsm[k * 32 + v];
-    dst[v] = (float)t;
-  }
-  __syncthreads();
-}
+constexpr int IT1_THREADS = 128;  // 640x480/4 pixel groups = 600 CTAs of 128: one resident wave at 5 CTAs/SM (<=102 registers)
+constexpr int IT1_CTAS_PER_SM = 5;
+constexpr int IT2_THREADS = 1024;
 
 // ---- geometric row: ICPReduction::search/getProducts (reduce.cu:224-331) ------------------------------------
 struct IcpFrame {
@@ -434,50 +405,55 @@ __device__ __forceinline__ void icp_accumulate(const IcpFrame& F, const f3& vcur
   accumulate29(row, acc);
 }
 
-// ---- photometric row: RGBReduction::getProducts (reduce.cu:419-480); cloud point recomputed from lastDepth
-//      with projectPointsKernel's arithmetic (cudafuncs.cu:670-688) ----------------------------------------
-__device__ __forceinline__ void rgb_accumulate(const DataTerm& corresp, float sigma, float z, float dx_raw, float dy_raw, float fx, float fy,
-                                               float cx, float cy, float sobelScale, float (&acc)[29]) {
-  float w = sigma + fabsf(corresp.diff);
-  w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
-  if (sigma == -1) w = 1;
-  float row[7];
-  row[6] = -w * corresp.diff;
-  const float invFx = 1.0f / fx, invFy = 1.0f / fy;
-  const f3 cp = mk3((float)((corresp.zero_x - cx) * z * invFx), (float)((corresp.zero_y - cy) * z * invFy), z);
-  const float invz = (float)(1.0 / (double)cp.z);
-  const float dI_dx_val = w * sobelScale * dx_raw;
-  const float dI_dy_val = w * sobelScale * dy_raw;
-  const float v0 = dI_dx_val * fx * invz;
-  const float v1 = dI_dy_val * fy * invz;
-  const float v2 = -(v0 * cp.x + v1 * cp.y) * invz;
-  row[0] = v0;
-  row[1] = v1;
-  row[2] = v2;
-  row[3] = -cp.z * v1 + cp.y * v2;
-  row[4] = cp.z * v0 - cp.x * v2;
-  row[5] = -cp.y * v0 + cp.x * v1;
-  accumulate29(row, acc);
-}
-
-// One Gauss-Newton step: geometric and/or photometric 6x6 systems reduced in ONE launch (icpStep + rgbStep,
-// reduce.cu:333-401,502-550). The last CTA sums the per-CTA partials in double; k_gn_update then solves.
-__global__ void __launch_bounds__(SE3_THREADS, SE3_CTAS_PER_SM) k_se3_step(OdomDev od, int level, int next_level, int do_icp, int do_rgb, int solve) {
+// First launch of a Gauss-Newton iteration. Two independent jobs share the launch so their memory round trips overlap:
+//  (a) photometric correspondences for this pose over the per-frame candidate list (RGBResidual::getProducts,
+//      reduce.cu:661-697; the pose-independent gates were applied when the list was built): writes one compact term per
+//      candidate and the CTA's {count, sum int(diff^2)};
+//  (b) the dense geometric rows (ICPReduction, reduce.cu:224-331) reduced to one 29-float partial per CTA.
+__global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev od, int level, int do_res, int do_icp, int solve) {
   GNState* gn = od.gn;
   if (solve && gn->break_level == level) return;  // rgbOnly `break`: rest of the level is skipped
-  __shared__ float sred[29 * (SE3_THREADS / 32)];
+  __shared__ float sred[29 * (IT1_THREADS / 32)];
+  __shared__ int sred_i[2 * (IT1_THREADS / 32)];
   const int rows = od.rows[level], cols = od.cols[level];
   const int N = rows * cols;
   const size_t plane = (size_t)N;
-  float lfx, lfy, lcx, lcy;
-  {
-    const int div = 1 << level;
-    lfx = gn->fx / div;
-    lfy = gn->fy / div;
-    lcx = gn->cx / div;
-    lcy = gn->cy / div;
+  const int gid = blockIdx.x * IT1_THREADS + threadIdx.x, gstride = gridDim.x * IT1_THREADS;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+  unsigned int cnt = 0, sig = 0;
+  if (do_res) {
+    const int base = gn->cand_base[level], ncand = gn->cand_base[level + 1] - base;
+    const m33 krkinv = load_m33(gn->krkinv);
+    const f3 kt = mk3(gn->kt[0], gn->kt[1], gn->kt[2]);
+    const float* __restrict__ lastDepth = od.lastDepth[level];
+    const uint8_t* __restrict__ lastImage = od.lastImage[level];
+    const int4* __restrict__ cand = od.cand + base;
+    int4* __restrict__ terms = od.terms + base;
+    for (int c = gid; c < ncand; c += gstride) {
+      const int4 cr = cand[c];
+      const int k = cr.x;
+      const int y = k / cols, x = k - y * cols;
+      const float d1 = __int_as_float(cr.y);
+      const float transformed_d1 = (float)(d1 * (krkinv.r[2].x * x + krkinv.r[2].y * y + krkinv.r[2].z) + kt.z);
+      const int u0 = __float2int_rn((d1 * (krkinv.r[0].x * x + krkinv.r[0].y * y + krkinv.r[0].z) + kt.x) / transformed_d1);
+      const int v0 = __float2int_rn((d1 * (krkinv.r[1].x * x + krkinv.r[1].y * y + krkinv.r[1].z) + kt.y) / transformed_d1);
+      int4 out = make_int4(-1, 0, cr.z, 0);
+      if (u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows) {
+        const float d0 = lastDepth[(size_t)v0 * cols + u0];
+        const int li = lastImage[(size_t)v0 * cols + u0];
+        if (d0 > 0 && fabsf(transformed_d1 - d0) <= od.maxDepthDeltaRGB && li != 0) {
+          const float diff = (float)cr.w - (float)li;
+          out.x = (u0 & 0xffff) | (v0 << 16);
+          out.y = __float_as_int(diff);
+          out.w = __float_as_int(d0);
+          cnt += 1;
+          sig += (unsigned int)__float2int_rz(diff * diff);
+        }
+      }
+      terms[c] = out;
+    }
   }
-  float* my_partial = od.partials + (size_t)blockIdx.x * PARTIAL_STRIDE;
 
   if (do_icp) {
     IcpFrame F;
@@ -485,10 +461,13 @@ __global__ void __launch_bounds__(SE3_THREADS, SE3_CTAS_PER_SM) k_se3_step(OdomD
     F.Rprev_inv = load_m33(gn->Rprev_inv);
     F.tcurr = mk3(gn->tcurr[0], gn->tcurr[1], gn->tcurr[2]);
     F.tprev = mk3(gn->tprev[0], gn->tprev[1], gn->tprev[2]);
-    F.fx = lfx;
-    F.fy = lfy;
-    F.cx = lcx;
-    F.cy = lcy;
+    {
+      const int div = 1 << level;
+      F.fx = gn->fx / div;
+      F.fy = gn->fy / div;
+      F.cx = gn->cx / div;
+      F.cy = gn->cy / div;
+    }
     F.distThres = od.distThres;
     F.angleThres = od.angleThres;
     float acc[29];
@@ -501,7 +480,7 @@ __global__ void __launch_bounds__(SE3_THREADS, SE3_CTAS_PER_SM) k_se3_step(OdomD
     if ((cols & 3) == 0) {
       // 4 consecutive pixels per thread: six 128-bit coalesced loads for the live maps, the model maps gathered in pairs
       const int ngroups = N >> 2;
-      for (int g = blockIdx.x * SE3_THREADS + threadIdx.x; g < ngroups; g += gridDim.x * SE3_THREADS) {
+      for (int g = gid; g < ngroups; g += gstride) {
         const int i0 = g << 2;
         const float4 vx4 = *reinterpret_cast<const float4*>(vc + i0);
         const float4 vy4 = *reinterpret_cast<const float4*>(vc + plane + i0);
@@ -526,7 +505,7 @@ __global__ void __launch_bounds__(SE3_THREADS, SE3_CTAS_PER_SM) k_se3_step(OdomD
         }
       }
     } else {
-      for (int i = blockIdx.x * SE3_THREADS + threadIdx.x; i < N; i += gridDim.x * SE3_THREADS) {
+      for (int i = gid; i < N; i += gstride) {
         f3 vg, cp;
         const int q = icp_project(F, mk3(vc[i], vc[i + plane], vc[i + 2 * plane]), rows, cols, vg, cp);
         if (q >= 0)
@@ -534,87 +513,191 @@ __global__ void __launch_bounds__(SE3_THREADS, SE3_CTAS_PER_SM) k_se3_step(OdomD
                          mk3(np_[q], np_[q + plane], np_[q + 2 * plane]), acc);
       }
     }
-    block_reduce_sum<29, SE3_THREADS>(acc, sred);
+    block_reduce_sum<29, IT1_THREADS>(acc, sred);
     if (threadIdx.x == 0) {
+      float* my_partial = od.partials + (size_t)blockIdx.x * PARTIAL_STRIDE;
 #pragma unroll
       for (int k = 0; k < 29; ++k) my_partial[k] = acc[k];
     }
-    __syncthreads();
   }
-  if (do_rgb) {
-    const float sigma = gn->sigmaVal;
-    const DataTerm* __restrict__ corres = od.corres[level];
-    const float* __restrict__ lastDepth = od.lastDepth[level];
-    const int16_t* __restrict__ dIdx = od.dIdx[level];
-    const int16_t* __restrict__ dIdy = od.dIdy[level];
-    float acc[29];
+  if (do_res) {
+    // CTA sum of the two ints (wrapping adds, like the reference's int2 sums)
 #pragma unroll
-    for (int k = 0; k < 29; ++k) acc[k] = 0.f;
-    // 2 DataTerms (16 B each, one 128-bit load) per thread per iteration, their gathers issued together
-    const int4* __restrict__ c4 = reinterpret_cast<const int4*>(corres);
-    for (int i = (blockIdx.x * SE3_THREADS + threadIdx.x) * 2; i < N; i += gridDim.x * SE3_THREADS * 2) {
-      const int4 r0 = c4[i];
-      const int4 r1 = (i + 1 < N) ? c4[i + 1] : make_int4(0, 0, 0, 0);
-      DataTerm d0, d1;
-      d0.zero_x = (short)(r0.x & 0xffff);
-      d0.zero_y = (short)(r0.x >> 16);
-      d0.one_x = (short)(r0.y & 0xffff);
-      d0.one_y = (short)(r0.y >> 16);
-      d0.diff = __int_as_float(r0.z);
-      d0.valid = r0.w;
-      d1.zero_x = (short)(r1.x & 0xffff);
-      d1.zero_y = (short)(r1.x >> 16);
-      d1.one_x = (short)(r1.y & 0xffff);
-      d1.one_y = (short)(r1.y >> 16);
-      d1.diff = __int_as_float(r1.z);
-      d1.valid = r1.w;
-      const size_t z0 = d0.valid ? (size_t)d0.zero_y * cols + d0.zero_x : 0, o0 = d0.valid ? (size_t)d0.one_y * cols + d0.one_x : 0;
-      const size_t z1 = d1.valid ? (size_t)d1.zero_y * cols + d1.zero_x : 0, o1 = d1.valid ? (size_t)d1.one_y * cols + d1.one_x : 0;
-      const float zz0 = __ldg(lastDepth + z0), zz1 = __ldg(lastDepth + z1);
-      const float gx0 = (float)__ldg(dIdx + o0), gy0 = (float)__ldg(dIdy + o0);
-      const float gx1 = (float)__ldg(dIdx + o1), gy1 = (float)__ldg(dIdy + o1);
-      if (d0.valid) rgb_accumulate(d0, sigma, zz0, gx0, gy0, lfx, lfy, lcx, lcy, od.sobelScale, acc);
-      if (d1.valid) rgb_accumulate(d1, sigma, zz1, gx1, gy1, lfx, lfy, lcx, lcy, od.sobelScale, acc);
+    for (int off = 16; off > 0; off >>= 1) {
+      cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+      sig += __shfl_down_sync(0xffffffffu, sig, off);
     }
-    block_reduce_sum<29, SE3_THREADS>(acc, sred);
+    if (lane == 0) {
+      sred_i[wid * 2] = (int)cnt;
+      sred_i[wid * 2 + 1] = (int)sig;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
+      unsigned int c = 0, s = 0;
 #pragma unroll
-      for (int k = 0; k < 29; ++k) my_partial[32 + k] = acc[k];
+      for (int w = 0; w < IT1_THREADS / 32; ++w) {
+        c += (unsigned int)sred_i[w * 2];
+        s += (unsigned int)sred_i[w * 2 + 1];
+      }
+      od.partials_i[blockIdx.x * 2] = (int)c;
+      od.partials_i[blockIdx.x * 2 + 1] = (int)s;
     }
   }
 }
 
-// Final cross-CTA sums of one step (double, fixed order) + the serial part of the Gauss-Newton iteration, as one 1-CTA
-// launch: 32 warps sum 32 interleaved slices of the per-CTA partials with 4 loads in flight each, then warp 0 solves.
-// (The reference does this with reduceSum<<<1,1024>>>, cudaDeviceSynchronize, a blocking D2H and Eigen on the host.)
-__global__ void __launch_bounds__(1024) k_gn_update(OdomDev od, int level, int iter, int next_level, int nblocks, int do_icp, int do_rgb, int solve) {
+// ---- photometric row: RGBReduction::getProducts (reduce.cu:419-480); the cloud point is recomputed from the gathered
+//      lastDepth with projectPointsKernel's arithmetic (cudafuncs.cu:670-688) -------------------------------------
+__device__ __forceinline__ void rgb_accumulate(const int4& term, float sigma, float fx, float fy, float cx, float cy, float sobelScale,
+                                               float (&acc)[29]) {
+  const float diff = __int_as_float(term.y);
+  const int zx = (int)(short)(term.x & 0xffff), zy = term.x >> 16;
+  const float z = __int_as_float(term.w);
+  const float gx = (float)(short)(term.z & 0xffff), gy = (float)(short)(term.z >> 16);
+  float w = sigma + fabsf(diff);
+  w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
+  if (sigma == -1) w = 1;
+  float row[7];
+  row[6] = -w * diff;
+  const float invFx = 1.0f / fx, invFy = 1.0f / fy;
+  const f3 cp = mk3((float)((zx - cx) * z * invFx), (float)((zy - cy) * z * invFy), z);
+  const float invz = (float)(1.0 / (double)cp.z);
+  const float dI_dx_val = w * sobelScale * gx;
+  const float dI_dy_val = w * sobelScale * gy;
+  const float v0 = dI_dx_val * fx * invz;
+  const float v1 = dI_dy_val * fy * invz;
+  const float v2 = -(v0 * cp.x + v1 * cp.y) * invz;
+  row[0] = v0;
+  row[1] = v1;
+  row[2] = v2;
+  row[3] = -cp.z * v1 + cp.y * v2;
+  row[4] = cp.z * v0 - cp.x * v2;
+  row[5] = -cp.y * v0 + cp.x * v1;
+  accumulate29(row, acc);
+}
+
+// Second launch of a Gauss-Newton iteration: every CTA first finishes the correspondence statistics of k_iter1 (sigma,
+// rgbError and the rgbOnly break decision, RGBDOdometry.cpp:442-455 incl. the operator-precedence quirk), then the
+// photometric rows over the candidate terms are reduced; the CTA that takes the last ticket sums all partials in double
+// and its first warp solves and updates the pose. mode bits: 1 = rgb rows, 2 = icp partials present, 4 = solve,
+// 8 = correspondence statistics present, 16 = use sigma_override.
+__global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, int iter, int next_level, int nblocks1, int mode, float sigma_override) {
   __shared__ GnScratch S;
+  __shared__ float sred[29 * (IT2_THREADS / 32)];
+  __shared__ int s_ints[2];
+  __shared__ float s_sigma;
+  __shared__ int s_break;
   GNState* gn = od.gn;
+  const bool do_rgb = mode & 1, do_icp = mode & 2, solve = mode & 4, have_res = mode & 8;
   if (solve && gn->break_level == level) {
     // rgbOnly `break`: the first iteration of the next level still needs its warp matrices
-    if (threadIdx.x == 0 && next_level >= 0 && next_level != level) gn_prepare_warp(gn, next_level);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && next_level >= 0 && next_level != level) gn_prepare_warp(gn, next_level);
     return;
   }
-  const int v = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  double a0 = 0, a1 = 0;
-  {
-    const float* p = od.partials;
-    int b = sl;
-    for (; b + 96 < nblocks; b += 128) {
-      const float x0 = p[(size_t)b * PARTIAL_STRIDE + v], x1 = p[(size_t)(b + 32) * PARTIAL_STRIDE + v];
-      const float x2 = p[(size_t)(b + 64) * PARTIAL_STRIDE + v], x3 = p[(size_t)(b + 96) * PARTIAL_STRIDE + v];
-      const float y0 = p[(size_t)b * PARTIAL_STRIDE + 32 + v], y1 = p[(size_t)(b + 32) * PARTIAL_STRIDE + 32 + v];
-      const float y2 = p[(size_t)(b + 64) * PARTIAL_STRIDE + 32 + v], y3 = p[(size_t)(b + 96) * PARTIAL_STRIDE + 32 + v];
-      a0 += ((double)x0 + (double)x1) + ((double)x2 + (double)x3);
-      a1 += ((double)y0 + (double)y1) + ((double)y2 + (double)y3);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    s_break = 0;
+    s_sigma = (mode & 16) ? sigma_override : gn->sigmaVal;
+  }
+  if (have_res) {
+    unsigned int c = 0, s = 0;
+    for (int b = threadIdx.x; b < nblocks1; b += IT2_THREADS) {
+      c += (unsigned int)od.partials_i[b * 2];
+      s += (unsigned int)od.partials_i[b * 2 + 1];
     }
-    for (; b < nblocks; b += 32) {
-      a0 += (double)p[(size_t)b * PARTIAL_STRIDE + v];
-      a1 += (double)p[(size_t)b * PARTIAL_STRIDE + 32 + v];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      c += __shfl_down_sync(0xffffffffu, c, off);
+      s += __shfl_down_sync(0xffffffffu, s, off);
+    }
+    int* si = reinterpret_cast<int*>(sred);
+    if (lane == 0) {
+      si[wid * 2] = (int)c;
+      si[wid * 2 + 1] = (int)s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int cc = 0, ss = 0;
+      for (int w = 0; w < IT2_THREADS / 32; ++w) {
+        cc += (unsigned int)si[w * 2];
+        ss += (unsigned int)si[w * 2 + 1];
+      }
+      const int rgbSize = (int)cc, sigma = (int)ss;
+      s_ints[0] = rgbSize;
+      s_ints[1] = sigma;
+      // reference: std::sqrt((float)sigma / rgbSize == 0 ? 1 : rgbSize)  (RGBDOdometry.cpp:442, App. A-1)
+      float sigmaVal = (float)sqrt((double)(((float)sigma / rgbSize == 0) ? 1 : rgbSize));
+      const float rgbError = (float)(sqrt((double)sigma) / (rgbSize == 0 ? 1 : rgbSize));
+      const float prevError = (iter == 0) ? FLT_MAX : gn->rgbErrBuf[(iter + 1) & 1];  // RGBDOdometry.cpp:404
+      const bool brk = solve && gn->rgbOnly && rgbError > prevError;
+      if (gn->rgbOnly) sigmaVal = -1;
+      if (!(mode & 16)) s_sigma = sigmaVal;
+      s_break = brk ? 1 : 0;
+      if (blockIdx.x == 0) {
+        gn->sum_res[0] = rgbSize;
+        gn->sum_res[1] = sigma;
+        if (solve) {
+          gn->rgbSize = rgbSize;
+          gn->sigma = sigma;
+          if (brk) {
+            gn->break_level = level;
+            if (next_level >= 0 && next_level != level) gn_prepare_warp(gn, next_level);
+          } else {
+            gn->rgbErrBuf[iter & 1] = rgbError;
+            gn->lastRGBError = rgbError;
+            gn->lastRGBCount = (float)rgbSize;
+            gn->sigmaVal = sigmaVal;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (s_break) return;
+  } else {
+    __syncthreads();
+  }
+
+  // every CTA pre-sums its share of the dense pass's per-CTA partials (double, fixed order) so the last CTA only has
+  // gridDim.x values per term left
+  if (do_icp && threadIdx.x < 32) {
+    const int per = (nblocks1 + gridDim.x - 1) / gridDim.x;
+    const int b0 = blockIdx.x * per, b1 = min(b0 + per, nblocks1);
+    double a = 0;
+    for (int b = b0; b < b1; ++b) a += (double)od.partials[(size_t)b * PARTIAL_STRIDE + threadIdx.x];
+    od.partials2[blockIdx.x * 32 + threadIdx.x] = a;
+  }
+  if (do_rgb) {
+    const float sigma = s_sigma;
+    float lfx, lfy, lcx, lcy;
+    level_intr(gn, level, lfx, lfy, lcx, lcy);
+    const int base = gn->cand_base[level], ncand = gn->cand_base[level + 1] - base;
+    const int4* __restrict__ terms = od.terms + base;
+    float acc[29];
+#pragma unroll
+    for (int k = 0; k < 29; ++k) acc[k] = 0.f;
+    for (int c = blockIdx.x * IT2_THREADS + threadIdx.x; c < ncand; c += gridDim.x * IT2_THREADS) {
+      const int4 t = terms[c];
+      if (t.x != -1) rgb_accumulate(t, sigma, lfx, lfy, lcx, lcy, od.sobelScale, acc);
+    }
+    __syncthreads();
+    block_reduce_sum<29, IT2_THREADS>(acc, sred);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < 29; ++k) od.partials_rgb[blockIdx.x * 32 + k] = acc[k];
     }
   }
-  S.dsm[sl][v] = do_icp ? a0 : 0.0;
-  S.dsm[sl][32 + v] = do_rgb ? a1 : 0.0;
+  if (!last_block_done(od.counter)) return;
+
+  // final sums in double, fixed order: 32 warps x 32 values
+  {
+    const int v = lane, sl = wid;
+    double a0 = 0, a1 = 0;
+    if (do_icp)
+      for (int b = sl; b < (int)gridDim.x; b += 32) a0 += od.partials2[b * 32 + v];
+    if (do_rgb)
+      for (int b = sl; b < (int)gridDim.x; b += 32) a1 += (double)od.partials_rgb[b * 32 + v];
+    S.dsm[sl][v] = a0;
+    S.dsm[sl][32 + v] = a1;
+  }
   __syncthreads();
   if (threadIdx.x < 64) {
     double t = 0;
@@ -628,143 +711,45 @@ __global__ void __launch_bounds__(1024) k_gn_update(OdomDev od, int level, int i
       gn->sum_rgb[threadIdx.x - 32] = f;
   }
   __syncthreads();
+  if (threadIdx.x == 0) *od.counter = 0;
   if (!solve || threadIdx.x >= 32) return;
   gn_update_warp(od, S, level, iter, next_level);
 }
 
-// Photometric correspondences + {count, sum diff^2}: RGBResidual / computeRgbResidual (reduce.cu:603-787).
-// The last CTA also derives sigma / rgbError exactly as the host does (RGBDOdometry.cpp:442-455, incl. the
-// operator-precedence quirk) so the following step launch needs nothing from the host.
-__global__ void __launch_bounds__(RES_THREADS, RES_CTAS_PER_SM) k_rgb_residual(OdomDev od, int level, int iter, int finalize) {
-  GNState* gn = od.gn;
-  if (finalize && gn->break_level == level) return;
-  __shared__ int sred_i[2 * (RES_THREADS / 32)];
-  const int rows = od.rows[level], cols = od.cols[level];
-  const int N = rows * cols;
-  const m33 krkinv = load_m33(gn->krkinv);
-  const f3 kt = mk3(gn->kt[0], gn->kt[1], gn->kt[2]);
-  const float minScale = od.minScale[level];
-  const int16_t* __restrict__ dIdx = od.dIdx[level];
-  const int16_t* __restrict__ dIdy = od.dIdy[level];
-  const float* __restrict__ lastDepth = od.lastDepth[level];
-  const float* __restrict__ nextDepth = od.nextDepth[level];
-  const uint8_t* __restrict__ lastImage = od.lastImage[level];
-  const uint8_t* __restrict__ nextImage = od.nextImage[level];
-  int4* __restrict__ corres4 = reinterpret_cast<int4*>(od.corres[level]);
-  unsigned int cnt = 0, sig = 0;
-  for (int k = blockIdx.x * RES_THREADS + threadIdx.x; k < N; k += gridDim.x * RES_THREADS) {
-    const int i = k / cols, j0 = k - i * cols;
-    // everything that does not depend on the warp is loaded up front, branch-free, so the loads overlap
-    const int valx = dIdx[k], valy = dIdy[k];
-    const float d1 = nextDepth[k];
-    const int nI = nextImage[k];
-    bool valid = (j0 < cols - 5 && i < rows - 1);
-    {
-      const int u0 = max(i - 2, 0), u1 = min(i + 2, rows), v0 = max(j0 - 2, 0), v1 = min(j0 + 2, cols);
-      int allpos = 1;
-#pragma unroll
-      for (int du = 0; du < 4; ++du)
-#pragma unroll
-        for (int dv = 0; dv < 4; ++dv) {
-          const int u = u0 + du, v = v0 + dv;
-          const bool in = (u < u1) && (v < v1);
-          const int px = in ? (int)nextImage[(size_t)u * cols + v] : 1;
-          allpos &= (px > 0);
-        }
-      valid = valid && allpos;
-    }
-    int4 out = make_int4(0, 0, 0, 0);  // DataTerm{zero, one, diff, valid} packed
-    if (valid) {
-      const float mTwo = (float)((valx * valx) + (valy * valy));
-      if (mTwo >= minScale && !isnan(d1)) {
-        const int y = i, x = j0;
-        const float transformed_d1 = (float)(d1 * (krkinv.r[2].x * x + krkinv.r[2].y * y + krkinv.r[2].z) + kt.z);
-        const int u0 = __float2int_rn((d1 * (krkinv.r[0].x * x + krkinv.r[0].y * y + krkinv.r[0].z) + kt.x) / transformed_d1);
-        const int v0 = __float2int_rn((d1 * (krkinv.r[1].x * x + krkinv.r[1].y * y + krkinv.r[1].z) + kt.y) / transformed_d1);
-        if (u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows) {
-          const float d0 = lastDepth[(size_t)v0 * cols + u0];
-          const int li = lastImage[(size_t)v0 * cols + u0];
-          if (d0 > 0 && fabsf(transformed_d1 - d0) <= od.maxDepthDeltaRGB && li != 0) {
-            const float diff = (float)nI - (float)li;
-            out.x = (u0 & 0xffff) | (v0 << 16);
-            out.y = (x & 0xffff) | (y << 16);
-            out.z = __float_as_int(diff);
-            out.w = 1;
-            cnt += 1;
-            sig += (unsigned int)__float2int_rz(diff * diff);
-          }
-        }
-      }
-    }
-    corres4[k] = out;
+// expands the compact per-candidate terms into the reference's dense DataTerm image (inspection / stage API only)
+__global__ void k_terms_expand(OdomDev od, int level) {
+  const GNState* gn = od.gn;
+  const int cols = od.cols[level];
+  const int base = gn->cand_base[level], ncand = gn->cand_base[level + 1] - base;
+  DataTerm* out = od.corres[level];
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncand; c += gridDim.x * blockDim.x) {
+    const int4 cr = od.cand[base + c], t = od.terms[base + c];
+    if (t.x == -1) continue;
+    DataTerm d;
+    d.zero_x = (short)(t.x & 0xffff);
+    d.zero_y = (short)(t.x >> 16);
+    d.one_x = (short)(cr.x % cols);
+    d.one_y = (short)(cr.x / cols);
+    d.diff = __int_as_float(t.y);
+    d.valid = 1;
+    out[cr.x] = d;
   }
-  // block reduce two ints (wrapping adds, like the reference's int2 sums)
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+}
+
+__device__ __forceinline__ void so3_final_sum(const float* partials, int nblocks, float* dst, double* dsm) {
+  const int v = threadIdx.x & 31, s = threadIdx.x >> 5;
+  double acc = 0;
+  if (v < 11)
+    for (int b = s; b < nblocks; b += RED_THREADS / 32) acc += (double)partials[(size_t)b * PARTIAL_STRIDE + v];
+  dsm[s * 32 + v] = acc;
+  __syncthreads();
+  if (s == 0 && v < 11) {
+    double t = 0;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    cnt += __shfl_down_sync(0xffffffffu, cnt, off);
-    sig += __shfl_down_sync(0xffffffffu, sig, off);
-  }
-  if (lane == 0) {
-    sred_i[wid * 2] = (int)cnt;
-    sred_i[wid * 2 + 1] = (int)sig;
+    for (int k = 0; k < RED_THREADS / 32; ++k) t += dsm[k * 32 + v];
+    dst[v] = (float)t;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int c = 0, s = 0;
-    for (int w = 0; w < RES_THREADS / 32; ++w) {
-      c += (unsigned int)sred_i[w * 2];
-      s += (unsigned int)sred_i[w * 2 + 1];
-    }
-    od.partials_i[blockIdx.x * 2] = (int)c;
-    od.partials_i[blockIdx.x * 2 + 1] = (int)s;
-  }
-  if (!last_block_done(od.counter)) return;
-  {
-    unsigned int c2 = 0, s2 = 0;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += RES_THREADS) {
-      c2 += (unsigned int)od.partials_i[b * 2];
-      s2 += (unsigned int)od.partials_i[b * 2 + 1];
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      c2 += __shfl_down_sync(0xffffffffu, c2, off);
-      s2 += __shfl_down_sync(0xffffffffu, s2, off);
-    }
-    __syncthreads();
-    if (lane == 0) {
-      sred_i[wid * 2] = (int)c2;
-      sred_i[wid * 2 + 1] = (int)s2;
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    unsigned int c = 0, s = 0;
-    for (int w = 0; w < RES_THREADS / 32; ++w) {
-      c += (unsigned int)sred_i[w * 2];
-      s += (unsigned int)sred_i[w * 2 + 1];
-    }
-    *od.counter = 0;
-    const int rgbSize = (int)c, sigma = (int)s;
-    gn->sum_res[0] = rgbSize;
-    gn->sum_res[1] = sigma;
-    if (finalize) {
-      gn->rgbSize = rgbSize;
-      gn->sigma = sigma;
-      // reference: std::sqrt((float)sigma / rgbSize == 0 ? 1 : rgbSize)  (RGBDOdometry.cpp:442, App. A-1)
-      float sigmaVal = (float)sqrt((double)(((float)sigma / rgbSize == 0) ? 1 : rgbSize));
-      const float rgbError = (float)(sqrt((double)sigma) / (rgbSize == 0 ? 1 : rgbSize));
-      const float prevError = (iter == 0) ? FLT_MAX : gn->lastRGBError;  // RGBDOdometry.cpp:404
-      if (gn->rgbOnly && rgbError > prevError) {
-        gn->break_level = level;
-      } else {
-        gn->lastRGBError = rgbError;
-        gn->lastRGBCount = (float)rgbSize;
-        if (gn->rgbOnly) sigmaVal = -1;
-        gn->sigmaVal = sigmaVal;
-      }
-    }
-  }
 }
 
 // SO3 pre-alignment step: SO3Reduction / so3Step + the host loop body (reduce.cu:789-973, RGBDOdometry.cpp:305-368)
@@ -834,7 +819,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_so3_step(OdomDev od, int iter, 
     for (int k = 0; k < 11; ++k) my_partial[k] = acc[k];
   }
   if (!last_block_done(od.counter)) return;
-  final_sum<RED_THREADS>(od.partials, gridDim.x, 0, 11, gn->sum_so3, dsm);
+  so3_final_sum(od.partials, gridDim.x, gn->sum_so3, dsm);
   if (threadIdx.x != 0) return;
   *od.counter = 0;
   if (!solve) return;
@@ -904,6 +889,13 @@ inline int red_blocks(const EfContext* ctx, int n_items, int per_thread, int thr
   return b;
 }
 
+inline int iter2_blocks(int npx, bool rgb, int nb1) {
+  int b = rgb ? (npx / 8 + IT2_THREADS - 1) / IT2_THREADS : 1;  // candidates are typically <= 1/8 of the pixels; the loop strides anyway
+  const int b_icp = (nb1 + 15) / 16;                            // <= 16 dense-pass partials pre-summed per CTA
+  if (b_icp > b) b = b_icp;
+  return b < 1 ? 1 : (b > MAX_RGB_BLOCKS ? MAX_RGB_BLOCKS : b);
+}
+
 #define EF_CHECK_LAST()                          \
   do {                                           \
     cudaError_t e__ = cudaGetLastError();        \
@@ -941,11 +933,11 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
   for (int s = 0; s < ns; ++s) {
     const int lv = sched_level[s];
     const int npx = od.rows[lv] * od.cols[lv];
-    if (rgb) EF_LAUNCH(ctx, k_rgb_residual, red_blocks(ctx, npx, 4, RES_THREADS, RES_CTAS_PER_SM), RES_THREADS, 0, od, lv, sched_iter[s], 1);
     const int next_lv = (s + 1 < ns) ? sched_level[s + 1] : -1;
-    const int nbs = red_blocks(ctx, npx, 4, SE3_THREADS, SE3_CTAS_PER_SM);
-    EF_LAUNCH(ctx, k_se3_step, nbs, SE3_THREADS, 0, od, lv, next_lv, icp ? 1 : 0, rgb ? 1 : 0, 1);
-    EF_LAUNCH(ctx, k_gn_update, 1, 1024, 0, od, lv, sched_iter[s], next_lv, nbs, icp ? 1 : 0, rgb ? 1 : 0, 1);
+    const int nb1 = red_blocks(ctx, npx, 4, IT1_THREADS, IT1_CTAS_PER_SM);
+    EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, lv, rgb ? 1 : 0, icp ? 1 : 0, 1);
+    const int nb2 = iter2_blocks(npx, rgb, icp ? nb1 : 0);
+    EF_LAUNCH(ctx, k_iter2, nb2, IT2_THREADS, 0, od, lv, sched_iter[s], next_lv, nb1, (rgb ? 1 | 8 : 0) | (icp ? 2 : 0) | 4, 0.f);
   }
   if (so3)
     for (int i = 0; i < NUM_PYRS; ++i) {  // RGBDOdometry.cpp:560-564: handle swap
@@ -972,18 +964,24 @@ int odom_set_pose_async(EfContext* ctx, int which, const double* T_dev) {
 }
 
 // stand-alone reduction launches for the stage API
-int launch_se3_step_raw(EfContext* ctx, int which, int level, bool do_icp, bool do_rgb) {
+int launch_se3_step_raw(EfContext* ctx, int which, int level, bool do_icp, bool do_rgb, float sigma) {
   OdomDev& od = ctx->odom[which];
-  const int nb = red_blocks(ctx, od.rows[level] * od.cols[level], 4, SE3_THREADS, SE3_CTAS_PER_SM);
-  EF_LAUNCH(ctx, k_se3_step, nb, SE3_THREADS, 0, od, level, -1, do_icp ? 1 : 0, do_rgb ? 1 : 0, 0);
-  EF_LAUNCH(ctx, k_gn_update, 1, 1024, 0, od, level, 0, -1, nb, do_icp ? 1 : 0, do_rgb ? 1 : 0, 0);
+  const int npx = od.rows[level] * od.cols[level];
+  const int nb1 = red_blocks(ctx, npx, 4, IT1_THREADS, IT1_CTAS_PER_SM);
+  if (do_icp) EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, level, 0, 1, 0);
+  EF_LAUNCH(ctx, k_iter2, iter2_blocks(npx, do_rgb, do_icp ? nb1 : 0), IT2_THREADS, 0, od, level, 0, -1, nb1, (do_rgb ? 1 | 16 : 0) | (do_icp ? 2 : 0), sigma);
   EF_CHECK_LAST();
   return 0;
 }
 int launch_rgb_residual_raw(EfContext* ctx, int which, int level) {
   OdomDev& od = ctx->odom[which];
-  const int nb = red_blocks(ctx, od.rows[level] * od.cols[level], 4, RES_THREADS, RES_CTAS_PER_SM);
-  EF_LAUNCH(ctx, k_rgb_residual, nb, RES_THREADS, 0, od, level, 0, 0);
+  const int npx = od.rows[level] * od.cols[level];
+  const int nb1 = red_blocks(ctx, npx, 4, IT1_THREADS, IT1_CTAS_PER_SM);
+  EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, level, 1, 0, 0);
+  EF_LAUNCH(ctx, k_iter2, 1, IT2_THREADS, 0, od, level, 0, -1, nb1, 8, 0.f);
+  cudaError_t e = cudaMemsetAsync(od.corres[level], 0, (size_t)npx * sizeof(DataTerm), ctx->stream);
+  if (e != cudaSuccess) return (int)e;
+  EF_LAUNCH(ctx, k_terms_expand, 128, 256, 0, od, level);
   EF_CHECK_LAST();
   return 0;
 }

@@ -260,24 +260,32 @@ __global__ void k_pyr_down_depth_image(const float* __restrict__ dsrc, float* __
   }
 }
 
-// computeDerivativeImages / applyKernel (cudafuncs.cu:612-668) for all three levels in one launch
+// computeDerivativeImages / applyKernel (cudafuncs.cu:612-668) for all three levels in one launch, fused with the
+// pose-independent gates of computeRgbResidual (reduce.cu:641-660): a pixel is a photometric *candidate* when
+// j < cols-5, i < rows-1, its 4x4 neighbourhood of the live image is non-zero, its gradient magnitude passes minScale and
+// its depth is finite. None of this changes across the 19 Gauss-Newton iterations, so it is evaluated once per frame and
+// the iterations only visit the compacted candidate list (typically ~10 % of the pixels at level 0).
 struct SobelArgs {
   const uint8_t* src[NUM_PYRS];
+  const float* depth[NUM_PYRS];
   int16_t* dx[NUM_PYRS];
   int16_t* dy[NUM_PYRS];
   int rows[NUM_PYRS], cols[NUM_PYRS];
+  int start[NUM_PYRS + 1];
+  float minScale[NUM_PYRS];
 };
-__global__ void k_sobel(SobelArgs a) {
-  const int lv = blockIdx.y;
-  const int rows = a.rows[lv], cols = a.cols[lv];
-  const size_t np = (size_t)rows * cols;
+__global__ void k_sobel_cand(SobelArgs a, uint8_t* __restrict__ flags) {
   const float gsx[9] = {(float)0.52201, (float)0.00000, (float)-0.52201, (float)0.79451, (float)-0.00000,
                         (float)-0.79451, (float)0.52201, (float)0.00000, (float)-0.52201};
   const float gsy[9] = {(float)0.52201, (float)0.79451, (float)0.52201, (float)0.00000, (float)0.00000,
                         (float)0.00000, (float)-0.52201, (float)-0.79451, (float)-0.52201};
-  const uint8_t* src = a.src[lv];
-  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += (size_t)gridDim.x * blockDim.x) {
-    const int y = (int)(p / cols), x = (int)(p - (size_t)y * cols);
+  const int total = a.start[NUM_PYRS];
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+    const int lv = (f >= a.start[2]) ? 2 : (f >= a.start[1] ? 1 : 0);
+    const int rows = a.rows[lv], cols = a.cols[lv];
+    const int p = f - a.start[lv];
+    const uint8_t* __restrict__ src = a.src[lv];
+    const int y = p / cols, x = p - y * cols;
     float dxVal = 0, dyVal = 0;
     int kernelIndex = 8;
     for (int j = max(y - 1, 0); j <= min(y + 1, rows - 1); j++)
@@ -287,8 +295,33 @@ __global__ void k_sobel(SobelArgs a) {
         dyVal += s * gsy[kernelIndex];
         --kernelIndex;
       }
-    a.dx[lv][p] = (int16_t)__float2int_rz(dxVal);
-    a.dy[lv][p] = (int16_t)__float2int_rz(dyVal);
+    const int valx = (int16_t)__float2int_rz(dxVal), valy = (int16_t)__float2int_rz(dyVal);
+    a.dx[lv][p] = (int16_t)valx;
+    a.dy[lv][p] = (int16_t)valy;
+    bool ok = (x < cols - 5 && y < rows - 1);
+    if (ok) {
+      const float mTwo = (float)((valx * valx) + (valy * valy));
+      ok = (mTwo >= a.minScale[lv]) && !isnan(a.depth[lv][p]);
+    }
+    if (ok) {
+      for (int u = max(y - 2, 0); u < min(y + 2, rows); u++)
+        for (int v = max(x - 2, 0); v < min(x + 2, cols); v++) ok = ok && (src[(size_t)u * cols + v] > 0);
+    }
+    flags[f] = ok ? 1 : 0;
+  }
+}
+
+__global__ void k_cand_scatter(SobelArgs a, const uint8_t* __restrict__ flags, const int* __restrict__ offsets, int4* __restrict__ cand,
+                               GNState* gn) {
+  const int total = a.start[NUM_PYRS];
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+    const int lv = (f >= a.start[2]) ? 2 : (f >= a.start[1] ? 1 : 0);
+    const int o = offsets[f];
+    if (f == a.start[lv]) gn->cand_base[lv] = o;  // exclusive prefix at the first pixel of the level
+    if (!flags[f]) continue;
+    const int p = f - a.start[lv];
+    const int g = ((int)(uint16_t)a.dx[lv][p]) | (((int)(uint16_t)a.dy[lv][p]) << 16);
+    cand[o] = make_int4(p, __float_as_int(a.depth[lv][p]), g, (int)a.src[lv][p]);
   }
 }
 
@@ -314,6 +347,8 @@ inline int flat_blocks(const EfContext* ctx, size_t n) {
 }  // namespace
 
 namespace ef {
+int run_scan(EfContext* ctx, const uint8_t* flags, const int* n_a, const int* n_b, size_t max_items, int* offsets, int* total);
+void scan_scratch(EfContext* ctx, uint8_t** flags, int** offsets);
 
 int odom_init_icp_depth(EfContext* ctx, int which, const uint16_t* depth_dev, float cutoff) {
   OdomDev& od = ctx->odom[which];
@@ -399,12 +434,23 @@ int launch_sobel(EfContext* ctx, int which) {
   SobelArgs a;
   for (int i = 0; i < NUM_PYRS; ++i) {
     a.src[i] = od.nextImage[i];
+    a.depth[i] = od.nextDepth[i];
     a.dx[i] = od.dIdx[i];
     a.dy[i] = od.dIdy[i];
     a.rows[i] = od.rows[i];
     a.cols[i] = od.cols[i];
+    a.start[i] = od.level_start[i];
+    a.minScale[i] = od.minScale[i];
   }
-  EF_LAUNCH(ctx, k_sobel, dim3(flat_blocks(ctx, (size_t)od.width * od.height), NUM_PYRS), 256, 0, a);
+  a.start[NUM_PYRS] = od.level_start[NUM_PYRS];
+  const size_t flat = (size_t)od.level_start[NUM_PYRS];
+  uint8_t* flags;
+  int* offsets;
+  scan_scratch(ctx, &flags, &offsets);
+  EF_LAUNCH(ctx, k_sobel_cand, flat_blocks(ctx, flat), 256, 0, a, flags);
+  int rc = run_scan(ctx, flags, &od.gn->flat_n, nullptr, flat, offsets, &od.gn->cand_base[NUM_PYRS]);
+  if (rc) return rc;
+  EF_LAUNCH(ctx, k_cand_scatter, flat_blocks(ctx, flat), 256, 0, a, (const uint8_t*)flags, (const int*)offsets, od.cand, od.gn);
   EF_CHECK_LAST();
   return 0;
 }
