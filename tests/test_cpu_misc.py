@@ -1,0 +1,239 @@
+"""CPU tests: C-ABI surface, synthetic data / .klg format, analytic known-answer tests of the oracle, multi-process logic."""
+import ctypes
+import os
+import re
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------- C ABI
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "efusion_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(ef_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    """libefusion.so must load without a GPU and export every entry point include/efusion_b200.h declares."""
+    so = os.path.join(ROOT, "elasticfusion_b200", "libefusion.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["bash", os.path.join(ROOT, "build.sh")])
+    lib = ctypes.CDLL(so)
+    names = _declared_symbols()
+    assert len(names) >= 45
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_abi_argument_validation_without_gpu():
+    from elasticfusion_b200 import capi
+
+    cfg = capi.default_config(640, 480, 528.0, 528.0, 320.0, 240.0)
+    assert (cfg.time_delta, cfg.count_thresh, cfg.confidence, cfg.depth_cutoff, cfg.icp_weight, cfg.so3) == (200, 35000, 10.0, 3.0, 10.0, 1)
+    assert abs(cfg.err_thresh - 5e-5) < 1e-10 and abs(cfg.fern_thresh - 0.3095) < 1e-6 and cfg.capacity == 3072 * 3072
+    out = ctypes.c_void_p()
+    lib = capi.lib()
+    assert lib.ef_create(None, None, ctypes.byref(out)) == -1  # EF_EINVAL
+    cfg.close_loops = 1
+    assert lib.ef_create(ctypes.byref(cfg), None, ctypes.byref(out)) == -1  # loop closure is out of scope
+    assert lib.ef_error_string(-1).decode() == "invalid argument"
+    assert lib.ef_sync(None) == -1 and lib.ef_process_frame(None, None, None, 0, ctypes.c_float(1), None) == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from elasticfusion_b200 import capi
+
+    monkeypatch.setattr(capi, "_LIB", None)
+    monkeypatch.setattr(capi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(capi.EfError):
+        capi.lib()
+
+
+# ---------------------------------------------------------------- synthetic data and .klg
+def test_klg_roundtrip_and_layout(tmp_path, small_K, small_frames):
+    from elasticfusion_b200 import synth
+
+    p = str(tmp_path / "s.klg")
+    synth.write_klg(p, [(f[0], f[1]) for f in small_frames])
+    raw = open(p, "rb").read()
+    n_px = small_K.width * small_K.height
+    assert struct.unpack("<i", raw[:4])[0] == len(small_frames)
+    ts, dsz, isz = struct.unpack("<qii", raw[4:20])
+    assert (ts, dsz, isz) == (0, 2 * n_px, 3 * n_px)  # raw payload sizes select the uncompressed path of RawLogReader
+    back = list(synth.read_klg(p, small_K.width, small_K.height))
+    assert len(back) == len(small_frames)
+    for (ts, rgb, d), (rgb0, d0, _) in zip(back, small_frames):
+        assert np.array_equal(rgb, rgb0) and np.array_equal(d, d0)
+
+
+def test_render_is_consistent_with_ground_truth_pose(small_K):
+    """Back-project frame 1, move it by the ground-truth relative pose, re-project into frame 0: depths agree to the mm."""
+    from elasticfusion_b200 import synth
+
+    K = small_K
+    fr = list(synth.sequence(2, K, seed=3, noise=False, speed=6.0))
+    d0, d1 = fr[0][1].astype(np.float64) / 1000, fr[1][1].astype(np.float64) / 1000
+    T01 = fr[1][2]
+    u, v = np.meshgrid(np.arange(K.width), np.arange(K.height))
+    P1 = np.stack([(u - K.cx) / K.fx * d1, (v - K.cy) / K.fy * d1, d1, np.ones_like(d1)], -1) @ T01.T
+    ui = np.rint(P1[..., 0] / P1[..., 2] * K.fx + K.cx).astype(int)
+    vi = np.rint(P1[..., 1] / P1[..., 2] * K.fy + K.cy).astype(int)
+    ok = (ui >= 0) & (ui < K.width) & (vi >= 0) & (vi < K.height) & (d1 > 0)
+    diff = P1[..., 2][ok] - d0[vi[ok], ui[ok]]
+    assert abs(np.median(diff)) < 2e-3
+    assert fr[0][0].min() >= 1  # no zero intensities (nextImage > 0 gate)
+
+
+# ---------------------------------------------------------------- analytic KATs of the oracle
+def test_icp_converges_to_ground_truth_on_exact_maps(small_K):
+    """Planar room, noise-free float vertex/normal maps: the point-plane system has zero residual at the true pose, so
+    Gauss-Newton on the oracle's A, b must converge to the ground-truth relative pose (micrometres)."""
+    from elasticfusion_b200 import synth
+    from oracle import ef_oracle as eo
+
+    K = small_K
+    traj = synth.trajectory(2, seed=5, speed=6.0)
+    T01 = np.linalg.inv(traj[0]) @ traj[1]
+    H, W = K.height, K.width
+
+    def maps(T):
+        _, _, z, n = synth.render(T, K)
+        u, v = np.meshgrid(np.arange(W), np.arange(H))
+        z = np.where(z < 6, z, np.nan)
+        vm = np.concatenate([(u - K.cx) / K.fx * z, (v - K.cy) / K.fy * z, z], 0).astype(np.float32)
+        nm = np.concatenate([n[..., 0], n[..., 1], n[..., 2]], 0).astype(np.float32)
+        nm[:H][np.isnan(z)] = np.nan
+        return np.ascontiguousarray(vm), np.ascontiguousarray(nm)
+
+    vm0, nm0 = maps(traj[0])
+    vm1, nm1 = maps(traj[1])
+    ang = float(np.sin(np.float32(20.0) * np.float32(3.14159254) / np.float32(180.0)))
+
+    def rodr(w):
+        th = np.linalg.norm(w)
+        if th < 1e-12:
+            return np.eye(3)
+        k = w / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+
+    resultRt, Rc, tc = np.eye(4), np.eye(3), np.zeros(3)
+    for _ in range(12):
+        A, b, res = eo.icp_step(Rc, tc, vm1, nm1, np.eye(3), np.zeros(3), K.fx, K.fy, K.cx, K.cy, vm0, nm0, 0.10, ang)
+        x = np.linalg.solve(A.astype(np.float64), b.astype(np.float64))
+        upd = np.eye(4)
+        upd[:3, :3], upd[:3, 3] = rodr(x[3:]), x[:3]
+        resultRt = upd @ resultRt
+        inv = np.linalg.inv(resultRt)
+        Rc, tc = inv[:3, :3], inv[:3, 3]
+    assert res[1] > 0.5 * H * W
+    assert np.linalg.norm(tc - T01[:3, 3]) < 5e-6
+    assert np.abs(Rc - T01[:3, :3]).max() < 5e-6
+    assert np.allclose(A, A.T)
+
+
+def test_preprocess_kats():
+    from oracle import ef_oracle as eo
+
+    d = np.full((40, 50), 1500, np.uint16)
+    assert np.array_equal(eo.bilateral(d, 3.0), d)  # constant depth is a fixed point of the bilateral filter
+    d[5, 5], d[6, 6], d[7, 7] = 200, 3001, 0  # < 300 mm, > cutoff, missing
+    f = eo.bilateral(d, 3.0)
+    assert f[5, 5] == 0 and f[6, 6] == 0 and f[7, 7] == 0
+    m = eo.metric(d, 3.0)
+    assert m[5, 5] == 0 and m[6, 6] == 0 and m[0, 0] == np.float32(1.5)
+    p = eo.pyr_down_u16(np.full((8, 8), 1000, np.uint16))
+    assert p.shape == (4, 4) and (p == 1000).all()
+
+
+def test_index_map_depth_test_and_id_zero_quirk(small_K):
+    """Two surfels on the same pixel: the nearer wins; equal depth -> lower id wins; surfel 0 is indistinguishable from empty."""
+    from oracle import ef_oracle as eo
+
+    K = small_K
+
+    def surfel(x, y, z, t=1.0):
+        return [x, y, z, 1.0, 123456.0, 0, 1.0, t, 0, 0, -1, 0.01]
+
+    s = np.array([surfel(0, 0, 2.0), surfel(0, 0, 1.0), surfel(0.3, 0, 1.5), surfel(0.3, 0, 1.5)], np.float32)
+    idx, vc, ct, nr = eo.predict_indices(s, np.eye(4), 2, 20.0, 1 << 30, K)
+    cy, cx = int(K.cy), int(K.cx)
+    assert idx[cy, cx] == 1 and vc[cy, cx, 2] == 1.0
+    px = int(np.floor(K.fx * 0.3 / 1.5 + K.cx))
+    assert idx[cy, px] == 2  # equal depth: earlier primitive
+    assert (idx > 0).sum() == 2
+    s0 = np.array([surfel(0, 0, 1.0)], np.float32)
+    idx0, vc0, _, _ = eo.predict_indices(s0, np.eye(4), 2, 20.0, 1 << 30, K)
+    assert idx0.max() == 0 and vc0[cy, cx, 2] == 1.0  # attributes are written but the id reads as "empty" (App. A-18)
+
+
+def test_raycast_single_surfel_disc(small_K):
+    from oracle import ef_oracle as eo
+
+    K = small_K
+    r = 0.05
+    s = np.array([[0, 0, 1.0, 20.0, float((200 << 16) + (100 << 8) + 50), 0, 3.0, 5.0, 0, 0, -1, r]], np.float32)
+    img, vtx, nrm, tm = eo.combined_predict(s, np.eye(4), 20.0, 10.0, 5, 5, 1 << 30, K)
+    hit = vtx[..., 2] > 0
+    area = hit.sum()
+    expected = np.pi * (r * K.fx) ** 2  # fronto-parallel disc of radius r at z = 1
+    assert abs(area - expected) / expected < 0.15
+    assert np.allclose(vtx[..., 2][hit], 1.0, atol=1e-6)
+    assert (img[hit][:, :3] == [200, 100, 50]).all() and (img[hit][:, 3] == 255).all() and (tm[hit] == 3).all()
+    lo = np.array([[0, 0, 1.0, 5.0, 1.0, 0, 3.0, 5.0, 0, 0, -1, r]], np.float32)  # confidence below the threshold: not rendered
+    assert eo.combined_predict(lo, np.eye(4), 20.0, 10.0, 5, 5, 1 << 30, K)[1][..., 2].max() == 0
+
+
+def test_fuse_clean_invariants(small_K, small_frames):
+    """Map order invariant (App. A-22): surfels stay sorted by init time and new ones are appended; fuse never moves ids."""
+    from oracle import ef_oracle as eo
+
+    f = eo.Fusion(small_K, capacity=100000)
+    counts = []
+    for i, (rgb, d, _) in enumerate(small_frames):
+        f.process_frame(rgb, d, i)
+        m = f.map()
+        counts.append(len(m))
+        assert (np.diff(m[:, 6]) >= 0).all()  # init times non-decreasing
+        assert (m[:, 7] >= m[:, 6]).all() and (m[:, 7] <= f.tick).all()
+    assert counts[0] > 1000 and counts[-1] > counts[0]
+    assert f.tick == len(small_frames) + 1
+
+
+# ---------------------------------------------------------------- multi-process host logic (gloo, world_size 2)
+def _worker(rank, world, port, out_q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from elasticfusion_b200 import multi
+
+    seqs = multi.shard_sequences(5, world, rank)
+    multi.barrier(dist)
+    agg = multi.aggregate_throughput(dist, multi.local_frames(10, seqs), 0.5 * (rank + 1))
+    out_q.put((rank, seqs, agg))
+    dist.destroy_process_group()
+
+
+def test_sharding_and_aggregation_gloo_world2():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][1] == [0, 2, 4] and res[1][1] == [1, 3]
+    for _, _, agg in res:
+        assert agg["frames"] == 50 and agg["seconds"] == 1.0 and agg["fps"] == 50.0
