@@ -1,0 +1,39 @@
+// The reference README's "How do I just use the Core API?" program (README.md:74-100), against libefusion.so (B200).
+// Usage: core_api_example <raw.klg> <width> <height> <fx> <fy> <cx> <cy>   -> prints the final pose and surfel count.
+#include <ElasticFusion.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+int main(int argc, char** argv) {
+  if (argc < 8) return 2;
+  const int w = std::atoi(argv[2]), h = std::atoi(argv[3]);
+  Resolution::getInstance(w, h);
+  Intrinsics::getInstance((float)std::atof(argv[4]), (float)std::atof(argv[5]), (float)std::atof(argv[6]), (float)std::atof(argv[7]));
+  // open loop, as `ElasticFusion -o` configures it (MainController.cpp:179-183)
+  ElasticFusion eFusion(2147483647 / 2, 35000, 5e-05, 1e-05, false, false, false, 115, 10, 3, 10, false, 0.3095, true, false, "/tmp/ef_b200_example",
+                        500000);
+  FILE* f = std::fopen(argv[1], "rb");
+  if (!f) return 3;
+  int32_t numFrames = 0;
+  if (std::fread(&numFrames, 4, 1, f) != 1) return 4;
+  std::vector<uint8_t> rgb((size_t)w * h * 3);
+  std::vector<uint16_t> depth((size_t)w * h);
+  for (int i = 0; i < numFrames; ++i) {
+    int64_t ts;
+    int32_t dsz, isz;
+    if (std::fread(&ts, 8, 1, f) != 1 || std::fread(&dsz, 4, 1, f) != 1 || std::fread(&isz, 4, 1, f) != 1) return 5;
+    if (dsz != w * h * 2 || isz != w * h * 3) return 6;  // raw payloads only (Tools/RawLogReader.cpp:80-97)
+    if (std::fread(depth.data(), 1, dsz, f) != (size_t)dsz || std::fread(rgb.data(), 1, isz, f) != (size_t)isz) return 7;
+    eFusion.processFrame(rgb.data(), depth.data(), ts, 1.0f);
+  }
+  std::fclose(f);
+  const auto T = eFusion.get_T_wc().matrix();
+  std::printf("POSE");
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) std::printf(" %.9f", (double)T(r, c));
+  std::printf("\nCOUNT %u TICK %d\n", eFusion.getGlobalModel().lastCount(), eFusion.getTick());
+  return 0;
+}
