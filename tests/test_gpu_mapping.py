@@ -187,3 +187,31 @@ def test_pipeline_matches_oracle(frames, K):
         assert ctx.get_tick() == f.tick
     finally:
         ctx.close()
+
+
+def test_sequence_ate_vs_oracle(K):
+    """BASELINE.json parity bar for the whole path: estimated SE(3) trajectory within 1e-3 m ATE of the oracle run on the
+    same 60-frame noisy synthetic sequence (model-based tracking kicks in once surfels become stable), surfel count within
+    0.5 %, and both runs agree with ground truth to the same accuracy."""
+    from elasticfusion_b200 import synth
+
+    n = 60
+    frames = list(synth.sequence(n, K, seed=11, noise=True))
+    f = run_oracle(frames, K, 0, capacity=600000)
+    ctx = make_ctx(K, capacity=600000)
+    est_p, est_o = [], []
+    try:
+        for i, (rgb, depth, _) in enumerate(frames):
+            f.process_frame(rgb, depth, i * 33333)
+            ctx.process_frame(rgb, depth, i * 33333)
+            est_p.append(ctx.get_pose())
+            est_o.append(f.pose)
+        est_p, est_o = np.array(est_p), np.array(est_o)
+        gt = np.array([fr[2] for fr in frames])
+        ate_po = synth.ate_rmse(est_p, est_o)
+        assert ate_po < 1e-3, ate_po
+        assert abs(synth.ate_rmse(est_p, gt) - synth.ate_rmse(est_o, gt)) < 1e-3
+        assert abs(ctx.map_count() - f.count) <= 5e-3 * f.count, (ctx.map_count(), f.count)
+        assert np.abs(est_p[-1][:3, :3] - est_o[-1][:3, :3]).max() < 1e-3
+    finally:
+        ctx.close()
