@@ -204,6 +204,17 @@ static int alloc_odom(EfContext* ctx, OdomDev& od) {
   g.fy = c.fy;
   g.cx = c.cx;
   g.cy = c.cy;
+  for (int lv = 0; lv < NUM_PYRS; ++lv) {
+    const int div = 1 << lv;  // CameraModel::operator()(level), reference Core/Cuda/types.cuh:92-95
+    const double fx = (double)(c.fx / div), fy = (double)(c.fy / div), cx = (double)(c.cx / div), cy = (double)(c.cy / div);
+    const double K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+    const double ifx = 1.0 / fx, ify = 1.0 / fy;
+    const double Ki[9] = {ifx, 0, -cx * ifx, 0, ify, -cy * ify, 0, 0, 1};
+    for (int k = 0; k < 9; ++k) {
+      g.Kd[lv][k] = K[k];
+      g.Kinvd[lv][k] = Ki[k];
+    }
+  }
   g.break_level = -1;
   g.weighting = 1.0f;
   g.flat_n = od.level_start[NUM_PYRS];
@@ -845,3 +856,8 @@ extern "C" int ef_process_frame(EfContext* ctx, const uint8_t* rgb, const uint16
   ctx->host_count = *(int*)(s + 128);
   return 0;
 }
+
+// debug exports (phase profiling builds)
+extern "C" void* ef_debug_gn(EfContext* ctx, int which) { return ctx ? (void*)ctx->odom[which].gn : nullptr; }
+extern "C" int ef_debug_gn_size() { return (int)sizeof(GNState); }
+extern "C" int ef_debug_dbg_offset() { return (int)offsetof(GNState, dbg); }

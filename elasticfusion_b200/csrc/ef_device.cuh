@@ -59,31 +59,42 @@ __device__ __forceinline__ f3 rot(const float* m, const f3& v) {
              (m[8] * v.x + m[9] * v.y) + m[10] * v.z);
 }
 
-// warp / block sum of N floats held per thread; result valid in thread 0 of the block.
+// Warp sum of up to 32 per-lane values by recursive halving ("transpose-reduce"): at each of the 5 stages a lane keeps
+// half of its values and trades the other half with its partner, so 32 values cost 31 shuffles + 31 adds instead of
+// 32 x 5 for independent shuffle trees. On return lane l holds the warp total of value l in v[0].
+template <int N>
+__device__ __forceinline__ float warp_reduce_transpose(const float (&in)[N]) {
+  static_assert(N <= 32, "at most 32 values");
+  const int lane = threadIdx.x & 31;
+  float v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = (k < N) ? in[k] : 0.f;
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int k = 0; k < half; ++k) {
+      const float send = upper ? v[k] : v[k + half];
+      const float keep = upper ? v[k + half] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+// block sum of N (<= 32) floats held per thread; on return threads 0..N-1 hold the CTA total of value threadIdx.x in v[0]
+// (fixed summation order: butterfly inside a warp, then warps in index order).
 template <int N, int THREADS>
-__device__ __forceinline__ void block_reduce_sum(float (&v)[N], float* smem /* N * (THREADS/32) floats */) {
+__device__ __forceinline__ void block_reduce_sum(float (&v)[N], float* smem /* 32 * (THREADS/32) floats */) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < N; ++k) {
-    float x = v[k];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-    v[k] = x;
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < N; ++k) smem[wid * N + k] = v[k];
-  }
+  const float mine = warp_reduce_transpose<N>(v);
+  smem[wid * 32 + lane] = mine;
   __syncthreads();
   if (wid == 0) {
-    constexpr int NW = THREADS / 32;
+    float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      float x = (lane < NW) ? smem[lane * N + k] : 0.f;
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-      v[k] = x;
-    }
+    for (int w = 0; w < THREADS / 32; ++w) t += smem[w * 32 + lane];
+    v[0] = t;
   }
 }
 

@@ -12,7 +12,7 @@ constexpr int RED_THREADS = 256;     // threads per reduction CTA
 constexpr int MAX_RED_BLOCKS = 1184; // 148 SMs x 8 resident 256-thread CTAs
 constexpr int PARTIAL_STRIDE = 64;   // floats per CTA partial: [0,29) geometric system, [32,61) photometric system
 constexpr int MAX_TRACE = 48;
-constexpr int MAX_RGB_BLOCKS = 64;
+constexpr int MAX_RGB_BLOCKS = 160;
 
 // reference DataTerm (Core/Cuda/types.cuh:79-84): 16 bytes, bool widened to int32
 struct DataTerm {
@@ -45,15 +45,18 @@ struct GNState {
 
   float sum_icp[32], sum_rgb[32], sum_so3[12];  // last reduced systems (reference JtJJtrSE3 / JtJJtrSO3 order)
   int sum_res[2];                               // last {count, sigma} of the residual pass
+  unsigned int res_acc[2];                      // accumulators of the running residual pass (re-armed by k_iter2)
 
   int rgbOnly, icp, rgb, so3;
   float icpWeight;
   float fx, fy, cx, cy;
+  double Kd[NUM_PYRS][9], Kinvd[NUM_PYRS][9];  // per-level K (float intrinsics / 2^level, widened) and its inverse
   int trace_n;
   int cand_base[NUM_PYRS + 1];  // photometric candidates of level L live in cand[cand_base[L], cand_base[L+1])
   int flat_n;                   // total pixels over the three levels
   float rgbErrBuf[2];           // rgbError of the previous / current iteration (double-buffered across CTAs)
   float weighting;  // velocity weighting for fusion (ElasticFusion.cpp:369-383)
+  long long dbg[32];  // phase timestamps (clock64) when built with -DEF_PROFILE_PHASES
 };
 
 // pose matrices consumed by the map kernels (float, as the reference's shader uniforms)

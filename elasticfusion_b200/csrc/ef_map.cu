@@ -105,6 +105,27 @@ __device__ __forceinline__ unsigned int depth24(float zw) {
   return (unsigned int)rintf(zw * 16777215.0f);
 }
 
+
+// The reference walks a 4x4 sample window with float loop counters (data.vert:132-160, copy_unstable.vert:75-111):
+//   for (float i = c - 2*step; i < c + 2*step; i += step)   with step = half a texel, nearest sampling.
+// The samples land on <= 3 distinct texels per axis, some of them twice. This evaluates the float loop literally once per axis
+// and returns the distinct texel indices (ascending, first-occurrence order) with how many samples hit each.
+__device__ __forceinline__ int window_axis(float centre, float step, int n, int (&tex)[3], int (&mult)[3]) {
+  int cnt = 0;
+  const float lo = centre - (1.0f * step * 2.0f), hi = centre + (1.0f * step * 2.0f);
+  for (float i = lo; i < hi; i += step) {
+    const int t = texel(i, n);
+    if (cnt > 0 && tex[cnt - 1] == t) {
+      mult[cnt - 1]++;
+    } else if (cnt < 3) {
+      tex[cnt] = t;
+      mult[cnt] = 1;
+      cnt++;
+    }
+  }
+  return cnt;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // pose upload: T_wc (double) -> float pose and float inverse, as the shader uniforms (GlobalModel.cpp:405,562)
 // ---------------------------------------------------------------------------------------------------------------
@@ -168,26 +189,36 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_flags(const uint8_t* __re
     const int warp_excl = wid ? s_warp[wid - 1] : 0;
     const int thread_excl = warp_excl + incl - sum;
     const int aggregate = s_warp[SCAN_THREADS / 32 - 1];
-    // publish aggregate, look back for the exclusive prefix
-    if (threadIdx.x == 0) {
+    // publish the aggregate, then look back for the exclusive prefix 32 predecessors at a time (decoupled look-back:
+    // status 1 = aggregate only, 2 = inclusive prefix; status and value share one 64-bit word, so no fence is needed)
+    if (wid == 0) {
+      volatile unsigned long long* vstate = state;
       int prefix = 0;
       if (tile == 0) {
-        atomicExch(&state[0], (2ull << 32) | (unsigned int)aggregate);
+        if (lane == 0) vstate[0] = (2ull << 32) | (unsigned int)aggregate;
       } else {
-        atomicExch(&state[tile], (1ull << 32) | (unsigned int)aggregate);
+        if (lane == 0) vstate[tile] = (1ull << 32) | (unsigned int)aggregate;
         int look = tile - 1;
         while (true) {
-          const unsigned long long s = atomicAdd(&state[look], 0ull);
-          const unsigned int st = (unsigned int)(s >> 32);
-          if (st == 0) continue;
-          prefix += (int)(unsigned int)(s & 0xffffffffull);
-          if (st == 2) break;
-          --look;
+          const int idx = look - lane;
+          const unsigned long long w = (idx >= 0) ? vstate[idx] : (2ull << 32);
+          const unsigned int st = (unsigned int)(w >> 32);
+          if (__any_sync(0xffffffffu, st == 0)) continue;  // a predecessor has not published yet: re-read
+          const unsigned int m2 = __ballot_sync(0xffffffffu, st == 2);
+          const int first2 = m2 ? (__ffs(m2) - 1) : 32;
+          int val = (lane <= first2) ? (int)(unsigned int)(w & 0xffffffffull) : 0;
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
+          prefix += val;
+          if (m2) break;
+          look -= 32;
         }
-        atomicExch(&state[tile], (2ull << 32) | (unsigned int)(prefix + aggregate));
+        if (lane == 0) vstate[tile] = (2ull << 32) | (unsigned int)(prefix + aggregate);
       }
-      s_prefix = prefix;
-      if (tile == num_tiles - 1 && total_out) *total_out = prefix + aggregate;
+      if (lane == 0) {
+        s_prefix = prefix;
+        if (tile == num_tiles - 1 && total_out) *total_out = prefix + aggregate;
+      }
     }
     __syncthreads();
     int run = s_prefix + thread_excl;
@@ -314,7 +345,20 @@ struct FuseArgs {
   float max_depth;
 };
 
-// measurement surfel of pixel (i,j) as data.vert builds it; returns false if the pixel takes no part this frame
+// Only pixels with x % 2 == y % 2 == time % 2 take part in a frame (data.vert:112): the fuse kernels run
+// over that quarter grid. q -> (i, j) keeps the reference's draw order (x-major), so compaction order is unchanged.
+struct Quarter {
+  int p, ni, nj;
+};
+__device__ __host__ __forceinline__ Quarter quarter_of(int time, int rows, int cols) {
+  Quarter q;
+  q.p = ((time % 2) + 2) % 2;
+  q.ni = (cols - q.p + 1) / 2;
+  q.nj = (rows - q.p + 1) / 2;
+  return q;
+}
+
+// measurement geometry of pixel (i,j) as data.vert builds it; returns false if the pixel takes no part this frame
 __device__ __forceinline__ bool fuse_active(const FuseArgs& a, int i, int j, float& tcx, float& tcy, float& x, float& y, f3& vPosLocal) {
   tcx = uv_coord(i, a.cols);
   tcy = uv_coord(j, a.rows);
@@ -335,10 +379,12 @@ constexpr uint32_t ASSOC_NONE = 0xffffffffu, ASSOC_NEW = 0xfffffffeu;
 
 __global__ void k_fuse_associate(FuseArgs a, const int* __restrict__ count, uint32_t* __restrict__ assoc, uint32_t* __restrict__ pending,
                                  uint8_t* __restrict__ new_flags) {
-  const int n = a.rows * a.cols;
+  const Quarter Q = quarter_of(a.time, a.rows, a.cols);
+  const int nq = Q.ni * Q.nj;
   const int cnt = *count;
-  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
-    const int i = d / a.rows, j = d - i * a.rows;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+    const int i = 2 * (q / Q.nj) + Q.p, j = 2 * (q % Q.nj) + Q.p;
+    const uint32_t d = (uint32_t)i * a.rows + j;  // draw index in the reference's uv buffer
     float tcx, tcy, x, y;
     f3 vPosLocal;
     uint32_t res = ASSOC_NONE;
@@ -354,14 +400,18 @@ __global__ void k_fuse_associate(FuseArgs a, const int* __restrict__ count, uint
       const float indexXStep = (1.0f / (fcols * scale)) * 0.5f;
       const float indexYStep = (1.0f / (frows * scale)) * 0.5f;
       float bestDist = 1000;
-      const float windowMultiplier = 2;
       const float xl = (x - a.c.cx) * ifx;
       const float yl = (y - a.c.cy) * ify;
       const float lambda = sqrtf(xl * xl + yl * yl + 1);
       const f3 ray = mk3(xl, yl, 1);
-      for (float ii = tcx - (scale * indexXStep * windowMultiplier); ii < tcx + (scale * indexXStep * windowMultiplier); ii += indexXStep)
-        for (float jj = tcy - (scale * indexYStep * windowMultiplier); jj < tcy + (scale * indexYStep * windowMultiplier); jj += indexYStep) {
-          const int p = texel(jj, a.rows) * a.cols + texel(ii, a.cols);
+      // duplicates of a texel cannot change the outcome (strict `dist < bestDist`), so each distinct texel is visited once,
+      // in the reference's order (x outer, y inner, ascending)
+      int tx[3], mx[3], ty[3], my[3];
+      const int nx = window_axis(tcx, indexXStep, a.cols, tx, mx);
+      const int ny = window_axis(tcy, indexYStep, a.rows, ty, my);
+      for (int ia = 0; ia < nx; ++ia)
+        for (int jb = 0; jb < ny; ++jb) {
+          const int p = ty[jb] * a.cols + tx[ia];
           const uint32_t current = a.index[p];
           if (current > 0U) {
             const float4 vc = a.vert_conf[p];
@@ -380,14 +430,14 @@ __global__ void k_fuse_associate(FuseArgs a, const int* __restrict__ count, uint
         }
       if (counter > 0) {
         res = best;
-        if ((int)best < cnt) atomicMin(&pending[best], (uint32_t)d);  // lowest draw index wins the update-map texel
+        if ((int)best < cnt) atomicMin(&pending[best], d);  // lowest draw index wins the update-map texel
       } else {
         res = ASSOC_NEW;
         is_new = 1;
       }
     }
-    assoc[d] = res;
-    new_flags[d] = is_new;
+    assoc[q] = res;
+    new_flags[q] = is_new;
   }
 }
 
@@ -412,25 +462,27 @@ __global__ void k_fuse_update(FuseArgs a, const MapPose* __restrict__ mp, const 
                               const int* __restrict__ new_total, float4* __restrict__ pos_conf, float4* __restrict__ color_time,
                               float4* __restrict__ norm_rad, float4* __restrict__ new_pos, float4* __restrict__ new_col,
                               float4* __restrict__ new_nr, int* __restrict__ new_count) {
-  const int n = a.rows * a.cols;
+  const Quarter Q = quarter_of(a.time, a.rows, a.cols);
+  const int nq = Q.ni * Q.nj;
   const int cnt = *count;
   const float weighting = gn->weighting;
   if (blockIdx.x == 0 && threadIdx.x == 0) *new_count = *new_total;
-  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
-    const uint32_t as = assoc[d];
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+    const uint32_t as = assoc[q];
     if (as == ASSOC_NONE) continue;
-    const int i = d / a.rows, j = d - i * a.rows;
+    const int i = 2 * (q / Q.nj) + Q.p, j = 2 * (q % Q.nj) + Q.p;
+    const uint32_t d = (uint32_t)i * a.rows + j;
     float4 mpos, mcol, mnr;
     if (as == ASSOC_NEW) {
       fuse_measurement(a, mp, weighting, i, j, mpos, mcol, mnr);
       mcol.w = -2.f;
-      const int k = new_off[d];
+      const int k = new_off[q];
       new_pos[k] = mpos;
       new_col[k] = mcol;
       new_nr[k] = mnr;
       continue;
     }
-    if ((int)as >= cnt || pending[as] != (uint32_t)d) continue;
+    if ((int)as >= cnt || pending[as] != d) continue;
     pending[as] = 0xffffffffu;  // re-arm the slot: exactly one pixel owns it
     fuse_measurement(a, mp, weighting, i, j, mpos, mcol, mnr);
     // update.vert:49-84
@@ -478,24 +530,29 @@ __device__ __forceinline__ bool clean_test(const CleanArgs& a, const MapPose* mp
   const float scale = 1.0f;
   const float indexXStep = (1.0f / (fcols * scale)) * 0.5f;
   const float indexYStep = (1.0f / (frows * scale)) * 0.5f;
-  const float windowMultiplier = 2;
   int count = 0, zCount = 0;
   if ((float)a.time - col.w < (float)a.time_delta && localPos.z > 0 && x > 0 && y > 0 && x < fcols && y < frows) {
     const f3 localNorm = normalized(rot(mp->t_inv, mk3(nr.x, nr.y, nr.z)));
-    for (float i = x / fcols - (scale * indexXStep * windowMultiplier); i < x / fcols + (scale * indexXStep * windowMultiplier); i += indexXStep)
-      for (float j = y / frows - (scale * indexYStep * windowMultiplier); j < y / frows + (scale * indexYStep * windowMultiplier); j += indexYStep) {
-        const int p = texel(j, a.rows) * a.cols + texel(i, a.cols);
+    // duplicate samples COUNT here (copy_unstable.vert:94,106): each distinct texel is read once and
+    // weighted by the number of float-loop samples that land on it
+    int tx[3], mx[3], ty[3], my[3];
+    const int nx = window_axis(x / fcols, indexXStep, a.cols, tx, mx);
+    const int ny = window_axis(y / frows, indexYStep, a.rows, ty, my);
+    for (int ia = 0; ia < nx; ++ia)
+      for (int jb = 0; jb < ny; ++jb) {
+        const int p = ty[jb] * a.cols + tx[ia];
         const uint32_t current = a.index[p];
         if (current > 0U) {
+          const int m = mx[ia] * my[jb];
           const float4 vc = a.vert_conf[p];
           const float4 ct = a.col_time[p];
           const float dx = vc.x - localPos.x, dy = vc.y - localPos.y;
           if (ct.z < col.z && vc.w > a.conf_threshold && vc.z > localPos.z && vc.z - localPos.z < 0.01f &&
               sqrtf(dx * dx + dy * dy) < nr.w * 1.4f)
-            count++;
+            count += m;
           if (ct.w == (float)a.time && vc.w > a.conf_threshold && vc.z > localPos.z && vc.z - localPos.z > 0.01f &&
               fabsf(localNorm.z) > 0.85f)
-            zCount++;
+            zCount += m;
         }
       }
   }
@@ -749,8 +806,8 @@ __global__ void k_unpack_aos(const float4* __restrict__ in, int n, float4* __res
   }
 }
 
-inline int sblocks(const EfContext* ctx, size_t n, int per_sm = 8) {
-  size_t b = (n + 255) / 256, cap = (size_t)ctx->num_sms * per_sm;
+inline int sblocks(const EfContext* ctx, size_t n, int per_sm = 8, int threads = 256) {
+  size_t b = (n + threads - 1) / threads, cap = (size_t)ctx->num_sms * per_sm;
   return (int)(b < cap ? (b ? b : 1) : cap);
 }
 inline Cam cam_of(const EfContext* ctx) { return Cam{ctx->cfg.cx, ctx->cfg.cy, ctx->cfg.fx, ctx->cfg.fy}; }
@@ -930,11 +987,14 @@ int map_fuse_async(EfContext* ctx, int time, float max_depth, float weighting) {
     CU(cudaMemcpyAsync((char*)ctx->odom[0].gn + offsetof(GNState, weighting), (char*)ctx->pin_small + 2048, 4, cudaMemcpyHostToDevice, ctx->stream));
   }
   FuseArgs a = fuse_args(ctx, time, max_depth);
-  EF_LAUNCH(ctx, k_fuse_associate, sblocks(ctx, n), 256, 0, a, m.count, m.assoc_id, m.pending, m.flags);
-  EF_LAUNCH(ctx, k_set_int, 1, 32, 0, m.new_count, n);
-  int rc = run_scan(ctx, m.flags, m.new_count, nullptr, n, B.offsets, B.totals + 2);
+  const Quarter Q = quarter_of(time, m.rows, m.cols);
+  const int nq = Q.ni * Q.nj;
+  (void)n;
+  EF_LAUNCH(ctx, k_fuse_associate, sblocks(ctx, nq, 16, 128), 128, 0, a, m.count, m.assoc_id, m.pending, m.flags);
+  EF_LAUNCH(ctx, k_set_int, 1, 32, 0, m.new_count, nq);
+  int rc = run_scan(ctx, m.flags, m.new_count, nullptr, nq, B.offsets, B.totals + 2);
   if (rc) return rc;
-  EF_LAUNCH(ctx, k_fuse_update, sblocks(ctx, n), 256, 0, a, m.pose, (const GNState*)ctx->odom[0].gn, m.count, m.assoc_id, m.pending, B.offsets,
+  EF_LAUNCH(ctx, k_fuse_update, sblocks(ctx, nq, 16, 128), 128, 0, a, m.pose, (const GNState*)ctx->odom[0].gn, m.count, m.assoc_id, m.pending, B.offsets,
             B.totals + 2, m.pos_conf, m.color_time, m.norm_rad, m.new_pos, m.new_col, m.new_nr, m.new_count);
   LAST();
   return 0;

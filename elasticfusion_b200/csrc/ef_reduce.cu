@@ -16,6 +16,12 @@
 
 using namespace ef;
 
+#ifdef EF_PROFILE_PHASES
+#define EF_STAMP(gn, slot, cond) do { if (cond) (gn)->dbg[slot] = clock64(); } while (0)
+#else
+#define EF_STAMP(gn, slot, cond) do { } while (0)
+#endif
+
 namespace ef {
 int launch_sobel(EfContext* ctx, int which);
 }
@@ -34,12 +40,12 @@ __device__ __forceinline__ void level_intr(const GNState* gn, int level, float& 
 
 // K and K^-1 of a pyramid level in double; the pinhole inverse is closed-form (no general 3x3 inverse on the device)
 __device__ __forceinline__ void level_K(const GNState* gn, int level, double* K, double* Kinv) {
-  float lfx, lfy, lcx, lcy;
-  level_intr(gn, level, lfx, lfy, lcx, lcy);
-  const double fx = lfx, fy = lfy, cx = lcx, cy = lcy;
-  K[0] = fx; K[1] = 0; K[2] = cx; K[3] = 0; K[4] = fy; K[5] = cy; K[6] = 0; K[7] = 0; K[8] = 1;
-  const double ifx = 1.0 / fx, ify = 1.0 / fy;
-  Kinv[0] = ifx; Kinv[1] = 0; Kinv[2] = -cx * ifx; Kinv[3] = 0; Kinv[4] = ify; Kinv[5] = -cy * ify; Kinv[6] = 0; Kinv[7] = 0; Kinv[8] = 1;
+  // filled once at context creation (ef_api.cu): K and its closed-form inverse for each pyramid level
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    K[k] = gn->Kd[level][k];
+    Kinv[k] = gn->Kinvd[level][k];
+  }
 }
 
 // warp matrices for the next photometric residual pass (RGBDOdometry.cpp:407-417). resultRt is a rigid transform
@@ -181,7 +187,7 @@ __device__ __forceinline__ void unpack_se3(const float* h, float* A, float* b) {
 
 // Shared-memory scratch of the update kernel
 struct GnScratch {
-  double dsm[32][64];  // per-slice partial sums (32 slices x 64 values)
+  double dsm[8][64];   // per-slice partial sums (IT2_THREADS/32 slices x 64 values)
   float sums[64];      // reduced systems: [0,29) geometric, [32,61) photometric
   float A_icp[36], b_icp[8], A_rgb[36], b_rgb[8];
   double lastA[36], lastb[8], result[8];
@@ -254,6 +260,7 @@ __device__ void gn_update_warp(const OdomDev& od, GnScratch& S, int level, int i
   }
   __syncwarp();
   const float res0 = S.sums[27], res1 = S.sums[28];
+  EF_STAMP(gn, 13, lane == 0 && level == 0);
   if (lane == 0) {
     gn->lastICPError = sqrtf(res0) / res1;
     gn->lastICPCount = res1;
@@ -265,12 +272,14 @@ __device__ void gn_update_warp(const OdomDev& od, GnScratch& S, int level, int i
     efm::ldlt_solve_unrolled<6>(A, b, x);
 #pragma unroll
     for (int k = 0; k < 6; ++k) S.result[k] = x[k];
+    EF_STAMP(gn, 14, level == 0);
     // OdometryProvider::computeUpdateSE3 (OdometryProvider.h:73-96)
     double rvec[3] = {x[3], x[4], x[5]}, Rd[9];
     efm::rodrigues(rvec, Rd);
     const double upd[16] = {Rd[0], Rd[1], Rd[2], x[0], Rd[3], Rd[4], Rd[5], x[1], Rd[6], Rd[7], Rd[8], x[2], 0, 0, 0, 1};
 #pragma unroll
     for (int k = 0; k < 16; ++k) S.upd[k] = upd[k];
+    EF_STAMP(gn, 15, level == 0);
   }
   __syncwarp();
   if (lane < 16) {
@@ -362,7 +371,7 @@ __device__ void gn_update_warp(const OdomDev& od, GnScratch& S, int level, int i
 
 constexpr int IT1_THREADS = 128;  // 640x480/4 pixel groups = 600 CTAs of 128: one resident wave at 5 CTAs/SM (<=102 registers)
 constexpr int IT1_CTAS_PER_SM = 5;
-constexpr int IT2_THREADS = 1024;
+constexpr int IT2_THREADS = 256;
 
 // ---- geometric row: ICPReduction::search/getProducts (reduce.cu:224-331) ------------------------------------
 struct IcpFrame {
@@ -413,14 +422,15 @@ __device__ __forceinline__ void icp_accumulate(const IcpFrame& F, const f3& vcur
 __global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev od, int level, int do_res, int do_icp, int solve) {
   GNState* gn = od.gn;
   if (solve && gn->break_level == level) return;  // rgbOnly `break`: rest of the level is skipped
-  __shared__ float sred[29 * (IT1_THREADS / 32)];
-  __shared__ int sred_i[2 * (IT1_THREADS / 32)];
+  __shared__ float sred[32 * (IT1_THREADS / 32)];
   const int rows = od.rows[level], cols = od.cols[level];
   const int N = rows * cols;
   const size_t plane = (size_t)N;
   const int gid = blockIdx.x * IT1_THREADS + threadIdx.x, gstride = gridDim.x * IT1_THREADS;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
+  const bool stamp = (blockIdx.x == 0 && threadIdx.x == 0 && level == 0);
+  EF_STAMP(gn, 0, stamp);
   unsigned int cnt = 0, sig = 0;
   if (do_res) {
     const int base = gn->cand_base[level], ncand = gn->cand_base[level + 1] - base;
@@ -455,6 +465,7 @@ __global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev 
     }
   }
 
+  EF_STAMP(gn, 1, stamp);
   if (do_icp) {
     IcpFrame F;
     F.Rcurr = load_m33(gn->Rcurr);
@@ -513,34 +524,22 @@ __global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev 
                          mk3(np_[q], np_[q + plane], np_[q + 2 * plane]), acc);
       }
     }
+    EF_STAMP(gn, 2, stamp);
     block_reduce_sum<29, IT1_THREADS>(acc, sred);
-    if (threadIdx.x == 0) {
-      float* my_partial = od.partials + (size_t)blockIdx.x * PARTIAL_STRIDE;
-#pragma unroll
-      for (int k = 0; k < 29; ++k) my_partial[k] = acc[k];
-    }
+    EF_STAMP(gn, 3, stamp);
+    if (threadIdx.x < 29) od.partials[(size_t)blockIdx.x * PARTIAL_STRIDE + threadIdx.x] = acc[0];
   }
   if (do_res) {
-    // CTA sum of the two ints (wrapping adds, like the reference's int2 sums)
+    // CTA sum of the two ints, then one integer atomic per CTA (wrapping adds like the reference's int2 sums; integer
+    // addition is order independent, so the totals stay deterministic)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       cnt += __shfl_down_sync(0xffffffffu, cnt, off);
       sig += __shfl_down_sync(0xffffffffu, sig, off);
     }
-    if (lane == 0) {
-      sred_i[wid * 2] = (int)cnt;
-      sred_i[wid * 2 + 1] = (int)sig;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned int c = 0, s = 0;
-#pragma unroll
-      for (int w = 0; w < IT1_THREADS / 32; ++w) {
-        c += (unsigned int)sred_i[w * 2];
-        s += (unsigned int)sred_i[w * 2 + 1];
-      }
-      od.partials_i[blockIdx.x * 2] = (int)c;
-      od.partials_i[blockIdx.x * 2 + 1] = (int)s;
+    if (lane == 0 && (cnt | sig)) {
+      atomicAdd(&gn->res_acc[0], cnt);
+      atomicAdd(&gn->res_acc[1], sig);
     }
   }
 }
@@ -582,8 +581,7 @@ __device__ __forceinline__ void rgb_accumulate(const int4& term, float sigma, fl
 // 8 = correspondence statistics present, 16 = use sigma_override.
 __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, int iter, int next_level, int nblocks1, int mode, float sigma_override) {
   __shared__ GnScratch S;
-  __shared__ float sred[29 * (IT2_THREADS / 32)];
-  __shared__ int s_ints[2];
+  __shared__ float sred[32 * (IT2_THREADS / 32)];
   __shared__ float s_sigma;
   __shared__ int s_break;
   GNState* gn = od.gn;
@@ -594,43 +592,40 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
     return;
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool stamp = (threadIdx.x == 0 && level == 0);
+  EF_STAMP(gn, 8, stamp && blockIdx.x == 0);
+
+  // issue the loads that do not depend on sigma first: this CTA's candidate terms and its share of the dense partials
+  const int base = gn->cand_base[level], ncand = do_rgb ? gn->cand_base[level + 1] - base : 0;
+  const int4* __restrict__ terms = od.terms + base;
+  const int c0 = blockIdx.x * IT2_THREADS + threadIdx.x, cstride = gridDim.x * IT2_THREADS;
+  int4 t0 = make_int4(-1, 0, 0, 0);
+  if (c0 < ncand) t0 = terms[c0];
+  double presum = 0;
+  if (do_icp && threadIdx.x < 32) {
+    const int per = (nblocks1 + gridDim.x - 1) / gridDim.x;
+    const int b0 = blockIdx.x * per, b1 = min(b0 + per, nblocks1);
+    for (int bb = b0; bb < b1; bb += 8) {  // 8 independent loads in flight
+      float x[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = (bb + k < b1) ? od.partials[(size_t)(bb + k) * PARTIAL_STRIDE + threadIdx.x] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) presum += (double)x[k];
+    }
+  }
+
   if (threadIdx.x == 0) {
     s_break = 0;
-    s_sigma = (mode & 16) ? sigma_override : gn->sigmaVal;
-  }
-  if (have_res) {
-    unsigned int c = 0, s = 0;
-    for (int b = threadIdx.x; b < nblocks1; b += IT2_THREADS) {
-      c += (unsigned int)od.partials_i[b * 2];
-      s += (unsigned int)od.partials_i[b * 2 + 1];
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      c += __shfl_down_sync(0xffffffffu, c, off);
-      s += __shfl_down_sync(0xffffffffu, s, off);
-    }
-    int* si = reinterpret_cast<int*>(sred);
-    if (lane == 0) {
-      si[wid * 2] = (int)c;
-      si[wid * 2 + 1] = (int)s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned int cc = 0, ss = 0;
-      for (int w = 0; w < IT2_THREADS / 32; ++w) {
-        cc += (unsigned int)si[w * 2];
-        ss += (unsigned int)si[w * 2 + 1];
-      }
-      const int rgbSize = (int)cc, sigma = (int)ss;
-      s_ints[0] = rgbSize;
-      s_ints[1] = sigma;
+    float sig_val = (mode & 16) ? sigma_override : gn->sigmaVal;
+    if (have_res) {
+      const int rgbSize = (int)gn->res_acc[0], sigma = (int)gn->res_acc[1];
       // reference: std::sqrt((float)sigma / rgbSize == 0 ? 1 : rgbSize)  (RGBDOdometry.cpp:442, App. A-1)
       float sigmaVal = (float)sqrt((double)(((float)sigma / rgbSize == 0) ? 1 : rgbSize));
       const float rgbError = (float)(sqrt((double)sigma) / (rgbSize == 0 ? 1 : rgbSize));
       const float prevError = (iter == 0) ? FLT_MAX : gn->rgbErrBuf[(iter + 1) & 1];  // RGBDOdometry.cpp:404
       const bool brk = solve && gn->rgbOnly && rgbError > prevError;
       if (gn->rgbOnly) sigmaVal = -1;
-      if (!(mode & 16)) s_sigma = sigmaVal;
+      if (!(mode & 16)) sig_val = sigmaVal;
       s_break = brk ? 1 : 0;
       if (blockIdx.x == 0) {
         gn->sum_res[0] = rgbSize;
@@ -650,51 +645,62 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
         }
       }
     }
-    __syncthreads();
-    if (s_break) return;
-  } else {
-    __syncthreads();
+    s_sigma = sig_val;
   }
+  __syncthreads();
+  EF_STAMP(gn, 9, stamp && blockIdx.x == 0);
+  const bool brk = s_break != 0;
 
-  // every CTA pre-sums its share of the dense pass's per-CTA partials (double, fixed order) so the last CTA only has
-  // gridDim.x values per term left
-  if (do_icp && threadIdx.x < 32) {
-    const int per = (nblocks1 + gridDim.x - 1) / gridDim.x;
-    const int b0 = blockIdx.x * per, b1 = min(b0 + per, nblocks1);
-    double a = 0;
-    for (int b = b0; b < b1; ++b) a += (double)od.partials[(size_t)b * PARTIAL_STRIDE + threadIdx.x];
-    od.partials2[blockIdx.x * 32 + threadIdx.x] = a;
-  }
-  if (do_rgb) {
-    const float sigma = s_sigma;
-    float lfx, lfy, lcx, lcy;
-    level_intr(gn, level, lfx, lfy, lcx, lcy);
-    const int base = gn->cand_base[level], ncand = gn->cand_base[level + 1] - base;
-    const int4* __restrict__ terms = od.terms + base;
-    float acc[29];
+  if (!brk) {
+    if (do_icp && threadIdx.x < 32) od.partials2[blockIdx.x * 32 + threadIdx.x] = presum;
+    if (do_rgb) {
+      const float sigma = s_sigma;
+      float lfx, lfy, lcx, lcy;
+      level_intr(gn, level, lfx, lfy, lcx, lcy);
+      float acc[29];
 #pragma unroll
-    for (int k = 0; k < 29; ++k) acc[k] = 0.f;
-    for (int c = blockIdx.x * IT2_THREADS + threadIdx.x; c < ncand; c += gridDim.x * IT2_THREADS) {
-      const int4 t = terms[c];
-      if (t.x != -1) rgb_accumulate(t, sigma, lfx, lfy, lcx, lcy, od.sobelScale, acc);
-    }
-    __syncthreads();
-    block_reduce_sum<29, IT2_THREADS>(acc, sred);
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int k = 0; k < 29; ++k) od.partials_rgb[blockIdx.x * 32 + k] = acc[k];
+      for (int k = 0; k < 29; ++k) acc[k] = 0.f;
+      if (t0.x != -1) rgb_accumulate(t0, sigma, lfx, lfy, lcx, lcy, od.sobelScale, acc);
+      for (int c = c0 + cstride; c < ncand; c += cstride) {
+        const int4 t = terms[c];
+        if (t.x != -1) rgb_accumulate(t, sigma, lfx, lfy, lcx, lcy, od.sobelScale, acc);
+      }
+      block_reduce_sum<29, IT2_THREADS>(acc, sred);
+      if (threadIdx.x < 29) od.partials_rgb[blockIdx.x * 32 + threadIdx.x] = acc[0];
     }
   }
+  EF_STAMP(gn, 10, stamp && blockIdx.x == 0);
+  // every CTA takes a ticket (also on `break`, so the accumulators of k_iter1 get re-armed exactly once)
   if (!last_block_done(od.counter)) return;
+  EF_STAMP(gn, 11, stamp);
+  if (threadIdx.x == 0) {
+    *od.counter = 0;
+    gn->res_acc[0] = 0u;
+    gn->res_acc[1] = 0u;
+  }
+  if (brk) return;
 
-  // final sums in double, fixed order: 32 warps x 32 values
+  // final sums in double, fixed order: IT2_THREADS/32 warps x 32 values
   {
     const int v = lane, sl = wid;
     double a0 = 0, a1 = 0;
-    if (do_icp)
-      for (int b = sl; b < (int)gridDim.x; b += 32) a0 += od.partials2[b * 32 + v];
-    if (do_rgb)
-      for (int b = sl; b < (int)gridDim.x; b += 32) a1 += (double)od.partials_rgb[b * 32 + v];
+    constexpr int SL = IT2_THREADS / 32;
+    for (int bb = sl; bb < (int)gridDim.x; bb += 8 * SL) {  // 16 independent loads in flight per thread
+      double x[8];
+      float y[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int b = bb + k * SL;
+        const bool in = b < (int)gridDim.x;
+        x[k] = (in && do_icp) ? od.partials2[b * 32 + v] : 0.0;
+        y[k] = (in && do_rgb) ? od.partials_rgb[b * 32 + v] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a0 += x[k];
+        a1 += (double)y[k];
+      }
+    }
     S.dsm[sl][v] = a0;
     S.dsm[sl][32 + v] = a1;
   }
@@ -702,7 +708,7 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
   if (threadIdx.x < 64) {
     double t = 0;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) t += S.dsm[k][threadIdx.x];
+    for (int k = 0; k < IT2_THREADS / 32; ++k) t += S.dsm[k][threadIdx.x];
     const float f = (float)t;
     S.sums[threadIdx.x] = f;
     if (threadIdx.x < 32)
@@ -711,9 +717,10 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
       gn->sum_rgb[threadIdx.x - 32] = f;
   }
   __syncthreads();
-  if (threadIdx.x == 0) *od.counter = 0;
+  EF_STAMP(gn, 12, stamp);
   if (!solve || threadIdx.x >= 32) return;
   gn_update_warp(od, S, level, iter, next_level);
+  EF_STAMP(gn, 16, stamp);
 }
 
 // expands the compact per-candidate terms into the reference's dense DataTerm image (inspection / stage API only)
@@ -766,7 +773,7 @@ __device__ __forceinline__ void so3_gradient(const uint8_t* img, int cols, int x
 __global__ void __launch_bounds__(RED_THREADS) k_so3_step(OdomDev od, int iter, int solve) {
   GNState* gn = od.gn;
   if (solve && gn->so3_done) return;
-  __shared__ float sred[11 * (RED_THREADS / 32)];
+  __shared__ float sred[32 * (RED_THREADS / 32)];
   __shared__ double dsm[(RED_THREADS / 32) * 32];
   const int level = 2;
   const int rows = od.rows[level], cols = od.cols[level];
@@ -813,11 +820,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_so3_step(OdomDev od, int iter, 
     }
   }
   block_reduce_sum<11, RED_THREADS>(acc, sred);
-  if (threadIdx.x == 0) {
-    float* my_partial = od.partials + (size_t)blockIdx.x * PARTIAL_STRIDE;
-#pragma unroll
-    for (int k = 0; k < 11; ++k) my_partial[k] = acc[k];
-  }
+  if (threadIdx.x < 11) od.partials[(size_t)blockIdx.x * PARTIAL_STRIDE + threadIdx.x] = acc[0];
   if (!last_block_done(od.counter)) return;
   so3_final_sum(od.partials, gridDim.x, gn->sum_so3, dsm);
   if (threadIdx.x != 0) return;
@@ -891,7 +894,7 @@ inline int red_blocks(const EfContext* ctx, int n_items, int per_thread, int thr
 
 inline int iter2_blocks(int npx, bool rgb, int nb1) {
   int b = rgb ? (npx / 8 + IT2_THREADS - 1) / IT2_THREADS : 1;  // candidates are typically <= 1/8 of the pixels; the loop strides anyway
-  const int b_icp = (nb1 + 15) / 16;                            // <= 16 dense-pass partials pre-summed per CTA
+  const int b_icp = (nb1 + 7) / 8;                              // <= 8 dense-pass partials pre-summed per CTA
   if (b_icp > b) b = b_icp;
   return b < 1 ? 1 : (b > MAX_RGB_BLOCKS ? MAX_RGB_BLOCKS : b);
 }
