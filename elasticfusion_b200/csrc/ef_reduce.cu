@@ -194,6 +194,8 @@ struct GnScratch {
   double rRt[16], nrt[16], upd[16];
   double K[9], Kinv[9], Rt[16], tmp[9];
   float Rprev[9], tprev[3], iR[9], it[3];
+  int flags[2];
+  double w;
 };
 
 // packed index k (reference JtJJtrSE3 order, types.cuh:98-104) -> (i, j) with j == 6 meaning the b column
@@ -217,12 +219,9 @@ __device__ __forceinline__ void se3_unpack_index(int k, int& i, int& j) {
 __device__ void gn_update_warp(const OdomDev& od, GnScratch& S, int level, int iter, int next_level) {
   GNState* gn = od.gn;
   const int lane = threadIdx.x;
-  // stage state
-  if (lane < 16) S.rRt[lane] = gn->resultRt[lane];
-  if (lane < 9) S.Rprev[lane] = gn->Rprev[lane];
-  if (lane < 3) S.tprev[lane] = gn->tprev[lane];
-  const int icp = gn->icp, rgb = gn->rgb;
-  const double w = gn->icpWeight;
+  // (resultRt, Rprev, tprev were staged into S at the top of k_iter2, long before this CTA took the last ticket)
+  const int icp = S.flags[0], rgb = S.flags[1];
+  const double w = S.w;
   if (lane < 27) {
     int i, j;
     se3_unpack_index(lane, i, j);
@@ -432,6 +431,7 @@ __global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev 
   const bool stamp = (blockIdx.x == 0 && threadIdx.x == 0 && level == 0);
   EF_STAMP(gn, 0, stamp);
   unsigned int cnt = 0, sig = 0;
+  const bool vec = (cols & 3) == 0;
   if (do_res) {
     const int base = gn->cand_base[level], ncand = gn->cand_base[level + 1] - base;
     const m33 krkinv = load_m33(gn->krkinv);
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev 
     const float* __restrict__ nc = od.nmap_curr[level];
     const float* __restrict__ vp = od.vmap_g_prev[level];
     const float* __restrict__ np_ = od.nmap_g_prev[level];
-    if ((cols & 3) == 0) {
+    if (vec) {
       // 4 consecutive pixels per thread: six 128-bit coalesced loads for the live maps, the model maps gathered in pairs
       const int ngroups = N >> 2;
       for (int g = gid; g < ngroups; g += gstride) {
@@ -601,6 +601,16 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
   const int c0 = blockIdx.x * IT2_THREADS + threadIdx.x, cstride = gridDim.x * IT2_THREADS;
   int4 t0 = make_int4(-1, 0, 0, 0);
   if (c0 < ncand) t0 = terms[c0];
+  if (solve && wid == 1) {  // state of the solve: not written by anything in this launch before the last CTA's update
+    if (lane < 16) S.rRt[lane] = gn->resultRt[lane];
+    if (lane < 9) S.Rprev[lane] = gn->Rprev[lane];
+    if (lane < 3) S.tprev[lane] = gn->tprev[lane];
+    if (lane == 0) {
+      S.flags[0] = gn->icp;
+      S.flags[1] = gn->rgb;
+      S.w = gn->icpWeight;
+    }
+  }
   double presum = 0;
   if (do_icp && threadIdx.x < 32) {
     const int per = (nblocks1 + gridDim.x - 1) / gridDim.x;

@@ -25,30 +25,42 @@ using namespace ef;
 // pyramid / image kernels
 // =============================================================================================
 
-// reference pyrDownGaussKernel, cudafuncs.cu:75-121 (sigma_color 30, centre-relative gate, truncating store)
-__global__ void k_pyr_down_u16(const uint16_t* __restrict__ src, int srows, int scols, uint16_t* __restrict__ dst) {
-  const int drows = srows / 2, dcols = scols / 2;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= dcols || y >= drows) return;
+// reference pyrDownGaussKernel, cudafuncs.cu:75-121 (sigma_color 30, centre-relative gate, truncating store).
+// `fetch(y, x)` abstracts the source so that level 2 can be produced in the same launch as level 1 by recomputing the
+// level-1 values it needs from level 0 (identical arithmetic -> identical values, one launch instead of two).
+template <typename Fetch>
+__device__ __forceinline__ uint16_t pyr_down_u16_at(Fetch fetch, int srows, int scols, int x, int y) {
   const int D = 5;
   const float sigma_color = 30.f;
   const float weights[3] = {0.375f, 0.25f, 0.0625f};
-  const int center = src[(2 * y) * scols + 2 * x];
+  const int center = fetch(2 * y, 2 * x);
   const int x_mi = max(0, 2 * x - D / 2) - 2 * x;
   const int y_mi = max(0, 2 * y - D / 2) - 2 * y;
   const int x_ma = min(scols, 2 * x - D / 2 + D) - 2 * x;
   const int y_ma = min(srows, 2 * y - D / 2 + D) - 2 * y;
   float sum = 0, wall = 0;
-  for (int yi = y_mi; yi < y_ma; ++yi)
-    for (int xi = x_mi; xi < x_ma; ++xi) {
-      const int val = src[(2 * y + yi) * scols + 2 * x + xi];
-      if ((float)abs(val - center) < 3 * sigma_color) {
+  // fixed 5x5 trip count with predication (same accumulation order): all taps are requested at once
+#pragma unroll
+  for (int yi = -2; yi <= 2; ++yi)
+#pragma unroll
+    for (int xi = -2; xi <= 2; ++xi) {
+      const bool in = (yi >= y_mi) && (yi < y_ma) && (xi >= x_mi) && (xi < x_ma);
+      const int val = in ? fetch(2 * y + yi, 2 * x + xi) : 0;
+      if (in && (float)abs(val - center) < 3 * sigma_color) {
         sum += val * weights[abs(xi)] * weights[abs(yi)];
         wall += weights[abs(xi)] * weights[abs(yi)];
       }
     }
-  dst[y * dcols + x] = (uint16_t)__float2int_rz(sum / wall);
+  return (uint16_t)__float2int_rz(sum / wall);
+}
+
+__global__ void k_pyr_down_u16(const uint16_t* __restrict__ src, int srows, int scols, uint16_t* __restrict__ dst) {
+  const int r1 = srows / 2, c1 = scols / 2;
+  auto f0 = [&](int yy, int xx) { return (int)src[(size_t)yy * scols + xx]; };
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < r1 * c1; t += gridDim.x * blockDim.x) {
+    const int y = t / c1, x = t - y * c1;
+    dst[t] = pyr_down_u16_at(f0, srows, scols, x, y);
+  }
 }
 
 // createVMap + createNMap fused (cudafuncs.cu:123-219): the normal is built from the three depths it needs with the
@@ -63,11 +75,15 @@ __device__ __forceinline__ bool vertex_from_depth(const uint16_t* depth, int col
   return false;
 }
 
-__global__ void k_vmap_nmap(const uint16_t* __restrict__ depth, int rows, int cols, float fx_inv, float fy_inv, float cx,
-                            float cy, float cutoff, float* __restrict__ vmap, float* __restrict__ nmap) {
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
-  const int v = blockIdx.y * blockDim.y + threadIdx.y;
-  if (u >= cols || v >= rows) return;
+struct VmapArgs {
+  const uint16_t* depth[NUM_PYRS];
+  float* vmap[NUM_PYRS];
+  float* nmap[NUM_PYRS];
+  int rows[NUM_PYRS], cols[NUM_PYRS], start[NUM_PYRS + 1];
+  float fx_inv[NUM_PYRS], fy_inv[NUM_PYRS], cx[NUM_PYRS], cy[NUM_PYRS];
+};
+__device__ __forceinline__ void vmap_nmap_at(const uint16_t* __restrict__ depth, int rows, int cols, float fx_inv, float fy_inv, float cx,
+                                             float cy, float cutoff, float* __restrict__ vmap, float* __restrict__ nmap, int u, int v) {
   const size_t plane = (size_t)rows * cols;
   const size_t p = (size_t)v * cols + u;
   f3 v00;
@@ -91,6 +107,15 @@ __global__ void k_vmap_nmap(const uint16_t* __restrict__ depth, int rows, int co
   nmap[p] = n.x;
   nmap[p + plane] = n.y;
   nmap[p + 2 * plane] = n.z;
+}
+__global__ void k_vmap_nmap(VmapArgs a, float cutoff) {
+  const int total = a.start[NUM_PYRS];
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+    const int lv = (f >= a.start[2]) ? 2 : (f >= a.start[1] ? 1 : 0);
+    const int p = f - a.start[lv];
+    const int v = p / a.cols[lv], u = p - v * a.cols[lv];
+    vmap_nmap_at(a.depth[lv], a.rows[lv], a.cols[lv], a.fx_inv[lv], a.fy_inv[lv], a.cx[lv], a.cy[lv], cutoff, a.vmap[lv], a.nmap[lv], u, v);
+  }
 }
 
 // copyMaps (cudafuncs.cu:295-381): predicted float4 vertex/normal maps -> vmaps_tmp (AoS copy) + SoA planes; z==0 -> NaN
@@ -217,46 +242,71 @@ __global__ void k_depth_intensity_l0(const float4* __restrict__ vmaps_tmp, const
 
 __device__ __constant__ float c_gauss25[25] = {1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 24, 6, 4, 16, 24, 16, 4, 1, 4, 6, 4, 1};
 
-// pyrDownKernelGaussF + pyrDownKernelIntensityGauss fused (cudafuncs.cu:383-411,512-562): window [2x-2, min(2x+3, n-1)),
-// flipped/shifted tap index, int normaliser, NaN / zero skipping, truncating u8 store. Either pair may be NULL.
-__global__ void k_pyr_down_depth_image(const float* __restrict__ dsrc, float* __restrict__ ddst, const uint8_t* __restrict__ isrc,
-                                       uint8_t* __restrict__ idst, int srows, int scols) {
-  const int drows = srows / 2, dcols = scols / 2;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= dcols || y >= drows) return;
+// pyrDownKernelGaussF + pyrDownKernelIntensityGauss (cudafuncs.cu:383-411,512-562): window [2x-2, min(2x+3, n-1)),
+// flipped/shifted tap index, int normaliser, NaN / zero skipping, truncating u8 store. As above, level 2 is produced in the
+// same launch by recomputing the level-1 taps it needs.
+template <typename Fetch>
+__device__ __forceinline__ float pyr_down_f_at(Fetch fetch, int srows, int scols, int x, int y) {
   const int D = 5;
   const int tx = min(2 * x - D / 2 + D, scols - 1);
   const int ty = min(2 * y - D / 2 + D, srows - 1);
+  float sum = 0;
+  int count = 0;
   const int cy0 = max(0, 2 * y - D / 2), cx0 = max(0, 2 * x - D / 2);
-  if (dsrc) {
-    float sum = 0;
-    int count = 0;
-    for (int cy = cy0; cy < ty; ++cy)
-      for (int cx = cx0; cx < tx; ++cx) {
-        const float s = dsrc[(size_t)cy * scols + cx];
-        if (!isnan(s)) {
-          const float w = c_gauss25[(ty - cy - 1) * 5 + (tx - cx - 1)];
-          sum += s * w;
-          count = __float2int_rz((float)count + w);
-        }
+#pragma unroll
+  for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 5; ++dx) {
+      const int cy = cy0 + dy, cx = cx0 + dx;
+      const bool in = (cy < ty) && (cx < tx);
+      const float s = in ? fetch(cy, cx) : 0.f;
+      if (in && !isnan(s)) {
+        const float w = c_gauss25[(ty - cy - 1) * 5 + (tx - cx - 1)];
+        sum += s * w;
+        count = __float2int_rz((float)count + w);
       }
-    ddst[(size_t)y * dcols + x] = (float)(sum / (float)count);
-  }
-  if (isrc) {
-    float sum = 0;
-    int count = 0;
-    for (int cy = cy0; cy < ty; ++cy)
-      for (int cx = cx0; cx < tx; ++cx) {
-        const uint8_t s = isrc[(size_t)cy * scols + cx];
-        if (s > 0) {
-          const float w = c_gauss25[(ty - cy - 1) * 5 + (tx - cx - 1)];
-          sum += s * w;
-          count = __float2int_rz((float)count + w);
-        }
+    }
+  return (float)(sum / (float)count);
+}
+template <typename Fetch>
+__device__ __forceinline__ uint8_t pyr_down_u8_at(Fetch fetch, int srows, int scols, int x, int y) {
+  const int D = 5;
+  const int tx = min(2 * x - D / 2 + D, scols - 1);
+  const int ty = min(2 * y - D / 2 + D, srows - 1);
+  float sum = 0;
+  int count = 0;
+  const int cy0 = max(0, 2 * y - D / 2), cx0 = max(0, 2 * x - D / 2);
+#pragma unroll
+  for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 5; ++dx) {
+      const int cy = cy0 + dy, cx = cx0 + dx;
+      const bool in = (cy < ty) && (cx < tx);
+      const int s = in ? fetch(cy, cx) : 0;
+      if (in && s > 0) {
+        const float w = c_gauss25[(ty - cy - 1) * 5 + (tx - cx - 1)];
+        sum += s * w;
+        count = __float2int_rz((float)count + w);
       }
-    int v = __float2int_rz(sum / (float)count);  // NaN -> 0
-    idst[(size_t)y * dcols + x] = (uint8_t)min(max(v, 0), 255);
+    }
+  const int v = __float2int_rz(sum / (float)count);  // NaN -> 0
+  return (uint8_t)min(max(v, 0), 255);
+}
+
+// depth (fp32) and intensity (u8) pyramid level in one launch. Either pair may be NULL.
+__global__ void k_pyr_down_depth_image(const float* __restrict__ d0, float* __restrict__ d1, const uint8_t* __restrict__ i0,
+                                       uint8_t* __restrict__ i1, int srows, int scols) {
+  const int r1 = srows / 2, c1 = scols / 2;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < r1 * c1; t += gridDim.x * blockDim.x) {
+    const int y = t / c1, x = t - y * c1;
+    if (d0) {
+      auto f0 = [&](int yy, int xx) { return d0[(size_t)yy * scols + xx]; };
+      d1[t] = pyr_down_f_at(f0, srows, scols, x, y);
+    }
+    if (i0) {
+      auto g0 = [&](int yy, int xx) { return (int)i0[(size_t)yy * scols + xx]; };
+      i1[t] = pyr_down_u8_at(g0, srows, scols, x, y);
+    }
   }
 }
 
@@ -354,15 +404,26 @@ int odom_init_icp_depth(EfContext* ctx, int which, const uint16_t* depth_dev, fl
   OdomDev& od = ctx->odom[which];
   cudaError_t e = cudaMemcpyAsync(od.depth_tmp[0], depth_dev, sizeof(uint16_t) * od.width * od.height, cudaMemcpyDeviceToDevice, ctx->stream);
   if (e != cudaSuccess) return (int)e;
-  const dim3 block(32, 8);
   for (int i = 1; i < NUM_PYRS; ++i)
-    EF_LAUNCH(ctx, k_pyr_down_u16, grid2d(od.cols[i], od.rows[i]), block, 0, od.depth_tmp[i - 1], od.rows[i - 1], od.cols[i - 1], od.depth_tmp[i]);
+    EF_LAUNCH(ctx, k_pyr_down_u16, flat_blocks(ctx, (size_t)od.rows[i] * od.cols[i] * 2), 128, 0, od.depth_tmp[i - 1], od.rows[i - 1], od.cols[i - 1],
+              od.depth_tmp[i]);
+  VmapArgs va;
   for (int i = 0; i < NUM_PYRS; ++i) {
     const int div = 1 << i;
     const float fx = ctx->cfg.fx / div, fy = ctx->cfg.fy / div, cx = ctx->cfg.cx / div, cy = ctx->cfg.cy / div;
-    EF_LAUNCH(ctx, k_vmap_nmap, grid2d(od.cols[i], od.rows[i]), block, 0, od.depth_tmp[i], od.rows[i], od.cols[i], 1.f / fx, 1.f / fy, cx, cy,
-              cutoff, od.vmap_curr[i], od.nmap_curr[i]);
+    va.depth[i] = od.depth_tmp[i];
+    va.vmap[i] = od.vmap_curr[i];
+    va.nmap[i] = od.nmap_curr[i];
+    va.rows[i] = od.rows[i];
+    va.cols[i] = od.cols[i];
+    va.start[i] = od.level_start[i];
+    va.fx_inv[i] = 1.f / fx;
+    va.fy_inv[i] = 1.f / fy;
+    va.cx[i] = cx;
+    va.cy[i] = cy;
   }
+  va.start[NUM_PYRS] = od.level_start[NUM_PYRS];
+  EF_LAUNCH(ctx, k_vmap_nmap, flat_blocks(ctx, (size_t)od.level_start[NUM_PYRS]), 256, 0, va, cutoff);
   EF_CHECK_LAST();
   return 0;
 }
@@ -409,10 +470,10 @@ int odom_populate(EfContext* ctx, int which, const uint8_t* rgba, float** destDe
   const size_t n = (size_t)od.width * od.height;
   EF_LAUNCH(ctx, k_depth_intensity_l0, flat_blocks(ctx, n), 256, 0, (const float4*)od.vmaps_tmp, (const uchar4*)rgba, (const uchar4*)rgbaB, flag,
             forceB ? 1 : 0, n, od.maxDepthRGB, with_depth ? destDepths[0] : (float*)nullptr, destImages[0]);
-  const dim3 block(32, 8);
   for (int i = 0; i + 1 < NUM_PYRS; ++i)
-    EF_LAUNCH(ctx, k_pyr_down_depth_image, grid2d(od.cols[i + 1], od.rows[i + 1]), block, 0, with_depth ? destDepths[i] : (const float*)nullptr,
-              with_depth ? destDepths[i + 1] : (float*)nullptr, destImages[i], destImages[i + 1], od.rows[i], od.cols[i]);
+    EF_LAUNCH(ctx, k_pyr_down_depth_image, flat_blocks(ctx, (size_t)od.rows[i + 1] * od.cols[i + 1] * 2), 128, 0,
+              with_depth ? destDepths[i] : (const float*)nullptr, with_depth ? destDepths[i + 1] : (float*)nullptr, (const uint8_t*)destImages[i],
+              destImages[i + 1], od.rows[i], od.cols[i]);
   EF_CHECK_LAST();
   return 0;
 }
