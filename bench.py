@@ -173,7 +173,6 @@ def run_ours(args, rank, world, dist):
     ctx.sync()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
     launches = ctx.launch_count() - l0
     frame_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
     dev_ms = float(sum(frame_ms))
@@ -201,6 +200,7 @@ def run_ours(args, rank, world, dist):
         _ = ctx2.T_host if hasattr(ctx2, "T_host") else None
         e2e_s += time.perf_counter() - t0
     barrier()
+    clocks = sampler.stop()  # sampled across the value, roofline and e2e loops
     pose2 = ctx2.get_pose()
     ctx2.close()
 
@@ -233,8 +233,9 @@ def run_ours(args, rank, world, dist):
 
 
 def icp_roofline(ctx, stream, flush, K):
-    """CUDA-event time of the ICP reduce launch on the pyramids left by the last tracked frame: cold (L2 flushed before
-    every launch) and warm (back to back)."""
+    """CUDA-event time of the dominant kernel (k_iter1: ICP residual + Jacobian + per-CTA 29-term reduction, level 0) on the
+    pyramids left by the last tracked frame. cold = L2 flushed before every launch (the HBM-roofline number); warm = back to
+    back (L2 resident). The complete reduction (dense pass + 1-CTA final sum) is reported beside it."""
     import torch
 
     T = ctx.get_pose()
@@ -243,27 +244,38 @@ def icp_roofline(ctx, stream, flush, K):
     ctx.icp_step_async(0, R, t, np.linalg.inv(R).astype(np.float32), t)
     ctx.sync()
     reps = 30
-    cold = []
-    with torch.cuda.stream(stream):
-        for k in range(reps):
-            flush.fill_(k)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record(stream)
-            ctx.icp_step_async(0)
-            e.record(stream)
-            cold.append((s, e))
-        ws, we = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ws.record(stream)
-        for k in range(reps):
-            ctx.icp_step_async(0)
-        we.record(stream)
-    ctx.sync()
-    cold_us = statistics.median([s.elapsed_time(e) * 1000.0 for s, e in cold])
-    warm_us = ws.elapsed_time(we) * 1000.0 / reps
+
+    def timed(fn, cold):
+        ev = []
+        with torch.cuda.stream(stream):
+            for k in range(reps):
+                if cold:
+                    flush.fill_(k)
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(stream)
+                fn()
+                e.record(stream)
+                ev.append((s, e))
+        ctx.sync()
+        return statistics.median([s.elapsed_time(e) * 1000.0 for s, e in ev])
+
+    dense_cold = timed(lambda: ctx.icp_dense_pass_async(0), True)
+    dense_warm = timed(lambda: ctx.icp_dense_pass_async(0), False)
+    full_cold = timed(lambda: ctx.icp_step_async(0), True)
+    full_warm = timed(lambda: ctx.icp_step_async(0), False)
     nbytes = 48 * K.width * K.height + 116
-    return {"kernel": "k_se3_step (ICP residual+Jacobian+29-term reduction, level 0)", "bound": "hbm", "unit": "GB/s",
-            "achieved": nbytes / (cold_us * 1e-6) / 1e9, "algorithmic_bytes": nbytes, "duration_us": cold_us,
-            "achieved_warm_l2": nbytes / (warm_us * 1e-6) / 1e9, "duration_warm_us": warm_us, "traffic": None}
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(f"k_iter1_{K.width}x{K.height}")
+        except Exception:
+            traffic = None
+    return {"kernel": "k_iter1 (ICP residual + Jacobian + per-CTA 29-term reduction, level 0; ef_reduce.cu)", "bound": "hbm", "unit": "GB/s",
+            "achieved": nbytes / (dense_cold * 1e-6) / 1e9, "algorithmic_bytes": nbytes, "duration_us": dense_cold,
+            "achieved_warm_l2": nbytes / (dense_warm * 1e-6) / 1e9, "duration_warm_us": dense_warm,
+            "complete_reduction_us": {"cold": full_cold, "warm": full_warm}, "traffic": traffic,
+            "timing": "CUDA events on the launching stream around one launch, median of 30, L2 flushed (256 MiB write) before each cold launch"}
 
 
 def cpu_baseline(K, rgb, depth, cap, seconds=20.0):
@@ -286,6 +298,8 @@ def run_reference(args, rank, world):
     for the GLSL mapping half. Falls back to the pure CPU oracle when oracle/_ref is absent."""
     if rank != 0:
         return
+    ncores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(ncores)  # torchrun pins it to 1; the reference arm may use every host core
     K, cap, wl_name = workload(args)
     n_total = args.warmup + args.steps
     budget_frames = min(n_total, 150)
@@ -298,6 +312,7 @@ def run_reference(args, rank, world):
         have_ref = False
     from oracle import ef_oracle as eo
 
+    eo.set_threads(ncores)
     if have_ref:
         from oracle import ef_ref
 
@@ -314,7 +329,7 @@ def run_reference(args, rank, world):
     for i in range(w, w + k):
         runner.process_frame(rgb[i], depth[i], i)
     dt = time.perf_counter() - t0
-    v = k * world / dt
+    v = k / dt  # one host, one set of cores: the CPU arm's throughput does not grow with the number of GPUs
     out = {"impl": "reference", "metric": "frames/sec, full track+fuse+predict (processFrame)", "value": v, "unit": "frames/s", "n_gpus": world,
            "steps": k, "warmup": w, "ms_per_step": dt / k * 1000.0, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic", "config": {"workload": wl_name, "frames_per_gpu": k, "open_loop": True},

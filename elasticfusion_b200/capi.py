@@ -260,6 +260,9 @@ class Context:
         Rc, tc, Rp, tp = f32(Rcurr), f32(tcurr), f32(Rprev_inv), f32(tprev)
         _chk(lib().ef_icp_step_async(self.h_ctx, which, level, _p(Rc), _p(tc), _p(Rp), _p(tp)))
 
+    def icp_dense_pass_async(self, level, which=0):
+        _chk(lib().ef_icp_dense_pass_async(self.h_ctx, which, level))
+
     def rgb_residual(self, level, krkinv, kt, which=0):
         kk = np.ascontiguousarray(krkinv, np.float32)
         k3 = np.ascontiguousarray(kt, np.float32)

@@ -26,6 +26,7 @@ int odom_finish_async(EfContext* ctx, int which, float weightMultiplier, bool ha
 int odom_set_pose_async(EfContext* ctx, int which, const double* T_dev);
 int launch_se3_step_raw(EfContext* ctx, int which, int level, bool do_icp, bool do_rgb, float sigma);
 int launch_rgb_residual_raw(EfContext* ctx, int which, int level);
+int launch_icp_dense_only(EfContext* ctx, int which, int level);
 int launch_so3_raw(EfContext* ctx, int which);
 int launch_sobel(EfContext* ctx, int which);
 int preprocess_depth(EfContext* ctx, const uint16_t* raw, float cutoff, uint16_t* filtered, float* metric, float* metric_filtered);
@@ -587,6 +588,11 @@ extern "C" int ef_icp_step_async(EfContext* ctx, int which, int level, const flo
     RC(upload_gn(ctx, which, offsetof(GNState, tprev), s + 21, 12));
   }
   return launch_se3_step_raw(ctx, which, level, true, false, 0.f);
+}
+
+extern "C" int ef_icp_dense_pass_async(EfContext* ctx, int which, int level) {
+  if (!ctx || !WHICH_OK(which) || level < 0 || level >= NUM_PYRS) return EF_EINVAL;
+  return launch_icp_dense_only(ctx, which, level);
 }
 
 extern "C" int ef_icp_step(EfContext* ctx, int which, int level, const float* Rcurr, const float* tcurr, const float* Rprev_inv,

@@ -986,6 +986,13 @@ int launch_se3_step_raw(EfContext* ctx, int which, int level, bool do_icp, bool 
   EF_CHECK_LAST();
   return 0;
 }
+int launch_icp_dense_only(EfContext* ctx, int which, int level) {
+  OdomDev& od = ctx->odom[which];
+  const int nb1 = red_blocks(ctx, od.rows[level] * od.cols[level], 4, IT1_THREADS, IT1_CTAS_PER_SM);
+  EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, level, 0, 1, 0);
+  EF_CHECK_LAST();
+  return 0;
+}
 int launch_rgb_residual_raw(EfContext* ctx, int which, int level) {
   OdomDev& od = ctx->odom[which];
   const int npx = od.rows[level] * od.cols[level];

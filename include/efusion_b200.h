@@ -141,9 +141,12 @@ int ef_rgb_residual(EfContext* ctx, int which, int level, const float* krkinv9, 
 int ef_rgb_step(EfContext* ctx, int which, int level, float sigma, float* A36, float* b6);
 int ef_so3_step(EfContext* ctx, int which, const float* image_basis9, const float* kinv9, const float* krlr9,
                 float* A9, float* b3, float* residual2);
-/* asynchronous variant for benchmarking the ICP reduction: result stays on the device */
+/* asynchronous variant for benchmarking the ICP reduction: result stays on the device. Poses may be NULL (reuse the last ones).
+ * ef_icp_dense_pass_async launches only the dense residual+Jacobian+per-CTA reduction kernel (k_iter1), without the 1-CTA
+ * final sum — the launch bench.py's roofline object times. */
 int ef_icp_step_async(EfContext* ctx, int which, int level, const float* Rcurr9, const float* tcurr3,
                       const float* Rprev_inv9, const float* tprev3);
+int ef_icp_dense_pass_async(EfContext* ctx, int which, int level);
 
 /* ---- depth preprocess: ElasticFusion::filterDepth + metriciseDepth (Core/ElasticFusion.cpp:655-673,
  *      Core/Shaders/depth_bilateral.frag, depth_metric.frag). DEVICE in/out, any out may be NULL ------------- */

@@ -38,6 +38,15 @@ def lib():
     return _LIB
 
 
+def set_threads(n: int) -> None:
+    """OpenMP thread count of the oracle (torchrun exports OMP_NUM_THREADS=1, which libgomp may already have read)."""
+    lib()
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
 class DataTerm(C.Structure):
     _fields_ = [("zero_x", C.c_int16), ("zero_y", C.c_int16), ("one_x", C.c_int16), ("one_y", C.c_int16),
                 ("diff", C.c_float), ("valid", C.c_int32)]
