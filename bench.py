@@ -288,18 +288,36 @@ def cpu_baseline(K, rgb, depth, cap, seconds=20.0):
         f.process_frame(rgb[n], depth[n], n)
         n += 1
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+    return {"value": n / dt, "unit": "frames/s", "cores": eo.get_threads(), "kind": "port",
             "sample": f"first {n} frames of the same sequence through the CPU oracle pipeline ({dt:.1f} s)", "stages_s": f.timers()}
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def usable_cores():
+    """Host threads this process may really use: affinity mask capped by the cgroup CPU quota (oversubscribing OpenMP
+    beyond that makes the spin-waiting teams collapse)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(p))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // p))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def run_reference(args, rank, world):
     """Reference arm: reference CUDA tracking (oracle/_ref, unmodified kernels driven like RGBDOdometry.cpp) + CPU oracle
     for the GLSL mapping half. Falls back to the pure CPU oracle when oracle/_ref is absent."""
     if rank != 0:
         return
-    ncores = os.cpu_count() or 1
-    os.environ["OMP_NUM_THREADS"] = str(ncores)  # torchrun pins it to 1; the reference arm may use every host core
+    pinned = "OMP_NUM_THREADS" in os.environ  # torchrun pins it to 1; the reference arm may use the usable host cores
     K, cap, wl_name = workload(args)
     n_total = args.warmup + args.steps
     budget_frames = min(n_total, 150)
@@ -312,7 +330,9 @@ def run_reference(args, rank, world):
         have_ref = False
     from oracle import ef_oracle as eo
 
-    eo.set_threads(ncores)
+    if pinned:
+        eo.set_threads(min(usable_cores(), 32))  # the oracle's row-parallel loops stop scaling (and can collapse) beyond this
+    ncores = eo.get_threads()
     if have_ref:
         from oracle import ef_ref
 
@@ -333,7 +353,7 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": "frames/sec, full track+fuse+predict (processFrame)", "value": v, "unit": "frames/s", "n_gpus": world,
            "steps": k, "warmup": w, "ms_per_step": dt / k * 1000.0, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic", "config": {"workload": wl_name, "frames_per_gpu": k, "open_loop": True},
-           "cpu_baseline": {"value": v, "unit": "frames/s", "cores": os.cpu_count(), "kind": kind, "sample": sample + f"; {k} frames"},
+           "cpu_baseline": {"value": v, "unit": "frames/s", "cores": ncores, "kind": kind, "sample": sample + f"; {k} frames"},
            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "stages_s": runner.timers() if hasattr(runner, "timers") else None}
     print(json.dumps(out))

@@ -265,6 +265,10 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
     ctx->own_stream = true;
   }
   ctx->launches = 0;
+  {
+    const char* e = getenv("EF_NO_PDL");
+    ctx->pdl = !(e && e[0] == '1');
+  }
   ctx->tick = 1;
   for (int k = 0; k < 16; ++k) ctx->T_wc[k] = (k % 5 == 0) ? 1.0 : 0.0;
   ctx->rgb_only = false;

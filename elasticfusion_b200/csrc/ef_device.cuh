@@ -98,6 +98,15 @@ __device__ __forceinline__ void block_reduce_sum(float (&v)[N], float* smem /* 3
   }
 }
 
+// Programmatic dependent launch: every kernel of the library starts with this. launch_dependents lets the NEXT kernel
+// in the stream be scheduled (its CTAs become resident and park at their own wait) while this grid is still running;
+// wait blocks until the PREVIOUS grid has completed and its memory is visible. Because every kernel waits before it
+// touches memory, stream order is preserved transitively -- only the launch latency of dependent kernels is hidden.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // "last block done" ticket: returns true in every thread of the block that arrives last.
 __device__ __forceinline__ bool last_block_done(unsigned int* counter) {
   __shared__ bool is_last;

@@ -147,6 +147,7 @@ struct EfContext {
   cudaStream_t stream;
   bool own_stream;
   int64_t launches;
+  bool pdl;  // programmatic dependent launch on every kernel (default on; EF_NO_PDL=1 disables)
 
   ef::OdomDev odom[2];
   ef::MapDev map;
@@ -170,8 +171,21 @@ struct EfContext {
 };
 
 // launch bookkeeping
-#define EF_LAUNCH(ctx, kernel, grid, block, smem, ...)                    \
-  do {                                                                     \
-    kernel<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__);             \
-    (ctx)->launches++;                                                     \
-  } while (0)
+// Every kernel is launched with programmatic stream serialisation allowed (see pdl_enter() in ef_device.cuh); set
+// EF_NO_PDL=1 in the environment to fall back to plain stream-ordered launches (A/B measurements).
+template <typename... KArgs, typename... Args>
+inline void ef_launch(EfContext* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctx->pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  ctx->launches++;
+}
+#define EF_LAUNCH(ctx, kernel, grid, block, smem, ...) ef_launch((ctx), kernel, dim3(grid), dim3(block), (smem), __VA_ARGS__)

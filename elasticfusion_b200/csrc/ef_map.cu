@@ -130,6 +130,7 @@ __device__ __forceinline__ int window_axis(float centre, float step, int n, int 
 // pose upload: T_wc (double) -> float pose and float inverse, as the shader uniforms (GlobalModel.cpp:405,562)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void k_update_pose(MapPose* mp, const double* T) {
+  pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double inv[16];
   efm::se3_inverse(T, inv);
@@ -145,6 +146,7 @@ __global__ void k_update_pose(MapPose* mp, const double* T) {
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_flags(const uint8_t* __restrict__ flags, const int* __restrict__ n_a,
                                                               const int* __restrict__ n_b, int* __restrict__ offsets,
                                                               unsigned long long* state, unsigned int* counter, int* total_out) {
+  pdl_enter();
   const int n = (n_a ? *n_a : 0) + (n_b ? *n_b : 0);
   const int num_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   __shared__ int s_warp[SCAN_THREADS / 32];
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_flags(const uint8_t* __re
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void k_feedback_flags(const float* __restrict__ depth_raw, const float* __restrict__ depth_filt, int rows, int cols,
                                  float max_depth, uint8_t* __restrict__ f_raw, uint8_t* __restrict__ f_filt) {
+  pdl_enter();
   const int n = rows * cols;
   for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < n; d += gridDim.x * blockDim.x) {
     const int i = d / rows, j = d - i * rows;  // draw order: x-major
@@ -251,6 +254,7 @@ __global__ void k_init_scatter(const uint8_t* __restrict__ rgb, const float* __r
                                const int* __restrict__ off_raw, const int* __restrict__ off_filt, const int* __restrict__ raw_total,
                                int capacity, float4* __restrict__ pos_conf, float4* __restrict__ color_time, float4* __restrict__ norm_rad,
                                int* __restrict__ count) {
+  pdl_enter();
   const float ifx = 1.0f / c.fx, ify = 1.0f / c.fy;
   const int n = rows * cols;
   if (blockIdx.x == 0 && threadIdx.x == 0) *count = min(*raw_total, capacity);
@@ -285,6 +289,7 @@ __global__ void k_init_scatter(const uint8_t* __restrict__ rgb, const float* __r
 __global__ void k_index_scatter(const float4* __restrict__ pos_conf, const float4* __restrict__ color_time, const int* __restrict__ count,
                                 const MapPose* __restrict__ mp, int time, float max_depth, int time_delta, int rows, int cols, Cam c,
                                 unsigned long long* __restrict__ zbuf) {
+  pdl_enter();
   const int n = *count;
   const float fcols = (float)cols, frows = (float)rows;
   for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
@@ -310,6 +315,7 @@ __global__ void k_index_resolve(const float4* __restrict__ pos_conf, const float
                                 const MapPose* __restrict__ mp, int n_px, const unsigned long long* __restrict__ zbuf,
                                 uint32_t* __restrict__ index, float4* __restrict__ vert_conf, float4* __restrict__ col_time,
                                 float4* __restrict__ nrm_rad) {
+  pdl_enter();
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_px; p += gridDim.x * blockDim.x) {
     const unsigned long long key = zbuf[p];
     if (key == kEmptyKey) {
@@ -379,6 +385,7 @@ constexpr uint32_t ASSOC_NONE = 0xffffffffu, ASSOC_NEW = 0xfffffffeu;
 
 __global__ void k_fuse_associate(FuseArgs a, const int* __restrict__ count, uint32_t* __restrict__ assoc, uint32_t* __restrict__ pending,
                                  uint8_t* __restrict__ new_flags) {
+  pdl_enter();
   const Quarter Q = quarter_of(a.time, a.rows, a.cols);
   const int nq = Q.ni * Q.nj;
   const int cnt = *count;
@@ -462,6 +469,7 @@ __global__ void k_fuse_update(FuseArgs a, const MapPose* __restrict__ mp, const 
                               const int* __restrict__ new_total, float4* __restrict__ pos_conf, float4* __restrict__ color_time,
                               float4* __restrict__ norm_rad, float4* __restrict__ new_pos, float4* __restrict__ new_col,
                               float4* __restrict__ new_nr, int* __restrict__ new_count) {
+  pdl_enter();
   const Quarter Q = quarter_of(a.time, a.rows, a.cols);
   const int nq = Q.ni * Q.nj;
   const int cnt = *count;
@@ -567,6 +575,7 @@ __global__ void k_clean_flags(CleanArgs a, const MapPose* __restrict__ mp, const
                               const float4* __restrict__ color_time, const float4* __restrict__ norm_rad, const int* __restrict__ count,
                               const float4* __restrict__ new_pos, const float4* __restrict__ new_col, const float4* __restrict__ new_nr,
                               const int* __restrict__ new_count, uint8_t* __restrict__ flags) {
+  pdl_enter();
   const int n_old = *count, total = n_old + *new_count;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
     float4 pos, col, nr;
@@ -589,6 +598,7 @@ __global__ void k_clean_scatter(int time, const float4* __restrict__ pos_conf, c
                                 const uint8_t* __restrict__ flags, const int* __restrict__ offsets, const int* __restrict__ total_kept,
                                 int capacity, float4* __restrict__ out_pos, float4* __restrict__ out_col, float4* __restrict__ out_nr,
                                 int* __restrict__ out_count) {
+  pdl_enter();
   const int n_old = *count, total = n_old + *new_count;
   if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = min(*total_kept, capacity);
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
@@ -670,6 +680,7 @@ __device__ __forceinline__ bool splat_fragment(const Splat& sp, const Cam& c, in
 __global__ void k_splat_scatter(RayArgs a, const MapPose* __restrict__ mp, const float4* __restrict__ pos_conf,
                                 const float4* __restrict__ color_time, const float4* __restrict__ norm_rad, const int* __restrict__ count,
                                 unsigned long long* __restrict__ zbuf) {
+  pdl_enter();
   const int n = *count;
   for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
     Splat sp;
@@ -696,6 +707,7 @@ __global__ void k_splat_resolve(RayArgs a, const MapPose* __restrict__ mp, const
                                 const float4* __restrict__ color_time, const float4* __restrict__ norm_rad,
                                 const unsigned long long* __restrict__ zbuf, uchar4* __restrict__ image, float4* __restrict__ vertex,
                                 float4* __restrict__ normal, uint16_t* __restrict__ time_out, float* __restrict__ depth_out) {
+  pdl_enter();
   const int n_px = a.rows * a.cols;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_px; p += gridDim.x * blockDim.x) {
     const unsigned long long key = zbuf[p];
@@ -738,6 +750,7 @@ __global__ void k_fill_in(const float4* __restrict__ vertex, const float4* __res
                           const uint16_t* __restrict__ raw_depth, const uint8_t* __restrict__ rgb, int rows, int cols, Cam c,
                           int pass_geom, int pass_img, float4* __restrict__ fvertex, float4* __restrict__ fnormal,
                           uchar4* __restrict__ fimage) {
+  pdl_enter();
   const float ifx = 1.0f / c.fx, ify = 1.0f / c.fy;
   const int n = rows * cols;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
@@ -769,6 +782,7 @@ __global__ void k_fill_in(const float4* __restrict__ vertex, const float4* __res
 
 // Resize::image (nearest decimation by 20) + ElasticFusion::denseEnough (Resize.cpp:50-79, ElasticFusion.cpp:256-268)
 __global__ void k_dense_enough(const uchar4* __restrict__ image, int rows, int cols, int factor, int* __restrict__ flag) {
+  pdl_enter();
   const int drows = rows / factor, dcols = cols / factor;
   __shared__ int s_sum;
   if (threadIdx.x == 0) s_sum = 0;
@@ -787,11 +801,13 @@ __global__ void k_dense_enough(const uchar4* __restrict__ image, int rows, int c
 }
 
 __global__ void k_set_int(int* p, int v) {
+  pdl_enter();
   if (threadIdx.x == 0 && blockIdx.x == 0) *p = v;
 }
 
 // AoS (reference Vertex layout) <-> SoA repack for downloadMap / upload
 __global__ void k_pack_aos(const float4* __restrict__ a, const float4* __restrict__ b, const float4* __restrict__ c, int n, float4* __restrict__ out) {
+  pdl_enter();
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     out[(size_t)k * 3 + 0] = a[k];
     out[(size_t)k * 3 + 1] = b[k];
@@ -799,6 +815,7 @@ __global__ void k_pack_aos(const float4* __restrict__ a, const float4* __restric
   }
 }
 __global__ void k_unpack_aos(const float4* __restrict__ in, int n, float4* __restrict__ a, float4* __restrict__ b, float4* __restrict__ c) {
+  pdl_enter();
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     a[k] = in[(size_t)k * 3 + 0];
     b[k] = in[(size_t)k * 3 + 1];

@@ -15,6 +15,7 @@ constexpr int SM_W = TILE_X + 2 * R, SM_H = TILE_Y + 2 * R;
 __global__ void __launch_bounds__(TILE_X* TILE_Y) k_preprocess_depth(const uint16_t* __restrict__ depth, int rows, int cols, float maxD,
                                                                       uint16_t* __restrict__ filtered, float* __restrict__ metric,
                                                                       float* __restrict__ metric_filtered) {
+  pdl_enter();
   // stage the (32+12) x (8+12) neighbourhood once per CTA; out-of-image taps are never read (the window is clipped)
   __shared__ float tile[SM_H][SM_W + 1];
   const int x0 = blockIdx.x * TILE_X - R, y0 = blockIdx.y * TILE_Y - R;
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_preprocess_depth(const uint1
 
 // GL_RGB upload into the RGBA8 texture the tracker samples (alpha = 255)
 __global__ void k_rgb_to_rgba(const uint8_t* __restrict__ rgb, uchar4* __restrict__ rgba, size_t n) {
+  pdl_enter();
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x)
     rgba[p] = make_uchar4(rgb[p * 3 + 0], rgb[p * 3 + 1], rgb[p * 3 + 2], 255);
 }

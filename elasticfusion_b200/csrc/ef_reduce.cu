@@ -79,6 +79,7 @@ __device__ void so3_prepare(GNState* gn) {
 
 // start of getIncrementalTransformation (RGBDOdometry.cpp:266-273,284-303)
 __global__ void k_gn_begin(GNState* gn, int rgbOnly, float icpWeight, int so3) {
+  pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   gn->rgbOnly = rgbOnly;
   gn->icpWeight = icpWeight;
@@ -108,6 +109,7 @@ __global__ void k_gn_begin(GNState* gn, int rgbOnly, float icpWeight, int so3) {
 
 // after the SO3 loop: seed resultRt (RGBDOdometry.cpp:379-388) and prepare the first SE3 iteration
 __global__ void k_gn_seed(GNState* gn, int first_level) {
+  pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   for (int k = 0; k < 16; ++k) gn->resultRt[k] = (k % 5 == 0) ? 1.0 : 0.0;
   if (gn->so3)
@@ -126,6 +128,7 @@ __global__ void k_gn_seed(GNState* gn, int first_level) {
 
 // end of getIncrementalTransformation (RGBDOdometry.cpp:555-570) + velocity weighting (ElasticFusion.cpp:369-383)
 __global__ void k_gn_finish(GNState* gn, float weightMultiplier, int have_track) {
+  pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double Tprev[16];
   for (int k = 0; k < 16; ++k) Tprev[k] = gn->T_wc[k];
@@ -165,6 +168,7 @@ __global__ void k_gn_finish(GNState* gn, float weightMultiplier, int have_track)
 // k_gn_finish needs the pre-tracking pose; stash it (tracking overwrites T_wc only at the end, so this is only needed
 // for the in_T_wc path where the host replaces the pose).
 __global__ void k_set_pose(GNState* gn, const double* T_new) {
+  pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   for (int k = 0; k < 16; ++k) {
     gn->resultRt[k] = gn->T_wc[k];
@@ -419,6 +423,7 @@ __device__ __forceinline__ void icp_accumulate(const IcpFrame& F, const f3& vcur
 //      candidate and the CTA's {count, sum int(diff^2)};
 //  (b) the dense geometric rows (ICPReduction, reduce.cu:224-331) reduced to one 29-float partial per CTA.
 __global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev od, int level, int do_res, int do_icp, int solve) {
+  pdl_enter();
   GNState* gn = od.gn;
   if (solve && gn->break_level == level) return;  // rgbOnly `break`: rest of the level is skipped
   __shared__ float sred[32 * (IT1_THREADS / 32)];
@@ -580,6 +585,7 @@ __device__ __forceinline__ void rgb_accumulate(const int4& term, float sigma, fl
 // and its first warp solves and updates the pose. mode bits: 1 = rgb rows, 2 = icp partials present, 4 = solve,
 // 8 = correspondence statistics present, 16 = use sigma_override.
 __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, int iter, int next_level, int nblocks1, int mode, float sigma_override) {
+  pdl_enter();
   __shared__ GnScratch S;
   __shared__ float sred[32 * (IT2_THREADS / 32)];
   __shared__ float s_sigma;
@@ -735,6 +741,7 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
 
 // expands the compact per-candidate terms into the reference's dense DataTerm image (inspection / stage API only)
 __global__ void k_terms_expand(OdomDev od, int level) {
+  pdl_enter();
   const GNState* gn = od.gn;
   const int cols = od.cols[level];
   const int base = gn->cand_base[level], ncand = gn->cand_base[level + 1] - base;
@@ -781,6 +788,7 @@ __device__ __forceinline__ void so3_gradient(const uint8_t* img, int cols, int x
 }
 
 __global__ void __launch_bounds__(RED_THREADS) k_so3_step(OdomDev od, int iter, int solve) {
+  pdl_enter();
   GNState* gn = od.gn;
   if (solve && gn->so3_done) return;
   __shared__ float sred[32 * (RED_THREADS / 32)];

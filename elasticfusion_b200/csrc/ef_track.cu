@@ -55,6 +55,7 @@ __device__ __forceinline__ uint16_t pyr_down_u16_at(Fetch fetch, int srows, int 
 }
 
 __global__ void k_pyr_down_u16(const uint16_t* __restrict__ src, int srows, int scols, uint16_t* __restrict__ dst) {
+  pdl_enter();
   const int r1 = srows / 2, c1 = scols / 2;
   auto f0 = [&](int yy, int xx) { return (int)src[(size_t)yy * scols + xx]; };
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < r1 * c1; t += gridDim.x * blockDim.x) {
@@ -109,6 +110,7 @@ __device__ __forceinline__ void vmap_nmap_at(const uint16_t* __restrict__ depth,
   nmap[p + 2 * plane] = n.z;
 }
 __global__ void k_vmap_nmap(VmapArgs a, float cutoff) {
+  pdl_enter();
   const int total = a.start[NUM_PYRS];
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
     const int lv = (f >= a.start[2]) ? 2 : (f >= a.start[1] ? 1 : 0);
@@ -124,6 +126,7 @@ __global__ void k_vmap_nmap(VmapArgs a, float cutoff) {
 __global__ void k_copy_maps(const float4* __restrict__ vtxA, const float4* __restrict__ nrmA, const float4* __restrict__ vtxB,
                             const float4* __restrict__ nrmB, const int* __restrict__ dense_flag, int rows, int cols,
                             float4* __restrict__ vmaps_tmp, float* __restrict__ vmap, float* __restrict__ nmap) {
+  pdl_enter();
   const size_t n = (size_t)rows * cols;
   const bool useB = dense_flag && (*dense_flag == 0);
   const float4* __restrict__ vtx = useB ? vtxB : vtxA;
@@ -149,6 +152,7 @@ __global__ void k_copy_maps(const float4* __restrict__ vtxA, const float4* __res
 // resizeVMap + resizeNMap (cudafuncs.cu:413-490) in one launch: 2x2 box average, any NaN -> NaN, normals renormalised
 __global__ void k_resize_maps(const float* __restrict__ vin, const float* __restrict__ nin, int srows, int scols,
                               float* __restrict__ vout, float* __restrict__ nout) {
+  pdl_enter();
   const int drows = srows / 2, dcols = scols / 2;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -190,6 +194,7 @@ struct XformArgs {
   int rows[NUM_PYRS], cols[NUM_PYRS];
 };
 __global__ void k_transform_maps(XformArgs a, const GNState* __restrict__ gn) {
+  pdl_enter();
   const int lv = blockIdx.y;
   const size_t np = (size_t)a.rows[lv] * a.cols[lv];
   float R[9], t[3];
@@ -226,6 +231,7 @@ __global__ void k_transform_maps(XformArgs a, const GNState* __restrict__ gn) {
 __global__ void k_depth_intensity_l0(const float4* __restrict__ vmaps_tmp, const uchar4* __restrict__ rgbaA,
                                      const uchar4* __restrict__ rgbaB, const int* __restrict__ dense_flag, int forceB, size_t n,
                                      float cutoff, float* __restrict__ depth, uint8_t* __restrict__ image) {
+  pdl_enter();
   const uchar4* __restrict__ rgba = (forceB || (dense_flag && *dense_flag == 0)) ? rgbaB : rgbaA;
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
     if (depth) {
@@ -296,6 +302,7 @@ __device__ __forceinline__ uint8_t pyr_down_u8_at(Fetch fetch, int srows, int sc
 // depth (fp32) and intensity (u8) pyramid level in one launch. Either pair may be NULL.
 __global__ void k_pyr_down_depth_image(const float* __restrict__ d0, float* __restrict__ d1, const uint8_t* __restrict__ i0,
                                        uint8_t* __restrict__ i1, int srows, int scols) {
+  pdl_enter();
   const int r1 = srows / 2, c1 = scols / 2;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < r1 * c1; t += gridDim.x * blockDim.x) {
     const int y = t / c1, x = t - y * c1;
@@ -325,6 +332,7 @@ struct SobelArgs {
   float minScale[NUM_PYRS];
 };
 __global__ void k_sobel_cand(SobelArgs a, uint8_t* __restrict__ flags) {
+  pdl_enter();
   const float gsx[9] = {(float)0.52201, (float)0.00000, (float)-0.52201, (float)0.79451, (float)-0.00000,
                         (float)-0.79451, (float)0.52201, (float)0.00000, (float)-0.52201};
   const float gsy[9] = {(float)0.52201, (float)0.79451, (float)0.52201, (float)0.00000, (float)0.00000,
@@ -363,6 +371,7 @@ __global__ void k_sobel_cand(SobelArgs a, uint8_t* __restrict__ flags) {
 
 __global__ void k_cand_scatter(SobelArgs a, const uint8_t* __restrict__ flags, const int* __restrict__ offsets, int4* __restrict__ cand,
                                GNState* gn) {
+  pdl_enter();
   const int total = a.start[NUM_PYRS];
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
     const int lv = (f >= a.start[2]) ? 2 : (f >= a.start[1] ? 1 : 0);

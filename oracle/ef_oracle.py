@@ -47,6 +47,15 @@ def set_threads(n: int) -> None:
         pass
 
 
+def get_threads() -> int:
+    """OpenMP team size the oracle will use."""
+    lib()
+    try:
+        return int(C.CDLL("libgomp.so.1").omp_get_max_threads())
+    except OSError:
+        return 1
+
+
 class DataTerm(C.Structure):
     _fields_ = [("zero_x", C.c_int16), ("zero_y", C.c_int16), ("one_x", C.c_int16), ("one_y", C.c_int16),
                 ("diff", C.c_float), ("valid", C.c_int32)]
