@@ -172,9 +172,25 @@ class Context:
 
     # ---- whole frame
     def process_frame(self, rgb, depth, timestamp=0, weight_multiplier=1.0, T_wc=None):
+        """rgb = depth = None consumes the frame staged by prefetch_frame()."""
+        if rgb is None and depth is None:
+            _chk(lib().ef_process_frame(self.h_ctx, None, None, C.c_int64(timestamp), _f(weight_multiplier), _p(_T(T_wc))))
+            return
         rgb = np.ascontiguousarray(rgb, np.uint8)
         depth = np.ascontiguousarray(depth, np.uint16)
         _chk(lib().ef_process_frame(self.h_ctx, _p(rgb), _p(depth), C.c_int64(timestamp), _f(weight_multiplier), _p(_T(T_wc))))
+
+    def prefetch_frame(self, rgb, depth):
+        """Look-ahead: stage + preprocess the NEXT frame (host arrays) on the side stream."""
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        _chk(lib().ef_prefetch_frame(self.h_ctx, _p(rgb), _p(depth)))
+
+    def prefetch_frame_device(self, rgb_ptr, depth_ptr):
+        _chk(lib().ef_prefetch_frame_device(self.h_ctx, C.c_void_p(rgb_ptr), C.c_void_p(depth_ptr)))
+
+    def finish_frame(self):
+        _chk(lib().ef_finish_frame(self.h_ctx))
 
     def process_frame_device(self, rgb_ptr, depth_ptr, timestamp=0, weight_multiplier=1.0, T_wc=None):
         _chk(lib().ef_process_frame_device(self.h_ctx, C.c_void_p(rgb_ptr), C.c_void_p(depth_ptr), C.c_int64(timestamp),

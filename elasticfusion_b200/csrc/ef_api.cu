@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "ef_internal.h"
@@ -20,7 +21,7 @@ int odom_init_icp_pred(EfContext* ctx, int which, const float* vtx4, const float
 int odom_init_icp_model(EfContext* ctx, int which, const float* vtx4, const float* nrm4, const float* vtxB = nullptr,
                         const float* nrmB = nullptr, const int* flag = nullptr);
 int odom_populate(EfContext* ctx, int which, const uint8_t* rgba, float** destDepths, uint8_t** destImages, bool with_depth,
-                  const uint8_t* rgbaB = nullptr, const int* flag = nullptr, bool forceB = false);
+                  const uint8_t* rgbaB = nullptr, const int* flag = nullptr, bool forceB = false, bool with_image = true);
 int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom, bool so3);
 int odom_finish_async(EfContext* ctx, int which, float weightMultiplier, bool have_track);
 int odom_set_pose_async(EfContext* ctx, int which, const double* T_dev);
@@ -268,6 +269,11 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
   {
     const char* e = getenv("EF_NO_PDL");
     ctx->pdl = !(e && e[0] == '1');
+    e = getenv("EF_STAGE_TIMING");
+    ctx->stage_timing = (e && e[0] == '1');
+    ctx->stage_n = 0;
+    if (ctx->stage_timing)
+      for (int i = 0; i < 16; ++i) cudaEventCreate(&ctx->stage_ev[i]);
   }
   ctx->tick = 1;
   for (int k = 0; k < 16; ++k) ctx->T_wc[k] = (k % 5 == 0) ? 1.0 : 0.0;
@@ -316,6 +322,37 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
   TA(t.time, n);
   TA(t.old_time, n);
   TA(t.synth_depth, n);
+  {
+    // spare input-side set + side stream of the frame look-ahead
+    Lookahead& la = ctx->la;
+    memset(&la, 0, sizeof(la));
+    TA(la.rgb, n * 3);
+    TA(la.rgba, n * 4);
+    TA(la.depth_raw, n);
+    TA(la.depth_filtered, n);
+    TA(la.depth_metric, n);
+    TA(la.depth_metric_filtered, n);
+    for (int i = 0; i < NUM_PYRS; ++i) {
+      const size_t ni = (size_t)ctx->odom[0].rows[i] * ctx->odom[0].cols[i];
+      TA(la.depth_tmp[i], ni);
+      TA(la.vmap_curr[i], 3 * ni);
+      TA(la.nmap_curr[i], 3 * ni);
+      TA(la.image[i], ni);
+      if (!rc) {
+        cudaMemsetAsync(la.vmap_curr[i], 0xff, 3 * ni * sizeof(float), ctx->stream);
+        cudaMemsetAsync(la.nmap_curr[i], 0xff, 3 * ni * sizeof(float), ctx->stream);
+      }
+    }
+    if (!rc) {
+      cudaError_t e = cudaStreamCreateWithFlags(&la.stream, cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&la.ready, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&la.spare_free, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&la.h2d_done, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaMallocHost((void**)&la.pin_rgb, n * 3);
+      if (e == cudaSuccess) e = cudaMallocHost((void**)&la.pin_depth, n * 2);
+      if (e != cudaSuccess) rc = (int)e;
+    }
+  }
 #undef TA
   if (!rc) rc = alloc_map(ctx);
   if (!rc) {
@@ -326,7 +363,9 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
     if (e != cudaSuccess) rc = (int)e;
   }
   if (!rc) {
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaEventRecord(ctx->la.spare_free, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->la.h2d_done, ctx->la.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = (int)e;
   }
   if (rc) {
@@ -341,6 +380,15 @@ extern "C" int ef_destroy(EfContext* ctx) {
   if (!ctx) return EF_EINVAL;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->la.stream) {
+    cudaStreamSynchronize(ctx->la.stream);
+    cudaStreamDestroy(ctx->la.stream);
+  }
+  if (ctx->la.ready) cudaEventDestroy(ctx->la.ready);
+  if (ctx->la.spare_free) cudaEventDestroy(ctx->la.spare_free);
+  if (ctx->la.h2d_done) cudaEventDestroy(ctx->la.h2d_done);
+  if (ctx->la.pin_rgb) cudaFreeHost(ctx->la.pin_rgb);
+  if (ctx->la.pin_depth) cudaFreeHost(ctx->la.pin_depth);
   map_free_host(ctx);
   for (void* p : arena(ctx)->blocks) cudaFree(p);
   if (ctx->pin_rgb) cudaFreeHost(ctx->pin_rgb);
@@ -356,6 +404,7 @@ extern "C" void* ef_stream(EfContext* ctx) { return ctx ? (void*)ctx->stream : n
 extern "C" int ef_sync(EfContext* ctx) {
   if (!ctx) return EF_EINVAL;
   CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->la.stream));
   return 0;
 }
 extern "C" int ef_launch_count(EfContext* ctx, int64_t* n) {
@@ -795,10 +844,9 @@ extern "C" int ef_predict(EfContext* ctx) {
   return predict_async(ctx);
 }
 
-extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, const uint16_t* depth_dev, int64_t timestamp,
-                                       float weight_multiplier, const double* in_T_wc) {
-  (void)timestamp;
-  if (!ctx || !rgb_dev || !depth_dev) return EF_EINVAL;
+// Input side of a frame: everything that depends neither on the map nor on the pose (ElasticFusion.cpp:278-285 and the
+// live half of RGBDOdometry::initICP / initRGB). Runs on ctx->stream into the live buffer set.
+static int frame_input_side(EfContext* ctx, const uint8_t* rgb_dev, const uint16_t* depth_dev) {
   const size_t n = (size_t)ctx->cfg.width * ctx->cfg.height;
   Textures& t = ctx->tex;
   // texture uploads, reference ElasticFusion.cpp:278-280
@@ -807,11 +855,98 @@ extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, c
   RC(rgb_to_rgba(ctx, t.rgb, t.rgba));
   // filterDepth + metriciseDepth, ElasticFusion.cpp:284-285
   RC(preprocess_depth(ctx, t.depth_raw, ctx->depth_cutoff, t.depth_filtered, t.depth_metric, t.depth_metric_filtered));
+  // frameToModel.initICP(filtered depth) and the intensity half of initRGB, ElasticFusion.cpp:318-319
+  RC(odom_init_icp_depth(ctx, 0, t.depth_filtered, ctx->max_depth_processed));
+  RC(odom_populate(ctx, 0, t.rgba, nullptr, ctx->odom[0].nextImage, false));
+  return 0;
+}
+
+static void swap_sides(EfContext* ctx) {
+  Lookahead& la = ctx->la;
+  Textures& t = ctx->tex;
+  OdomDev& od = ctx->odom[0];
+  std::swap(t.rgb, la.rgb);
+  std::swap(t.rgba, la.rgba);
+  std::swap(t.depth_raw, la.depth_raw);
+  std::swap(t.depth_filtered, la.depth_filtered);
+  std::swap(t.depth_metric, la.depth_metric);
+  std::swap(t.depth_metric_filtered, la.depth_metric_filtered);
+  for (int i = 0; i < NUM_PYRS; ++i) {
+    std::swap(od.depth_tmp[i], la.depth_tmp[i]);
+    std::swap(od.vmap_curr[i], la.vmap_curr[i]);
+    std::swap(od.nmap_curr[i], la.nmap_curr[i]);
+    std::swap(od.nextImage[i], la.image[i]);
+  }
+}
+
+// rgb/depth: device pointers, or pinned host staging when from_host
+static int prefetch_common(EfContext* ctx, const uint8_t* rgb, const uint16_t* depth, bool from_host) {
+  Lookahead& la = ctx->la;
+  if (la.pending) return EF_ESTATE;
+  const size_t n = (size_t)ctx->cfg.width * ctx->cfg.height;
+  cudaStream_t main_stream = ctx->stream;
+  swap_sides(ctx);  // the helpers below write the live pointers: make the spare set live while enqueueing
+  ctx->stream = la.stream;
+  int rc = 0;
+  cudaError_t e = cudaStreamWaitEvent(la.stream, la.spare_free, 0);
+  if (e == cudaSuccess && from_host) {
+    e = cudaMemcpyAsync(ctx->tex.rgb, rgb, n * 3, cudaMemcpyHostToDevice, la.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->tex.depth_raw, depth, n * 2, cudaMemcpyHostToDevice, la.stream);
+    if (e == cudaSuccess) e = cudaEventRecord(la.h2d_done, la.stream);
+    rgb = ctx->tex.rgb;
+    depth = ctx->tex.depth_raw;
+  }
+  if (e != cudaSuccess) rc = (int)e;
+  if (!rc) rc = frame_input_side(ctx, rgb, depth);
+  if (!rc) {
+    e = cudaEventRecord(la.ready, la.stream);
+    if (e != cudaSuccess) rc = (int)e;
+  }
+  ctx->stream = main_stream;
+  swap_sides(ctx);
+  if (!rc) la.pending = true;
+  return rc;
+}
+
+extern "C" int ef_prefetch_frame_device(EfContext* ctx, const uint8_t* rgb_dev, const uint16_t* depth_dev) {
+  if (!ctx || !rgb_dev || !depth_dev) return EF_EINVAL;
+  return prefetch_common(ctx, rgb_dev, depth_dev, false);
+}
+
+extern "C" int ef_prefetch_frame(EfContext* ctx, const uint8_t* rgb, const uint16_t* depth) {
+  if (!ctx || !rgb || !depth) return EF_EINVAL;
+  if (ctx->la.pending) return EF_ESTATE;
+  const size_t n = (size_t)ctx->cfg.width * ctx->cfg.height;
+  CU(cudaEventSynchronize(ctx->la.h2d_done));  // the staging buffers of the previous prefetch have been read
+  memcpy(ctx->la.pin_rgb, rgb, n * 3);
+  memcpy(ctx->la.pin_depth, depth, n * 2);
+  return prefetch_common(ctx, ctx->la.pin_rgb, ctx->la.pin_depth, true);
+}
+
+extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, const uint16_t* depth_dev, int64_t timestamp,
+                                       float weight_multiplier, const double* in_T_wc) {
+  (void)timestamp;
+  if (!ctx || ((rgb_dev == nullptr) != (depth_dev == nullptr))) return EF_EINVAL;
+  Textures& t = ctx->tex;
+  Lookahead& la = ctx->la;
+  ef_stage(ctx, 0);
+  if (!rgb_dev) {
+    // consume the prefetched frame: its buffer set becomes live, the previous live set becomes the spare one
+    if (!la.pending) return EF_ESTATE;
+    swap_sides(ctx);
+    CU(cudaEventRecord(la.spare_free, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->stream, la.ready, 0));
+    la.pending = false;
+  } else {
+    if (la.pending) return EF_ESTATE;  // a prefetched frame must be consumed first (pass NULL, NULL)
+    RC(frame_input_side(ctx, rgb_dev, depth_dev));
+  }
+  ef_stage(ctx, 1);
 
   if (ctx->tick == 1) {
-    // ElasticFusion.cpp:290-296
+    // ElasticFusion.cpp:290-296; initFirstRGB: the intensity pyramid of the first frame is the SO(3) "last" image
     RC(map_initialise_async(ctx));
-    RC(odom_populate(ctx, 0, t.rgba, nullptr, ctx->odom[0].lastNextImage, false));
+    for (int i = 0; i < NUM_PYRS; ++i) std::swap(ctx->odom[0].nextImage[i], ctx->odom[0].lastNextImage[i]);
   } else {
     OdomDev& od = ctx->odom[0];
     if (!in_T_wc) {
@@ -819,9 +954,24 @@ extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, c
       // pyramid kernels together with the flag.
       RC(map_dense_enough_async(ctx));
       RC(map_select_model_inputs(ctx, nullptr, nullptr, nullptr));
-      RC(odom_init_icp_depth(ctx, 0, t.depth_filtered, ctx->max_depth_processed));
-      RC(odom_populate(ctx, 0, t.rgba, od.nextDepth, od.nextImage, true));
-      RC(odom_track_async(ctx, 0, ctx->rgb_only, ctx->icp_weight, ctx->pyramid, ctx->fast_odom, ctx->so3));
+      // initRGB's depth half (populateRGBDData -> verticesToDepth(vmaps_tmp), RGBDOdometry.cpp:212-222) reads the SAME
+      // vmaps_tmp initICPModel just filled, so in frame-to-model mode nextDepth is identical to lastDepth: alias it for
+      // the tracking call instead of building the pyramid twice.
+      float* saved[NUM_PYRS];
+      const bool alias = !ctx->frame_to_frame_rgb;
+      if (alias) {
+        for (int i = 0; i < NUM_PYRS; ++i) {
+          saved[i] = od.nextDepth[i];
+          od.nextDepth[i] = od.lastDepth[i];
+        }
+      } else {
+        RC(odom_populate(ctx, 0, t.rgba, od.nextDepth, od.nextImage, true, nullptr, nullptr, false, false));
+      }
+      ef_stage(ctx, 2);
+      int rc = odom_track_async(ctx, 0, ctx->rgb_only, ctx->icp_weight, ctx->pyramid, ctx->fast_odom, ctx->so3);
+      if (alias)
+        for (int i = 0; i < NUM_PYRS; ++i) od.nextDepth[i] = saved[i];
+      RC(rc);
       RC(odom_finish_async(ctx, 0, weight_multiplier, true));
     } else {
       CU(cudaStreamSynchronize(ctx->stream));
@@ -831,33 +981,30 @@ extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, c
       RC(odom_finish_async(ctx, 0, weight_multiplier, false));
     }
     RC(map_update_pose_async(ctx, nullptr));
+    ef_stage(ctx, 5);
     if (!ctx->cfg.skip_mid_predict) RC(predict_async(ctx));  // ElasticFusion.cpp:387 (only loop closure reads it)
     if (!ctx->rgb_only) {
       // ElasticFusion.cpp:536-585
       RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta));
+      ef_stage(ctx, 6);
       RC(map_fuse_async(ctx, ctx->tick, ctx->max_depth_processed, -1.0f));
+      ef_stage(ctx, 7);
       RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta));
+      ef_stage(ctx, 8);
       RC(map_clean_async(ctx, ctx->tick, ctx->confidence, ctx->cfg.time_delta, ctx->max_depth_processed));
+      ef_stage(ctx, 9);
     }
   }
   RC(map_update_pose_async(ctx, nullptr));
   RC(predict_async(ctx));  // ElasticFusion.cpp:599
+  ef_stage(ctx, 10);
   ctx->tick++;
   return 0;
 }
 
-extern "C" int ef_process_frame(EfContext* ctx, const uint8_t* rgb, const uint16_t* depth, int64_t timestamp, float weight_multiplier,
-                                const double* in_T_wc) {
-  if (!ctx || !rgb || !depth) return EF_EINVAL;
-  const size_t n = (size_t)ctx->cfg.width * ctx->cfg.height;
-  // the staging buffers may still be in flight from the previous frame
-  CU(cudaStreamSynchronize(ctx->stream));
-  memcpy(ctx->pin_rgb, rgb, n * 3);
-  memcpy(ctx->pin_depth, depth, n * 2);
-  CU(cudaMemcpyAsync(ctx->tex.rgb, ctx->pin_rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->tex.depth_raw, ctx->pin_depth, n * 2, cudaMemcpyHostToDevice, ctx->stream));
-  RC(ef_process_frame_device(ctx, ctx->tex.rgb, ctx->tex.depth_raw, timestamp, weight_multiplier, in_T_wc));
-  // results the caller can observe (get_T_wc, counts) are final on return
+// Completes the frame enqueued by ef_process_frame_device: pose and surfel count are read back and final on return.
+extern "C" int ef_finish_frame(EfContext* ctx) {
+  if (!ctx) return EF_EINVAL;
   char* s = (char*)ctx->pin_small + 8192;
   CU(cudaMemcpyAsync(s, (char*)ctx->odom[0].gn + offsetof(GNState, T_wc), sizeof(double) * 16, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(s + 128, ctx->map.count, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -867,7 +1014,40 @@ extern "C" int ef_process_frame(EfContext* ctx, const uint8_t* rgb, const uint16
   return 0;
 }
 
+extern "C" int ef_process_frame(EfContext* ctx, const uint8_t* rgb, const uint16_t* depth, int64_t timestamp, float weight_multiplier,
+                                const double* in_T_wc) {
+  if (!ctx || ((rgb == nullptr) != (depth == nullptr))) return EF_EINVAL;
+  if (!rgb) {
+    RC(ef_process_frame_device(ctx, nullptr, nullptr, timestamp, weight_multiplier, in_T_wc));  // prefetched frame
+    return ef_finish_frame(ctx);
+  }
+  const size_t n = (size_t)ctx->cfg.width * ctx->cfg.height;
+  // the staging buffers may still be in flight from the previous frame
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(ctx->pin_rgb, rgb, n * 3);
+  memcpy(ctx->pin_depth, depth, n * 2);
+  CU(cudaMemcpyAsync(ctx->tex.rgb, ctx->pin_rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->tex.depth_raw, ctx->pin_depth, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+  RC(ef_process_frame_device(ctx, ctx->tex.rgb, ctx->tex.depth_raw, timestamp, weight_multiplier, in_T_wc));
+  // results the caller can observe (get_T_wc, counts) are final on return
+  return ef_finish_frame(ctx);
+}
+
 // debug exports (phase profiling builds)
+// EF_STAGE_TIMING=1: milliseconds between consecutive stage events of the last frame (0 start, 1 preprocess, 2 pyramids,
+// 3 so3, 4 gauss-newton, 5 finish, 6 index map, 7 fuse, 8 index map, 9 clean, 10 predict); returns the event count
+extern "C" int ef_debug_stage_ms(EfContext* ctx, float* out) {
+  if (!ctx || !ctx->stage_timing) return 0;
+  cudaStreamSynchronize(ctx->stream);
+  int prev = -1;
+  for (int i = 0; i < 16; ++i) {
+    out[i] = 0.f;
+    if (!(ctx->stage_n >> i & 1)) continue;
+    if (prev >= 0) cudaEventElapsedTime(&out[i], ctx->stage_ev[prev], ctx->stage_ev[i]);
+    prev = i;
+  }
+  return 11;
+}
 extern "C" void* ef_debug_gn(EfContext* ctx, int which) { return ctx ? (void*)ctx->odom[which].gn : nullptr; }
 extern "C" int ef_debug_gn_size() { return (int)sizeof(GNState); }
 extern "C" int ef_debug_dbg_offset() { return (int)offsetof(GNState, dbg); }

@@ -138,6 +138,26 @@ struct Textures {
   float* synth_depth;
 };
 
+// Look-ahead ("prefetch") of the next frame: everything of a frame that does not depend on the map or the pose -- upload,
+// RGBA expansion, bilateral filter + metric depth, depth pyramid + vertex/normal maps, intensity pyramid -- can run on a
+// side stream while the previous frame is still in its (latency-bound) Gauss-Newton loop. The products live in a spare
+// set of buffers that is swapped with the live pointers of Textures / OdomDev when the frame is consumed.
+struct Lookahead {
+  cudaStream_t stream;
+  cudaEvent_t ready;       // side stream: the spare set is complete
+  cudaEvent_t spare_free;  // main stream: every reader of the spare set precedes this point
+  cudaEvent_t h2d_done;    // side stream: the pinned staging buffers may be rewritten
+  bool pending;            // a prefetched frame is waiting to be consumed
+  uint8_t *rgb, *rgba;
+  uint16_t *depth_raw, *depth_filtered;
+  float *depth_metric, *depth_metric_filtered;
+  uint16_t* depth_tmp[NUM_PYRS];
+  float *vmap_curr[NUM_PYRS], *nmap_curr[NUM_PYRS];
+  uint8_t* image[NUM_PYRS];
+  uint8_t* pin_rgb;
+  uint16_t* pin_depth;
+};
+
 }  // namespace ef
 
 struct EfContext {
@@ -147,11 +167,15 @@ struct EfContext {
   cudaStream_t stream;
   bool own_stream;
   int64_t launches;
+  bool stage_timing;            // EF_STAGE_TIMING=1: record an event after every stage of ef_process_frame_device
+  cudaEvent_t stage_ev[16];
+  int stage_n;
   bool pdl;  // programmatic dependent launch on every kernel (default on; EF_NO_PDL=1 disables)
 
   ef::OdomDev odom[2];
   ef::MapDev map;
   ef::Textures tex;
+  ef::Lookahead la;
 
   // host mirrors
   int tick;
@@ -171,6 +195,13 @@ struct EfContext {
 };
 
 // launch bookkeeping
+inline void ef_stage(EfContext* ctx, int i) {
+  if (ctx->stage_timing) {
+    cudaEventRecord(ctx->stage_ev[i], ctx->stream);
+    if (i == 0) ctx->stage_n = 0;  // bit mask of the events recorded for this frame
+    ctx->stage_n |= 1 << i;
+  }
+}
 // Every kernel is launched with programmatic stream serialisation allowed (see pdl_enter() in ef_device.cuh); set
 // EF_NO_PDL=1 in the environment to fall back to plain stream-ordered launches (A/B measurements).
 template <typename... KArgs, typename... Args>

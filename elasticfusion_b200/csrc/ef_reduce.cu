@@ -941,6 +941,7 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
     const int nb = red_blocks(ctx, od.rows[2] * od.cols[2], 1, RED_THREADS, 2);
     for (int i = 0; i < 10; ++i) EF_LAUNCH(ctx, k_so3_step, nb, RED_THREADS, 0, od, i, 1);
   }
+  ef_stage(ctx, 3);
   int iterations[NUM_PYRS] = {fastOdom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0};
   // static schedule of (level, iter)
   int sched_level[32], sched_iter[32], ns = 0;
@@ -960,6 +961,7 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
     const int nb2 = iter2_blocks(npx, rgb, icp ? nb1 : 0);
     EF_LAUNCH(ctx, k_iter2, nb2, IT2_THREADS, 0, od, lv, sched_iter[s], next_lv, nb1, (rgb ? 1 | 8 : 0) | (icp ? 2 : 0) | 4, 0.f);
   }
+  ef_stage(ctx, 4);
   if (so3)
     for (int i = 0; i < NUM_PYRS; ++i) {  // RGBDOdometry.cpp:560-564: handle swap
       uint8_t* t = od.lastNextImage[i];

@@ -474,15 +474,16 @@ int odom_init_icp_model(EfContext* ctx, int which, const float* vtx4, const floa
 
 // populateRGBDData (RGBDOdometry.cpp:212-234); with_depth=0 is initFirstRGB (:246-257)
 int odom_populate(EfContext* ctx, int which, const uint8_t* rgba, float** destDepths, uint8_t** destImages, bool with_depth,
-                  const uint8_t* rgbaB = nullptr, const int* flag = nullptr, bool forceB = false) {
+                  const uint8_t* rgbaB = nullptr, const int* flag = nullptr, bool forceB = false, bool with_image = true) {
   OdomDev& od = ctx->odom[which];
   const size_t n = (size_t)od.width * od.height;
   EF_LAUNCH(ctx, k_depth_intensity_l0, flat_blocks(ctx, n), 256, 0, (const float4*)od.vmaps_tmp, (const uchar4*)rgba, (const uchar4*)rgbaB, flag,
-            forceB ? 1 : 0, n, od.maxDepthRGB, with_depth ? destDepths[0] : (float*)nullptr, destImages[0]);
+            forceB ? 1 : 0, n, od.maxDepthRGB, with_depth ? destDepths[0] : (float*)nullptr, with_image ? destImages[0] : (uint8_t*)nullptr);
   for (int i = 0; i + 1 < NUM_PYRS; ++i)
     EF_LAUNCH(ctx, k_pyr_down_depth_image, flat_blocks(ctx, (size_t)od.rows[i + 1] * od.cols[i + 1] * 2), 128, 0,
-              with_depth ? destDepths[i] : (const float*)nullptr, with_depth ? destDepths[i + 1] : (float*)nullptr, (const uint8_t*)destImages[i],
-              destImages[i + 1], od.rows[i], od.cols[i]);
+              with_depth ? destDepths[i] : (const float*)nullptr, with_depth ? destDepths[i + 1] : (float*)nullptr,
+              with_image ? (const uint8_t*)destImages[i] : (const uint8_t*)nullptr, with_image ? destImages[i + 1] : (uint8_t*)nullptr, od.rows[i],
+              od.cols[i]);
   EF_CHECK_LAST();
   return 0;
 }

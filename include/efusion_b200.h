@@ -75,6 +75,19 @@ int ef_process_frame(EfContext* ctx, const uint8_t* rgb, const uint16_t* depth, 
 int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, const uint16_t* depth_dev, int64_t timestamp,
                             float weight_multiplier, const double* in_T_wc);
 int ef_sync(EfContext* ctx);
+/* Frame look-ahead (no reference counterpart: the reference uploads and filters a frame inside processFrame, each GL
+ * pass followed by glFinish — Core/ElasticFusion.cpp:278-285). Everything of the NEXT frame that depends neither on the
+ * map nor on the pose (upload, RGBA expansion, bilateral filter + metric depth, depth pyramid + vertex/normal maps,
+ * intensity pyramid) is enqueued on a side stream into a spare buffer set, so it overlaps the Gauss-Newton loop and the
+ * map update of the frame in flight. One frame may be pending; it is consumed by passing rgb = depth = NULL to
+ * ef_process_frame / ef_process_frame_device (EF_ESTATE if none is pending, or if a frame is passed while one is).
+ * Results are identical to the non-prefetched call. Typical loop:
+ *   ef_prefetch_frame(f0); for (i...) { ef_process_frame_device(NULL, NULL, ts[i], ...); ef_prefetch_frame(f[i+1]);
+ *   ef_finish_frame(); }                                                                                          */
+int ef_prefetch_frame(EfContext* ctx, const uint8_t* rgb, const uint16_t* depth);                /* HOST buffers   */
+int ef_prefetch_frame_device(EfContext* ctx, const uint8_t* rgb_dev, const uint16_t* depth_dev); /* DEVICE buffers */
+/* waits for the frame enqueued by ef_process_frame_device and refreshes the host mirrors (pose, surfel count) */
+int ef_finish_frame(EfContext* ctx);
 /* ElasticFusion::predict (Core/ElasticFusion.cpp:621-653) */
 int ef_predict(EfContext* ctx);
 

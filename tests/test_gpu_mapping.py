@@ -215,3 +215,59 @@ def test_sequence_ate_vs_oracle(K):
         assert np.abs(est_p[-1][:3, :3] - est_o[-1][:3, :3]).max() < 1e-3
     finally:
         ctx.close()
+
+
+def test_lookahead_matches_plain_calls(frames, K):
+    """ef_prefetch_frame (host and device variants): staging the next frame on the side stream while the current one is in
+    flight must not change anything -- poses, surfel counts and the final map are bit-identical to the plain per-frame calls.
+    Also the state machine: consuming without a pending frame, or passing a frame while one is pending, is EF_ESTATE."""
+    import torch
+    from elasticfusion_b200 import capi
+
+    def run(mode):
+        ctx = make_ctx(K)
+        poses, counts = [], []
+        try:
+            if mode == "plain":
+                for i, (rgb, depth, _) in enumerate(frames):
+                    ctx.process_frame(rgb, depth, i)
+                    poses.append(ctx.get_pose())
+                    counts.append(ctx.map_count())
+            elif mode == "host":
+                with pytest.raises(capi.EfError):
+                    ctx.process_frame(None, None, 0)  # nothing staged yet
+                ctx.prefetch_frame(frames[0][0], frames[0][1])
+                with pytest.raises(capi.EfError):
+                    ctx.prefetch_frame(frames[0][0], frames[0][1])  # one pending frame at most
+                with pytest.raises(capi.EfError):
+                    ctx.process_frame(frames[0][0], frames[0][1], 0)  # the staged frame has to be consumed first
+                for i in range(len(frames)):
+                    ctx.process_frame_device(None, None, i)
+                    if i + 1 < len(frames):
+                        ctx.prefetch_frame(frames[i + 1][0], frames[i + 1][1])
+                    ctx.finish_frame()
+                    poses.append(ctx.get_pose())
+                    counts.append(ctx.map_count())
+            else:
+                dev = [(torch.from_numpy(np.ascontiguousarray(r)).cuda(), torch.from_numpy(np.ascontiguousarray(d).view(np.int16)).cuda())
+                       for r, d, _ in frames]
+                torch.cuda.synchronize()
+                ctx.prefetch_frame_device(dev[0][0].data_ptr(), dev[0][1].data_ptr())
+                for i in range(len(frames)):
+                    ctx.process_frame_device(None, None, i)
+                    if i + 1 < len(frames):
+                        ctx.prefetch_frame_device(dev[i + 1][0].data_ptr(), dev[i + 1][1].data_ptr())
+                ctx.finish_frame()
+                poses.append(ctx.get_pose())
+                counts.append(ctx.map_count())
+            return np.array(poses), counts, ctx.map_download()
+        finally:
+            ctx.close()
+
+    p0, c0, m0 = run("plain")
+    p1, c1, m1 = run("host")
+    p2, c2, m2 = run("device")
+    assert np.array_equal(p0, p1) and c0 == c1
+    assert np.array_equal(m0, m1, equal_nan=True)
+    assert np.array_equal(p0[-1], p2[-1]) and c0[-1] == c2[-1]
+    assert np.array_equal(m0, m2, equal_nan=True)
