@@ -14,5 +14,6 @@ for f in ef_api ef_track ef_map ef_preprocess; do
 done
 $NVCC $COMMON --fmad=true -c $D/ef_reduce.cu -o $B/ef_reduce.o "$@" &
 wait
-$NVCC -shared -o elasticfusion_b200/libefusion.so $B/ef_api.o $B/ef_track.o $B/ef_map.o $B/ef_preprocess.o $B/ef_reduce.o -lcudart
-echo "built elasticfusion_b200/libefusion.so"
+OUT=${EF_OUT:-elasticfusion_b200/libefusion.so}
+$NVCC -shared -o $OUT $B/ef_api.o $B/ef_track.o $B/ef_map.o $B/ef_preprocess.o $B/ef_reduce.o -lcudart
+echo "built $OUT"

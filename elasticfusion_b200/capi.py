@@ -69,9 +69,10 @@ def lib():
     """Loads libefusion.so; raises if the CUDA extension has not been built (no fallback path exists)."""
     global _LIB
     if _LIB is None:
-        if not os.path.exists(LIB_PATH):
-            raise EfError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` or ./build.sh")
-        _LIB = C.CDLL(LIB_PATH)
+        path = os.environ.get("EF_LIB", LIB_PATH)  # EF_LIB: an instrumented build of the same library (scripts/phase_profile.py)
+        if not os.path.exists(path):
+            raise EfError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` or ./build.sh")
+        _LIB = C.CDLL(path)
         _LIB.ef_error_string.restype = C.c_char_p
         _LIB.ef_stream.restype = C.c_void_p
     return _LIB

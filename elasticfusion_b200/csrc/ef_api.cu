@@ -30,6 +30,7 @@ int launch_rgb_residual_raw(EfContext* ctx, int which, int level);
 int launch_icp_dense_only(EfContext* ctx, int which, int level);
 int launch_so3_raw(EfContext* ctx, int which);
 int launch_sobel(EfContext* ctx, int which);
+int odom_cluster_init(EfContext* ctx);
 int preprocess_depth(EfContext* ctx, const uint16_t* raw, float cutoff, uint16_t* filtered, float* metric, float* metric_filtered);
 int rgb_to_rgba(EfContext* ctx, const uint8_t* rgb, uint8_t* rgba);
 
@@ -269,6 +270,7 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
   {
     const char* e = getenv("EF_NO_PDL");
     ctx->pdl = !(e && e[0] == '1');
+    odom_cluster_init(ctx);
     e = getenv("EF_STAGE_TIMING");
     ctx->stage_timing = (e && e[0] == '1');
     ctx->stage_n = 0;

@@ -110,14 +110,16 @@ __device__ __forceinline__ void pdl_enter() {
 // "last block done" ticket: returns true in every thread of the block that arrives last.
 __device__ __forceinline__ bool last_block_done(unsigned int* counter) {
   __shared__ bool is_last;
-  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
+    // one gpu-scope fence by the thread that takes the ticket: it is cumulative over the CTA's writes ordered before it by
+    // the barrier above (release), and again before the CTA reads the other CTAs' results (acquire)
+    __threadfence();
     unsigned int t = atomicAdd(counter, 1u);
     is_last = (t == gridDim.x - 1);
+    if (is_last) __threadfence();
   }
   __syncthreads();
-  if (is_last) __threadfence();
   return is_last;
 }
 

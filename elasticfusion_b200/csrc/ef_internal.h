@@ -170,6 +170,7 @@ struct EfContext {
   bool stage_timing;            // EF_STAGE_TIMING=1: record an event after every stage of ef_process_frame_device
   cudaEvent_t stage_ev[16];
   int stage_n;
+  int cluster_size;    // CTAs of the coarse-level tracking cluster (16, 8 or 0 = off; EF_NO_CLUSTER=1 forces 0)
   bool pdl;  // programmatic dependent launch on every kernel (default on; EF_NO_PDL=1 disables)
 
   ef::OdomDev odom[2];

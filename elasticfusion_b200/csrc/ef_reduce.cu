@@ -11,13 +11,21 @@
 #include <stdio.h>
 
 #include "ef_device.cuh"
+#include <stdlib.h>
+#include <string.h>
+
 #include "ef_dmath.cuh"
 #include "ef_internal.h"
 
 using namespace ef;
 
 #ifdef EF_PROFILE_PHASES
-#define EF_STAMP(gn, slot, cond) do { if (cond) (gn)->dbg[slot] = clock64(); } while (0)
+__device__ __forceinline__ long long ef_gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define EF_STAMP(gn, slot, cond) do { if (cond) (gn)->dbg[slot] = ef_gtime(); } while (0)
 #else
 #define EF_STAMP(gn, slot, cond) do { } while (0)
 #endif
@@ -78,9 +86,7 @@ __device__ void so3_prepare(GNState* gn) {
 }
 
 // start of getIncrementalTransformation (RGBDOdometry.cpp:266-273,284-303)
-__global__ void k_gn_begin(GNState* gn, int rgbOnly, float icpWeight, int so3) {
-  pdl_enter();
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void gn_begin_body(GNState* gn, int rgbOnly, float icpWeight, int so3) {
   gn->rgbOnly = rgbOnly;
   gn->icpWeight = icpWeight;
   gn->icp = (!rgbOnly && icpWeight > 0) ? 1 : 0;
@@ -106,11 +112,14 @@ __global__ void k_gn_begin(GNState* gn, int rgbOnly, float icpWeight, int so3) {
   gn->trace_n = 0;
   if (so3) so3_prepare(gn);
 }
-
-// after the SO3 loop: seed resultRt (RGBDOdometry.cpp:379-388) and prepare the first SE3 iteration
-__global__ void k_gn_seed(GNState* gn, int first_level) {
+__global__ void k_gn_begin(GNState* gn, int rgbOnly, float icpWeight, int so3) {
   pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  gn_begin_body(gn, rgbOnly, icpWeight, so3);
+}
+
+// after the SO3 loop: seed resultRt (RGBDOdometry.cpp:379-388) and prepare the first SE3 iteration
+__device__ void gn_seed_body(GNState* gn, int first_level) {
   for (int k = 0; k < 16; ++k) gn->resultRt[k] = (k % 5 == 0) ? 1.0 : 0.0;
   if (gn->so3)
     for (int x = 0; x < 3; x++)
@@ -124,6 +133,11 @@ __global__ void k_gn_seed(GNState* gn, int first_level) {
     gn->lastRGBCount = 0.f;
   }
   gn_prepare_warp(gn, first_level);
+}
+__global__ void k_gn_seed(GNState* gn, int first_level) {
+  pdl_enter();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  gn_seed_body(gn, first_level);
 }
 
 // end of getIncrementalTransformation (RGBDOdometry.cpp:555-570) + velocity weighting (ElasticFusion.cpp:369-383)
@@ -191,7 +205,7 @@ __device__ __forceinline__ void unpack_se3(const float* h, float* A, float* b) {
 
 // Shared-memory scratch of the update kernel
 struct GnScratch {
-  double dsm[8][64];   // per-slice partial sums (IT2_THREADS/32 slices x 64 values)
+  double dsm[20][64];  // per-slice partial sums (threads/32 slices x 64 values)
   float sums[64];      // reduced systems: [0,29) geometric, [32,61) photometric
   float A_icp[36], b_icp[8], A_rgb[36], b_rgb[8];
   double lastA[36], lastb[8], result[8];
@@ -220,7 +234,7 @@ __device__ __forceinline__ void se3_unpack_index(int k, int& i, int& j) {
 // One SE3 Gauss-Newton update (RGBDOdometry.cpp:492-551) executed cooperatively by one warp: the independent pieces
 // (unpacking, lastA/lastb, 4x4 and 3x3 products, trace) are spread over the lanes; only the 6x6 LDL^T and the Rodrigues
 // formula run on lane 0. All operands live in shared memory.
-__device__ void gn_update_warp(const OdomDev& od, GnScratch& S, int level, int iter, int next_level) {
+__device__ __noinline__ void gn_update_warp(const OdomDev& od, GnScratch& S, int level, int iter, int next_level) {
   GNState* gn = od.gn;
   const int lane = threadIdx.x;
   // (resultRt, Rprev, tprev were staged into S at the top of k_iter2, long before this CTA took the last ticket)
@@ -422,18 +436,20 @@ __device__ __forceinline__ void icp_accumulate(const IcpFrame& F, const f3& vcur
 //      reduce.cu:661-697; the pose-independent gates were applied when the list was built): writes one compact term per
 //      candidate and the CTA's {count, sum int(diff^2)};
 //  (b) the dense geometric rows (ICPReduction, reduce.cu:224-331) reduced to one 29-float partial per CTA.
-__global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev od, int level, int do_res, int do_icp, int solve) {
-  pdl_enter();
+// vb / nvb: index and number of the (virtual) CTAs sharing the pass -- the launch grid for the stand-alone kernel, the
+// persistent grid for k_gn_loop. sred: 32 * THREADS/32 floats of shared memory.
+template <int THREADS>
+__device__ __forceinline__ void iter1_body(const OdomDev& od, int level, int do_res, int do_icp, int vb, int nvb, float* sred) {
   GNState* gn = od.gn;
-  if (solve && gn->break_level == level) return;  // rgbOnly `break`: rest of the level is skipped
-  __shared__ float sred[32 * (IT1_THREADS / 32)];
   const int rows = od.rows[level], cols = od.cols[level];
   const int N = rows * cols;
   const size_t plane = (size_t)N;
-  const int gid = blockIdx.x * IT1_THREADS + threadIdx.x, gstride = gridDim.x * IT1_THREADS;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // work items are dealt to warps round-robin ACROSS the CTAs (warp w of CTA b is global warp w * nvb + b), so a pass
+  // smaller than the grid still occupies every SM evenly
+  const int gid = (wid * nvb + vb) * 32 + lane, gstride = nvb * THREADS;
 
-  const bool stamp = (blockIdx.x == 0 && threadIdx.x == 0 && level == 0);
+  const bool stamp = (vb == 0 && threadIdx.x == 0 && level == 0);
   EF_STAMP(gn, 0, stamp);
   unsigned int cnt = 0, sig = 0;
   const bool vec = (cols & 3) == 0;
@@ -444,7 +460,7 @@ __global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev 
     const float* __restrict__ lastDepth = od.lastDepth[level];
     const uint8_t* __restrict__ lastImage = od.lastImage[level];
     const int4* __restrict__ cand = od.cand + base;
-    int4* __restrict__ terms = od.terms + base;
+    int4* terms = od.terms + base;
     for (int c = gid; c < ncand; c += gstride) {
       const int4 cr = cand[c];
       const int k = cr.x;
@@ -530,13 +546,37 @@ __global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev 
       }
     }
     EF_STAMP(gn, 2, stamp);
-    block_reduce_sum<29, IT1_THREADS>(acc, sred);
+    if (do_res) {
+      // warp totals of the two ints parked behind the float partials; the barrier inside block_reduce_sum publishes them
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+        sig += __shfl_down_sync(0xffffffffu, sig, off);
+      }
+    }
+    __shared__ unsigned int s_stat[2 * 32];
+    if (do_res && lane == 0) {
+      s_stat[wid] = cnt;
+      s_stat[32 + wid] = sig;
+    }
+    block_reduce_sum<29, THREADS>(acc, sred);
     EF_STAMP(gn, 3, stamp);
-    if (threadIdx.x < 29) od.partials[(size_t)blockIdx.x * PARTIAL_STRIDE + threadIdx.x] = acc[0];
-  }
-  if (do_res) {
-    // CTA sum of the two ints, then one integer atomic per CTA (wrapping adds like the reference's int2 sums; integer
-    // addition is order independent, so the totals stay deterministic)
+    if (threadIdx.x < 29) od.partials[(size_t)vb * PARTIAL_STRIDE + threadIdx.x] = acc[0];
+    if (do_res && threadIdx.x == 32) {
+      // one integer atomic pair per CTA (wrapping adds like the reference's int2 sums; integer addition is order
+      // independent, so the totals stay deterministic)
+      unsigned int c = 0, g = 0;
+#pragma unroll
+      for (int w = 0; w < THREADS / 32; ++w) {
+        c += s_stat[w];
+        g += s_stat[32 + w];
+      }
+      if (c | g) {
+        atomicAdd(&gn->res_acc[0], c);
+        atomicAdd(&gn->res_acc[1], g);
+      }
+    }
+  } else if (do_res) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       cnt += __shfl_down_sync(0xffffffffu, cnt, off);
@@ -547,6 +587,13 @@ __global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev 
       atomicAdd(&gn->res_acc[1], sig);
     }
   }
+}
+
+__global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev od, int level, int do_res, int do_icp, int solve) {
+  pdl_enter();
+  if (solve && od.gn->break_level == level) return;  // rgbOnly `break`: rest of the level is skipped
+  __shared__ float sred[32 * (IT1_THREADS / 32)];
+  iter1_body<IT1_THREADS>(od, level, do_res, do_icp, blockIdx.x, gridDim.x, sred);
 }
 
 // ---- photometric row: RGBReduction::getProducts (reduce.cu:419-480); the cloud point is recomputed from the gathered
@@ -584,30 +631,32 @@ __device__ __forceinline__ void rgb_accumulate(const int4& term, float sigma, fl
 // photometric rows over the candidate terms are reduced; the CTA that takes the last ticket sums all partials in double
 // and its first warp solves and updates the pose. mode bits: 1 = rgb rows, 2 = icp partials present, 4 = solve,
 // 8 = correspondence statistics present, 16 = use sigma_override.
-__global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, int iter, int next_level, int nblocks1, int mode, float sigma_override) {
-  pdl_enter();
-  __shared__ GnScratch S;
-  __shared__ float sred[32 * (IT2_THREADS / 32)];
-  __shared__ float s_sigma;
-  __shared__ int s_break;
+struct Iter2Shared {
+  GnScratch S;
+  float sred[32 * 20];  // up to 640 threads
+  float sigma;
+  int brk;
+};
+
+// Everything of the second phase up to the ticket: correspondence statistics (every CTA, redundantly), this CTA's share of
+// the dense-pass partials and the photometric rows over its candidates. Returns the rgbOnly `break` decision.
+template <int THREADS>
+__device__ __forceinline__ bool iter2_rows(const OdomDev& od, Iter2Shared& sh, int level, int iter, int next_level, int nblocks1, int mode,
+                                           float sigma_override, int vb, int nvb) {
+  GnScratch& S = sh.S;
   GNState* gn = od.gn;
   const bool do_rgb = mode & 1, do_icp = mode & 2, solve = mode & 4, have_res = mode & 8;
-  if (solve && gn->break_level == level) {
-    // rgbOnly `break`: the first iteration of the next level still needs its warp matrices
-    if (blockIdx.x == 0 && threadIdx.x == 0 && next_level >= 0 && next_level != level) gn_prepare_warp(gn, next_level);
-    return;
-  }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool stamp = (threadIdx.x == 0 && level == 0);
-  EF_STAMP(gn, 8, stamp && blockIdx.x == 0);
+  EF_STAMP(gn, 8, stamp && vb == 0);
 
   // issue the loads that do not depend on sigma first: this CTA's candidate terms and its share of the dense partials
   const int base = gn->cand_base[level], ncand = do_rgb ? gn->cand_base[level + 1] - base : 0;
-  const int4* __restrict__ terms = od.terms + base;
-  const int c0 = blockIdx.x * IT2_THREADS + threadIdx.x, cstride = gridDim.x * IT2_THREADS;
+  const int4* terms = od.terms + base;  // (not __restrict__: k_gn_loop writes them in its first phase)
+  const int c0 = (wid * nvb + vb) * 32 + lane, cstride = nvb * THREADS;
   int4 t0 = make_int4(-1, 0, 0, 0);
   if (c0 < ncand) t0 = terms[c0];
-  if (solve && wid == 1) {  // state of the solve: not written by anything in this launch before the last CTA's update
+  if (solve && wid == 1) {  // state of the solve: not written by anything in this phase before the last CTA's update
     if (lane < 16) S.rRt[lane] = gn->resultRt[lane];
     if (lane < 9) S.Rprev[lane] = gn->Rprev[lane];
     if (lane < 3) S.tprev[lane] = gn->tprev[lane];
@@ -619,8 +668,8 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
   }
   double presum = 0;
   if (do_icp && threadIdx.x < 32) {
-    const int per = (nblocks1 + gridDim.x - 1) / gridDim.x;
-    const int b0 = blockIdx.x * per, b1 = min(b0 + per, nblocks1);
+    const int per = (nblocks1 + nvb - 1) / nvb;
+    const int b0 = vb * per, b1 = min(b0 + per, nblocks1);
     for (int bb = b0; bb < b1; bb += 8) {  // 8 independent loads in flight
       float x[8];
 #pragma unroll
@@ -631,7 +680,7 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
   }
 
   if (threadIdx.x == 0) {
-    s_break = 0;
+    sh.brk = 0;
     float sig_val = (mode & 16) ? sigma_override : gn->sigmaVal;
     if (have_res) {
       const int rgbSize = (int)gn->res_acc[0], sigma = (int)gn->res_acc[1];
@@ -642,8 +691,8 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
       const bool brk = solve && gn->rgbOnly && rgbError > prevError;
       if (gn->rgbOnly) sigmaVal = -1;
       if (!(mode & 16)) sig_val = sigmaVal;
-      s_break = brk ? 1 : 0;
-      if (blockIdx.x == 0) {
+      sh.brk = brk ? 1 : 0;
+      if (vb == 0) {
         gn->sum_res[0] = rgbSize;
         gn->sum_res[1] = sigma;
         if (solve) {
@@ -661,16 +710,16 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
         }
       }
     }
-    s_sigma = sig_val;
+    sh.sigma = sig_val;
   }
   __syncthreads();
-  EF_STAMP(gn, 9, stamp && blockIdx.x == 0);
-  const bool brk = s_break != 0;
+  EF_STAMP(gn, 9, stamp && vb == 0);
+  const bool brk = sh.brk != 0;
 
   if (!brk) {
-    if (do_icp && threadIdx.x < 32) od.partials2[blockIdx.x * 32 + threadIdx.x] = presum;
+    if (do_icp && threadIdx.x < 32) od.partials2[vb * 32 + threadIdx.x] = presum;
     if (do_rgb) {
-      const float sigma = s_sigma;
+      const float sigma = sh.sigma;
       float lfx, lfy, lcx, lcy;
       level_intr(gn, level, lfx, lfy, lcx, lcy);
       float acc[29];
@@ -681,13 +730,23 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
         const int4 t = terms[c];
         if (t.x != -1) rgb_accumulate(t, sigma, lfx, lfy, lcx, lcy, od.sobelScale, acc);
       }
-      block_reduce_sum<29, IT2_THREADS>(acc, sred);
-      if (threadIdx.x < 29) od.partials_rgb[blockIdx.x * 32 + threadIdx.x] = acc[0];
+      block_reduce_sum<29, THREADS>(acc, sh.sred);
+      if (threadIdx.x < 29) od.partials_rgb[vb * 32 + threadIdx.x] = acc[0];
     }
   }
-  EF_STAMP(gn, 10, stamp && blockIdx.x == 0);
-  // every CTA takes a ticket (also on `break`, so the accumulators of k_iter1 get re-armed exactly once)
-  if (!last_block_done(od.counter)) return;
+  EF_STAMP(gn, 10, stamp && vb == 0);
+  return brk;
+}
+
+// The CTA that took the last ticket: re-arm the accumulators, sum all partials in double (fixed order: THREADS/32 slices
+// x 32 values) and let its first warp solve and update the pose.
+template <int THREADS>
+__device__ __forceinline__ void iter2_final(const OdomDev& od, Iter2Shared& sh, int level, int iter, int next_level, int mode, int nvb, bool brk) {
+  GnScratch& S = sh.S;
+  GNState* gn = od.gn;
+  const bool do_rgb = mode & 1, do_icp = mode & 2, solve = mode & 4;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool stamp = (threadIdx.x == 0 && level == 0);
   EF_STAMP(gn, 11, stamp);
   if (threadIdx.x == 0) {
     *od.counter = 0;
@@ -695,19 +754,17 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
     gn->res_acc[1] = 0u;
   }
   if (brk) return;
-
-  // final sums in double, fixed order: IT2_THREADS/32 warps x 32 values
   {
     const int v = lane, sl = wid;
     double a0 = 0, a1 = 0;
-    constexpr int SL = IT2_THREADS / 32;
-    for (int bb = sl; bb < (int)gridDim.x; bb += 8 * SL) {  // 16 independent loads in flight per thread
+    constexpr int SL = THREADS / 32;
+    for (int bb = sl; bb < nvb; bb += 8 * SL) {  // 16 independent loads in flight per thread
       double x[8];
       float y[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int b = bb + k * SL;
-        const bool in = b < (int)gridDim.x;
+        const bool in = b < nvb;
         x[k] = (in && do_icp) ? od.partials2[b * 32 + v] : 0.0;
         y[k] = (in && do_rgb) ? od.partials_rgb[b * 32 + v] : 0.f;
       }
@@ -724,7 +781,7 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
   if (threadIdx.x < 64) {
     double t = 0;
 #pragma unroll
-    for (int k = 0; k < IT2_THREADS / 32; ++k) t += S.dsm[k][threadIdx.x];
+    for (int k = 0; k < THREADS / 32; ++k) t += S.dsm[k][threadIdx.x];
     const float f = (float)t;
     S.sums[threadIdx.x] = f;
     if (threadIdx.x < 32)
@@ -738,6 +795,27 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
   gn_update_warp(od, S, level, iter, next_level);
   EF_STAMP(gn, 16, stamp);
 }
+
+// Second launch of a Gauss-Newton iteration: every CTA first finishes the correspondence statistics of k_iter1 (sigma,
+// rgbError and the rgbOnly break decision, RGBDOdometry.cpp:442-455 incl. the operator-precedence quirk), then the
+// photometric rows over the candidate terms are reduced; the CTA that takes the last ticket sums all partials in double
+// and its first warp solves and updates the pose. mode bits: 1 = rgb rows, 2 = icp partials present, 4 = solve,
+// 8 = correspondence statistics present, 16 = use sigma_override.
+__global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, int iter, int next_level, int nblocks1, int mode, float sigma_override) {
+  pdl_enter();
+  __shared__ Iter2Shared sh;
+  GNState* gn = od.gn;
+  if ((mode & 4) && gn->break_level == level) {
+    // rgbOnly `break`: the first iteration of the next level still needs its warp matrices
+    if (blockIdx.x == 0 && threadIdx.x == 0 && next_level >= 0 && next_level != level) gn_prepare_warp(gn, next_level);
+    return;
+  }
+  const bool brk = iter2_rows<IT2_THREADS>(od, sh, level, iter, next_level, nblocks1, mode, sigma_override, blockIdx.x, gridDim.x);
+  // every CTA takes a ticket (also on `break`, so the accumulators of k_iter1 get re-armed exactly once)
+  if (!last_block_done(od.counter)) return;
+  iter2_final<IT2_THREADS>(od, sh, level, iter, next_level, mode, gridDim.x, brk);
+}
+
 
 // expands the compact per-candidate terms into the reference's dense DataTerm image (inspection / stage API only)
 __global__ void k_terms_expand(OdomDev od, int level) {
@@ -760,17 +838,18 @@ __global__ void k_terms_expand(OdomDev od, int level) {
   }
 }
 
+template <int THREADS>
 __device__ __forceinline__ void so3_final_sum(const float* partials, int nblocks, float* dst, double* dsm) {
   const int v = threadIdx.x & 31, s = threadIdx.x >> 5;
   double acc = 0;
   if (v < 11)
-    for (int b = s; b < nblocks; b += RED_THREADS / 32) acc += (double)partials[(size_t)b * PARTIAL_STRIDE + v];
+    for (int b = s; b < nblocks; b += THREADS / 32) acc += (double)partials[(size_t)b * PARTIAL_STRIDE + v];
   dsm[s * 32 + v] = acc;
   __syncthreads();
   if (s == 0 && v < 11) {
     double t = 0;
 #pragma unroll
-    for (int k = 0; k < RED_THREADS / 32; ++k) t += dsm[k * 32 + v];
+    for (int k = 0; k < THREADS / 32; ++k) t += dsm[k * 32 + v];
     dst[v] = (float)t;
   }
   __syncthreads();
@@ -787,12 +866,10 @@ __device__ __forceinline__ void so3_gradient(const uint8_t* img, int cols, int x
   gy = ((back + actu) / 2.0f) - ((fore + actu) / 2.0f);
 }
 
-__global__ void __launch_bounds__(RED_THREADS) k_so3_step(OdomDev od, int iter, int solve) {
-  pdl_enter();
+// per-CTA partial of one SO3 step (11 floats into od.partials[vb])
+template <int THREADS>
+__device__ __forceinline__ void so3_partial(const OdomDev& od, int vb, int nvb, float* sred) {
   GNState* gn = od.gn;
-  if (solve && gn->so3_done) return;
-  __shared__ float sred[32 * (RED_THREADS / 32)];
-  __shared__ double dsm[(RED_THREADS / 32) * 32];
   const int level = 2;
   const int rows = od.rows[level], cols = od.cols[level];
   const int N = rows * cols;
@@ -802,7 +879,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_so3_step(OdomDev od, int iter, 
   float acc[11];
 #pragma unroll
   for (int k = 0; k < 11; ++k) acc[k] = 0.f;
-  for (int k = blockIdx.x * RED_THREADS + threadIdx.x; k < N; k += gridDim.x * RED_THREADS) {
+  for (int k = vb * THREADS + threadIdx.x; k < N; k += nvb * THREADS) {
     const int y = k / cols, x = k - y * cols;
     const f3 unwarped = mk3((float)x, (float)y, 1.0f);
     const f3 warped = mul(imageBasis, unwarped);
@@ -837,14 +914,13 @@ __global__ void __launch_bounds__(RED_THREADS) k_so3_step(OdomDev od, int iter, 
       acc[10] += 1.0f;
     }
   }
-  block_reduce_sum<11, RED_THREADS>(acc, sred);
-  if (threadIdx.x < 11) od.partials[(size_t)blockIdx.x * PARTIAL_STRIDE + threadIdx.x] = acc[0];
-  if (!last_block_done(od.counter)) return;
-  so3_final_sum(od.partials, gridDim.x, gn->sum_so3, dsm);
-  if (threadIdx.x != 0) return;
-  *od.counter = 0;
-  if (!solve) return;
+  block_reduce_sum<11, THREADS>(acc, sred);
+  if (threadIdx.x < 11) od.partials[(size_t)vb * PARTIAL_STRIDE + threadIdx.x] = acc[0];
+}
 
+// solve + convergence logic of one SO3 step on the reduced system in gn->sum_so3 (one thread)
+__device__ void so3_finish(const OdomDev& od, int iter) {
+  GNState* gn = od.gn;
   float jtj[9], jtr[3];
   {
     int shift = 0;
@@ -899,6 +975,100 @@ __global__ void __launch_bounds__(RED_THREADS) k_so3_step(OdomDev od, int iter, 
   so3_prepare(gn);
 }
 
+__global__ void __launch_bounds__(RED_THREADS) k_so3_step(OdomDev od, int iter, int solve) {
+  pdl_enter();
+  GNState* gn = od.gn;
+  if (solve && gn->so3_done) return;
+  __shared__ float sred[32 * (RED_THREADS / 32)];
+  __shared__ double dsm[(RED_THREADS / 32) * 32];
+  so3_partial<RED_THREADS>(od, blockIdx.x, gridDim.x, sred);
+  if (!last_block_done(od.counter)) return;
+  so3_final_sum<RED_THREADS>(od.partials, gridDim.x, gn->sum_so3, dsm);
+  if (threadIdx.x != 0) return;
+  *od.counter = 0;
+  if (!solve) return;
+  so3_finish(od, iter);
+}
+
+// ---- coarse levels in one thread-block cluster --------------------------------------------------------------------
+// At the coarse pyramid levels (160x120 and 320x240 of a 640x480 frame) an iteration is a chain of latencies, not work:
+// two dependent launches and a last-CTA ticket cost ~17 us for ~2 us of arithmetic. k_track_cluster runs the start of
+// getIncrementalTransformation (RGBDOdometry.cpp:266-303), the whole SO(3) pre-alignment loop (:305-368), the seeding of
+// the SE(3) estimate (:379-388) and every Gauss-Newton iteration of the levels >= 1 in ONE launch of a single cluster:
+// the CTAs of the cluster split the pixels, hardware cluster barriers (barrier.cluster, release/acquire) replace the kernel
+// boundaries and the ticket, and rank 0 does the final sums and the solve. The arithmetic inside a CTA is that of
+// k_so3_step / k_iter1 / k_iter2 (same device functions); only the pixel-to-CTA partition differs. Level 0 keeps the
+// two-launch form: there the dense pass is real work for all 148 SMs.
+struct GnSchedule {
+  int n;
+  signed char level[32], iter[32];
+};
+constexpr int CL_THREADS = 640;  // 20 warps, one CTA per SM
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned int cluster_rank() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned int cluster_size() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+
+__global__ void __launch_bounds__(CL_THREADS, 1) k_track_cluster(OdomDev od, GnSchedule sch, int rgbOnly, float icpWeight, int so3, int do_rgb,
+                                                                 int do_icp) {
+  pdl_enter();
+  __shared__ Iter2Shared sh;
+  __shared__ double so3_dsm[(CL_THREADS / 32) * 32];
+  GNState* gn = od.gn;
+  const int vb = (int)cluster_rank(), nvb = (int)cluster_size();
+  const bool leader = (vb == 0);
+
+  if (leader && threadIdx.x == 0) gn_begin_body(gn, rgbOnly, icpWeight, so3);
+  cluster_sync_all();
+  if (so3) {
+    for (int i = 0; i < 10; ++i) {
+      if (gn->so3_done) break;  // uniform: written by the leader before the previous barrier
+      so3_partial<CL_THREADS>(od, vb, nvb, sh.sred);
+      cluster_sync_all();
+      if (leader) {
+        so3_final_sum<CL_THREADS>(od.partials, nvb, gn->sum_so3, so3_dsm);
+        if (threadIdx.x == 0) so3_finish(od, i);
+      }
+      cluster_sync_all();
+    }
+  }
+  if (leader && threadIdx.x == 0) gn_seed_body(gn, sch.n ? sch.level[0] : 0);
+  cluster_sync_all();
+
+  const int mode = (do_rgb ? 1 | 8 : 0) | (do_icp ? 2 : 0) | 4;
+  int break_level = -1;
+  for (int s = 0; s < sch.n; ++s) {
+    const int lv = sch.level[s], it = sch.iter[s];
+    const int next_lv = sch.level[s + 1];  // the host appends the level that follows the last cluster iteration (or -1)
+    if (break_level == lv) {
+      // rgbOnly `break`: the rest of the level is skipped; its last slot prepares the next level's warp matrices
+      if (next_lv >= 0 && next_lv != lv) {
+        if (leader && threadIdx.x == 0) gn_prepare_warp(gn, next_lv);
+        cluster_sync_all();
+      }
+      continue;
+    }
+    iter1_body<CL_THREADS>(od, lv, do_rgb, do_icp, vb, nvb, sh.sred);
+    cluster_sync_all();
+    const bool brk = iter2_rows<CL_THREADS>(od, sh, lv, it, next_lv, do_icp ? nvb : 0, mode, 0.f, vb, nvb);
+    cluster_sync_all();
+    if (leader) iter2_final<CL_THREADS>(od, sh, lv, it, next_lv, mode, nvb, brk);
+    cluster_sync_all();
+    if (brk) break_level = lv;
+  }
+}
+
+
 namespace {
 
 inline int red_blocks(const EfContext* ctx, int n_items, int per_thread, int threads, int ctas_per_sm) {
@@ -928,6 +1098,35 @@ inline int iter2_blocks(int npx, bool rgb, int nb1) {
 namespace ef {
 
 // the device-resident Gauss-Newton schedule; T_wc in/out lives in gn->T_wc
+// Picks the cluster size of k_track_cluster: 16 CTAs (non-portable size, opt-in) when the device can co-schedule them,
+// else 8, else 0 = every iteration as two launches. EF_NO_CLUSTER=1 forces 0 (A/B measurements).
+int odom_cluster_init(EfContext* ctx) {
+  ctx->cluster_size = 0;
+  const char* e = getenv("EF_NO_CLUSTER");
+  if (e && e[0] == '1') return 0;
+  cudaFuncSetAttribute(k_track_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  const int tries[2] = {16, 8};
+  for (int k = 0; k < 2; ++k) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tries[k]);
+    cfg.blockDim = dim3(CL_THREADS);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = tries[k];
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_track_cluster, &cfg) == cudaSuccess && n >= 1) {
+      ctx->cluster_size = tries[k];
+      break;
+    }
+  }
+  (void)cudaGetLastError();
+  return 0;
+}
+
 int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom, bool so3) {
   OdomDev& od = ctx->odom[which];
   const bool icp = !rgbOnly && icpWeight > 0;
@@ -936,12 +1135,6 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
     int rc = launch_sobel(ctx, which);
     if (rc) return rc;
   }
-  EF_LAUNCH(ctx, k_gn_begin, 1, 32, 0, od.gn, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0);
-  if (so3) {
-    const int nb = red_blocks(ctx, od.rows[2] * od.cols[2], 1, RED_THREADS, 2);
-    for (int i = 0; i < 10; ++i) EF_LAUNCH(ctx, k_so3_step, nb, RED_THREADS, 0, od, i, 1);
-  }
-  ef_stage(ctx, 3);
   int iterations[NUM_PYRS] = {fastOdom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0};
   // static schedule of (level, iter)
   int sched_level[32], sched_iter[32], ns = 0;
@@ -951,8 +1144,46 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
       sched_iter[ns] = j;
       ++ns;
     }
-  EF_LAUNCH(ctx, k_gn_seed, 1, 32, 0, od.gn, ns ? sched_level[0] : 0);
-  for (int s = 0; s < ns; ++s) {
+  int s0 = 0;  // first schedule slot that still has to be launched the two-kernel way
+  if (ctx->cluster_size > 0) {
+    // SO(3) loop + seeding + every iteration of the levels >= 1 in one cluster launch
+    GnSchedule sch;
+    memset(&sch, 0, sizeof(sch));
+    while (s0 < ns && sched_level[s0] >= 1) {
+      sch.level[s0] = (signed char)sched_level[s0];
+      sch.iter[s0] = (signed char)sched_iter[s0];
+      ++s0;
+    }
+    sch.n = s0;
+    sch.level[s0] = (signed char)(s0 < ns ? sched_level[s0] : -1);
+    if (s0 == 0) sch.level[0] = (signed char)(ns ? sched_level[0] : 0);  // level the seeding prepares
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctx->cluster_size);
+    cfg.blockDim = dim3(CL_THREADS);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ctx->cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx->pdl ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_track_cluster, od, sch, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0, rgb ? 1 : 0, icp ? 1 : 0);
+    if (e != cudaSuccess) return (int)e;
+    ctx->launches++;
+    ef_stage(ctx, 3);
+  } else {
+    EF_LAUNCH(ctx, k_gn_begin, 1, 32, 0, od.gn, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0);
+    if (so3) {
+      const int nb = red_blocks(ctx, od.rows[2] * od.cols[2], 1, RED_THREADS, 2);
+      for (int i = 0; i < 10; ++i) EF_LAUNCH(ctx, k_so3_step, nb, RED_THREADS, 0, od, i, 1);
+    }
+    ef_stage(ctx, 3);
+    EF_LAUNCH(ctx, k_gn_seed, 1, 32, 0, od.gn, ns ? sched_level[0] : 0);
+  }
+  for (int s = s0; s < ns; ++s) {
     const int lv = sched_level[s];
     const int npx = od.rows[lv] * od.cols[lv];
     const int next_lv = (s + 1 < ns) ? sched_level[s + 1] : -1;

@@ -22,6 +22,12 @@ buf = (C.c_char * sz)()
 cudart.cudaMemcpy(buf, C.c_void_p(gnp), C.c_size_t(sz), 2)
 off = lib.ef_debug_dbg_offset()
 dbg = np.frombuffer(buf, dtype=np.int64, count=32, offset=off)
-print("k_iter1 cycles: start->after cand %d, icp loop %d, block reduce %d" % (dbg[1]-dbg[0], dbg[2]-dbg[1], dbg[3]-dbg[2]))
-print("k_iter2 block0: stats %d, rgb+presum %d" % (dbg[9]-dbg[8], dbg[10]-dbg[9]))
-print("k_iter2 last block: final sums %d, stage+lastA %d, ldlt %d, rodrigues %d, rest %d" % (dbg[12]-dbg[11], dbg[13]-dbg[12], dbg[14]-dbg[13], dbg[15]-dbg[14], dbg[16]-dbg[15]))
+d = dbg.astype(np.int64)
+print("globaltimer ns, last level-0 iteration (block 0 / last block stamps)")
+print("k_iter1: start->cand done %d, icp loop %d, block reduce %d   [k1 total %d]" % (d[1]-d[0], d[2]-d[1], d[3]-d[2], d[3]-d[0]))
+print("k1.end(block0) -> k2.start(block0): %d" % (d[8]-d[3]))
+print("k_iter2 block0: stats %d, rgb+presum %d" % (d[9]-d[8], d[10]-d[9]))
+print("k2 block0 done -> last block has ticket: %d" % (d[11]-d[10]))
+print("k_iter2 last block: final sums %d, stage+lastA %d, ldlt %d, rodrigues %d, rest %d" % (d[12]-d[11], d[13]-d[12], d[14]-d[13], d[15]-d[14], d[16]-d[15]))
+print("k1.start -> k2.end: %d" % (d[16]-d[0]))
+print("persistent loop (block 0): phase A %d, barrier %d, rows %d, rows end->ticket/flag wait start %d, flag wait %d, total iteration %d" % (d[4]-d[0], d[5]-d[4], d[10]-d[5], d[6]-d[10], d[7]-d[6], d[7]-d[0]))
