@@ -19,7 +19,7 @@ namespace ef {
 int odom_init_icp_depth(EfContext* ctx, int which, const uint16_t* depth_dev, float cutoff);
 int odom_init_icp_pred(EfContext* ctx, int which, const float* vtx4, const float* nrm4);
 int odom_init_icp_model(EfContext* ctx, int which, const float* vtx4, const float* nrm4, const float* vtxB = nullptr,
-                        const float* nrmB = nullptr, const int* flag = nullptr);
+                        const float* nrmB = nullptr, const int* flag = nullptr, bool with_global = true);
 int odom_populate(EfContext* ctx, int which, const uint8_t* rgba, float** destDepths, uint8_t** destImages, bool with_depth,
                   const uint8_t* rgbaB = nullptr, const int* flag = nullptr, bool forceB = false, bool with_image = true);
 int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom, bool so3);
@@ -30,7 +30,6 @@ int launch_rgb_residual_raw(EfContext* ctx, int which, int level);
 int launch_icp_dense_only(EfContext* ctx, int which, int level);
 int launch_so3_raw(EfContext* ctx, int which);
 int launch_sobel(EfContext* ctx, int which);
-int odom_cluster_init(EfContext* ctx);
 int preprocess_depth(EfContext* ctx, const uint16_t* raw, float cutoff, uint16_t* filtered, float* metric, float* metric_filtered);
 int rgb_to_rgba(EfContext* ctx, const uint8_t* rgb, uint8_t* rgba);
 
@@ -150,6 +149,8 @@ static int alloc_odom(EfContext* ctx, OdomDev& od) {
     CU(A->alloc(&od.depth_tmp[i], n));
     CU(A->alloc(&od.vmap_g_prev[i], 3 * n));
     CU(A->alloc(&od.nmap_g_prev[i], 3 * n));
+    CU(A->alloc(&od.vmap_c_prev[i], 3 * n));
+    CU(A->alloc(&od.nmap_c_prev[i], 3 * n));
     CU(A->alloc(&od.vmap_curr[i], 3 * n));
     CU(A->alloc(&od.nmap_curr[i], 3 * n));
     CU(A->alloc(&od.lastDepth[i], n));
@@ -163,6 +164,8 @@ static int alloc_odom(EfContext* ctx, OdomDev& od) {
     // the reference's cudaMalloc'd maps start uninitialised; NaN / zero fill keeps every first read defined
     CU(cudaMemsetAsync(od.vmap_g_prev[i], 0xff, 3 * n * sizeof(float), ctx->stream));
     CU(cudaMemsetAsync(od.nmap_g_prev[i], 0xff, 3 * n * sizeof(float), ctx->stream));
+    CU(cudaMemsetAsync(od.vmap_c_prev[i], 0xff, 3 * n * sizeof(float), ctx->stream));
+    CU(cudaMemsetAsync(od.nmap_c_prev[i], 0xff, 3 * n * sizeof(float), ctx->stream));
     CU(cudaMemsetAsync(od.vmap_curr[i], 0xff, 3 * n * sizeof(float), ctx->stream));
     CU(cudaMemsetAsync(od.nmap_curr[i], 0xff, 3 * n * sizeof(float), ctx->stream));
     CU(cudaMemsetAsync(od.lastDepth[i], 0xff, n * sizeof(float), ctx->stream));
@@ -270,7 +273,6 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
   {
     const char* e = getenv("EF_NO_PDL");
     ctx->pdl = !(e && e[0] == '1');
-    odom_cluster_init(ctx);
     e = getenv("EF_STAGE_TIMING");
     ctx->stage_timing = (e && e[0] == '1');
     ctx->stage_n = 0;
@@ -641,6 +643,14 @@ extern "C" int ef_icp_step_async(EfContext* ctx, int which, int level, const flo
     RC(upload_gn(ctx, which, offsetof(GNState, tcurr), s + 9, 12));
     RC(upload_gn(ctx, which, offsetof(GNState, Rprev_inv), s + 12, 36));
     RC(upload_gn(ctx, which, offsetof(GNState, tprev), s + 21, 12));
+    // the kernel works in the previous camera's frame: M = R_prev^-1 R_curr, t' = R_prev^-1 (t_curr - t_prev)
+    float* M = s + 24;
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c)
+        M[r * 3 + c] = Rprev_inv[r * 3 + 0] * Rcurr[0 * 3 + c] + Rprev_inv[r * 3 + 1] * Rcurr[1 * 3 + c] + Rprev_inv[r * 3 + 2] * Rcurr[2 * 3 + c];
+      M[9 + r] = Rprev_inv[r * 3 + 0] * (tcurr[0] - tprev[0]) + Rprev_inv[r * 3 + 1] * (tcurr[1] - tprev[1]) + Rprev_inv[r * 3 + 2] * (tcurr[2] - tprev[2]);
+    }
+    RC(upload_gn(ctx, which, offsetof(GNState, Mcp), M, 48));
   }
   return launch_se3_step_raw(ctx, which, level, true, false, 0.f);
 }

@@ -31,6 +31,7 @@ struct GNState {
 
   float Rprev[9], tprev[3], Rprev_inv[9];
   float Rcurr[9], tcurr[3];
+  float Mcp[9], tcp[3];  // current camera -> previous camera: R_prev^-1 R_curr, R_prev^-1 (t_curr - t_prev) (= the inverse increment)
   double resultRt[16];
   double resultR[9], lastResultR[9];
   float R_lr[9];
@@ -76,6 +77,7 @@ struct OdomDev {
   uint16_t* depth_tmp[NUM_PYRS];
   float* vmaps_tmp;  // float4 AoS, level 0
   float *vmap_g_prev[NUM_PYRS], *nmap_g_prev[NUM_PYRS], *vmap_curr[NUM_PYRS], *nmap_curr[NUM_PYRS];
+  float *vmap_c_prev[NUM_PYRS], *nmap_c_prev[NUM_PYRS];  // model maps in the previous camera's frame (what the ICP kernel reads)
   float *lastDepth[NUM_PYRS], *nextDepth[NUM_PYRS];
   uint8_t *lastImage[NUM_PYRS], *nextImage[NUM_PYRS], *lastNextImage[NUM_PYRS];
   int16_t *dIdx[NUM_PYRS], *dIdy[NUM_PYRS];
@@ -170,7 +172,6 @@ struct EfContext {
   bool stage_timing;            // EF_STAGE_TIMING=1: record an event after every stage of ef_process_frame_device
   cudaEvent_t stage_ev[16];
   int stage_n;
-  int cluster_size;    // CTAs of the coarse-level tracking cluster (16, 8 or 0 = off; EF_NO_CLUSTER=1 forces 0)
   bool pdl;  // programmatic dependent launch on every kernel (default on; EF_NO_PDL=1 disables)
 
   ef::OdomDev odom[2];

@@ -98,6 +98,8 @@ __device__ void gn_begin_body(GNState* gn, int rgbOnly, float icpWeight, int so3
   }
   for (int k = 0; k < 9; ++k) gn->Rcurr[k] = gn->Rprev[k];
   for (int k = 0; k < 3; ++k) gn->tcurr[k] = gn->tprev[k];
+  for (int k = 0; k < 9; ++k) gn->Mcp[k] = (k % 4 == 0) ? 1.f : 0.f;  // Rcurr = Rprev, tcurr = tprev
+  for (int k = 0; k < 3; ++k) gn->tcp[k] = 0.f;
   efm::inv3<float>(gn->Rprev, gn->Rprev_inv);
   const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   for (int k = 0; k < 9; ++k) {
@@ -350,6 +352,8 @@ __device__ __noinline__ void gn_update_warp(const OdomDev& od, GnScratch& S, int
     S.it[lane] = -(S.iR[lane * 3 + 0] * ot0 + S.iR[lane * 3 + 1] * ot1 + S.iR[lane * 3 + 2] * ot2);
   }
   __syncwarp();
+  if (lane >= 12 && lane < 21) gn->Mcp[lane - 12] = S.iR[lane - 12];  // Rprev^-1 Rcurr = the inverse increment itself
+  if (lane >= 21 && lane < 24) gn->tcp[lane - 21] = S.it[lane - 21];
   if (lane < 9) {
     const int r = lane / 3, c = lane % 3;
     gn->Rcurr[lane] = S.Rprev[r * 3 + 0] * S.iR[0 * 3 + c] + S.Rprev[r * 3 + 1] * S.iR[1 * 3 + c] + S.Rprev[r * 3 + 2] * S.iR[2 * 3 + c];
@@ -391,11 +395,18 @@ constexpr int IT1_CTAS_PER_SM = 5;
 constexpr int IT2_THREADS = 256;
 
 // ---- geometric row: ICPReduction::search/getProducts (reduce.cu:224-331) ------------------------------------
+// The reference moves the live vertex to the world (Rcurr, tcurr), back into the previous camera (Rprev^-1, tprev) to
+// project it, gathers the model point from WORLD-frame maps and rotates that back into the previous camera as well
+// (three 3x3 transforms + two extra for the normals, per pixel and iteration). All of it happens in one rigid frame
+// here: M = Rprev^-1 Rcurr and t' = Rprev^-1 (tcurr - tprev) are formed once per iteration (they are the inverse
+// increment the solver already has), the model maps stay in the previous camera's frame (no tranformMaps pass), and the
+// distance / angle gates compare squared norms (both are rotation invariant). Same correspondences, rows and sums up to
+// float rounding (parity tests: 1e-4 relative on A and b, as north_star asks; inlier counts within borderline flips).
 struct IcpFrame {
-  m33 Rcurr, Rprev_inv;
-  f3 tcurr, tprev;
+  m33 M;
+  f3 t;
   float fx, fy, cx, cy;
-  float distThres, angleThres;
+  float distThres2, angleThres2;
 };
 
 __device__ __forceinline__ void accumulate29(const float row[7], float (&acc)[29]) {
@@ -408,26 +419,23 @@ __device__ __forceinline__ void accumulate29(const float row[7], float (&acc)[29
   acc[28] += 1.0f;
 }
 
-// projective association of one live vertex: returns the model pixel (linear index) or -1
-__device__ __forceinline__ int icp_project(const IcpFrame& F, const f3& vcurr, int rows, int cols, f3& vcurr_g, f3& vcurr_cp) {
-  vcurr_g = mul(F.Rcurr, vcurr) + F.tcurr;
-  vcurr_cp = mul(F.Rprev_inv, vcurr_g - F.tprev);
-  const int ux = __float2int_rn(vcurr_cp.x * F.fx / vcurr_cp.z + F.cx);
-  const int uy = __float2int_rn(vcurr_cp.y * F.fy / vcurr_cp.z + F.cy);
-  if (ux < 0 || uy < 0 || ux >= cols || uy >= rows || vcurr_cp.z < 0) return -1;
+// projective association of one live vertex: s = its position in the previous camera; returns the model pixel or -1
+__device__ __forceinline__ int icp_project(const IcpFrame& F, const f3& vcurr, int rows, int cols, f3& s) {
+  s = mul(F.M, vcurr) + F.t;
+  const int ux = __float2int_rn(s.x * F.fx / s.z + F.cx);
+  const int uy = __float2int_rn(s.y * F.fy / s.z + F.cy);
+  if (ux < 0 || uy < 0 || ux >= cols || uy >= rows || s.z < 0) return -1;
   return uy * cols + ux;
 }
 
-__device__ __forceinline__ void icp_accumulate(const IcpFrame& F, const f3& vcurr_g, const f3& s_cp, const f3& ncurr, const f3& vprev_g,
-                                               const f3& nprev_g, float (&acc)[29]) {
-  const f3 ncurr_g = mul(F.Rcurr, ncurr);
-  const float dist = norm(vprev_g - vcurr_g);
-  const float sine = norm(cross(ncurr_g, nprev_g));
-  if (!(sine < F.angleThres && dist <= F.distThres && !isnan(ncurr.x) && !isnan(nprev_g.x))) return;
-  const f3 d_cp = mul(F.Rprev_inv, vprev_g - F.tprev);
-  const f3 n_cp = mul(F.Rprev_inv, nprev_g);
-  const f3 c = cross(s_cp, n_cp);
-  const float row[7] = {n_cp.x, n_cp.y, n_cp.z, c.x, c.y, c.z, dot(n_cp, s_cp - d_cp)};
+// s: live vertex, ncurr: live normal (current camera), d / n: model vertex and normal (previous camera)
+__device__ __forceinline__ void icp_accumulate(const IcpFrame& F, const f3& s, const f3& ncurr, const f3& d, const f3& n, float (&acc)[29]) {
+  const f3 nc = mul(F.M, ncurr);
+  const f3 e = s - d;
+  const f3 cr = cross(nc, n);
+  if (!(dot(cr, cr) < F.angleThres2 && dot(e, e) <= F.distThres2 && !isnan(ncurr.x) && !isnan(n.x))) return;
+  const f3 c = cross(s, n);
+  const float row[7] = {n.x, n.y, n.z, c.x, c.y, c.z, dot(n, e)};
   accumulate29(row, acc);
 }
 
@@ -489,10 +497,8 @@ __device__ __forceinline__ void iter1_body(const OdomDev& od, int level, int do_
   EF_STAMP(gn, 1, stamp);
   if (do_icp) {
     IcpFrame F;
-    F.Rcurr = load_m33(gn->Rcurr);
-    F.Rprev_inv = load_m33(gn->Rprev_inv);
-    F.tcurr = mk3(gn->tcurr[0], gn->tcurr[1], gn->tcurr[2]);
-    F.tprev = mk3(gn->tprev[0], gn->tprev[1], gn->tprev[2]);
+    F.M = load_m33(gn->Mcp);
+    F.t = mk3(gn->tcp[0], gn->tcp[1], gn->tcp[2]);
     {
       const int div = 1 << level;
       F.fx = gn->fx / div;
@@ -500,15 +506,15 @@ __device__ __forceinline__ void iter1_body(const OdomDev& od, int level, int do_
       F.cx = gn->cx / div;
       F.cy = gn->cy / div;
     }
-    F.distThres = od.distThres;
-    F.angleThres = od.angleThres;
+    F.distThres2 = od.distThres * od.distThres;
+    F.angleThres2 = od.angleThres * od.angleThres;
     float acc[29];
 #pragma unroll
     for (int k = 0; k < 29; ++k) acc[k] = 0.f;
     const float* __restrict__ vc = od.vmap_curr[level];
     const float* __restrict__ nc = od.nmap_curr[level];
-    const float* __restrict__ vp = od.vmap_g_prev[level];
-    const float* __restrict__ np_ = od.nmap_g_prev[level];
+    const float* __restrict__ vp = od.vmap_c_prev[level];
+    const float* __restrict__ np_ = od.nmap_c_prev[level];
     if (vec) {
       // 4 consecutive pixels per thread: six 128-bit coalesced loads for the live maps, the model maps gathered in pairs
       const int ngroups = N >> 2;
@@ -524,24 +530,24 @@ __device__ __forceinline__ void iter1_body(const OdomDev& od, int level, int do_
         const float nxs[4] = {nx4.x, nx4.y, nx4.z, nx4.w}, nys[4] = {ny4.x, ny4.y, ny4.z, ny4.w}, nzs[4] = {nz4.x, nz4.y, nz4.z, nz4.w};
 #pragma unroll
         for (int h = 0; h < 4; h += 2) {
-          f3 vg0, vg1, cp0, cp1;
-          const int q0 = icp_project(F, mk3(vxs[h], vys[h], vzs[h]), rows, cols, vg0, cp0);
-          const int q1 = icp_project(F, mk3(vxs[h + 1], vys[h + 1], vzs[h + 1]), rows, cols, vg1, cp1);
+          f3 s0, s1;
+          const int q0 = icp_project(F, mk3(vxs[h], vys[h], vzs[h]), rows, cols, s0);
+          const int q1 = icp_project(F, mk3(vxs[h + 1], vys[h + 1], vzs[h + 1]), rows, cols, s1);
           const int a0 = q0 < 0 ? 0 : q0, a1 = q1 < 0 ? 0 : q1;
           const float p00 = __ldg(vp + a0), p01 = __ldg(vp + plane + a0), p02 = __ldg(vp + 2 * plane + a0);
           const float p03 = __ldg(np_ + a0), p04 = __ldg(np_ + plane + a0), p05 = __ldg(np_ + 2 * plane + a0);
           const float p10 = __ldg(vp + a1), p11 = __ldg(vp + plane + a1), p12 = __ldg(vp + 2 * plane + a1);
           const float p13 = __ldg(np_ + a1), p14 = __ldg(np_ + plane + a1), p15 = __ldg(np_ + 2 * plane + a1);
-          if (q0 >= 0) icp_accumulate(F, vg0, cp0, mk3(nxs[h], nys[h], nzs[h]), mk3(p00, p01, p02), mk3(p03, p04, p05), acc);
-          if (q1 >= 0) icp_accumulate(F, vg1, cp1, mk3(nxs[h + 1], nys[h + 1], nzs[h + 1]), mk3(p10, p11, p12), mk3(p13, p14, p15), acc);
+          if (q0 >= 0) icp_accumulate(F, s0, mk3(nxs[h], nys[h], nzs[h]), mk3(p00, p01, p02), mk3(p03, p04, p05), acc);
+          if (q1 >= 0) icp_accumulate(F, s1, mk3(nxs[h + 1], nys[h + 1], nzs[h + 1]), mk3(p10, p11, p12), mk3(p13, p14, p15), acc);
         }
       }
     } else {
       for (int i = gid; i < N; i += gstride) {
-        f3 vg, cp;
-        const int q = icp_project(F, mk3(vc[i], vc[i + plane], vc[i + 2 * plane]), rows, cols, vg, cp);
+        f3 sp;
+        const int q = icp_project(F, mk3(vc[i], vc[i + plane], vc[i + 2 * plane]), rows, cols, sp);
         if (q >= 0)
-          icp_accumulate(F, vg, cp, mk3(nc[i], nc[i + plane], nc[i + 2 * plane]), mk3(vp[q], vp[q + plane], vp[q + 2 * plane]),
+          icp_accumulate(F, sp, mk3(nc[i], nc[i + plane], nc[i + 2 * plane]), mk3(vp[q], vp[q + plane], vp[q + 2 * plane]),
                          mk3(np_[q], np_[q + plane], np_[q + 2 * plane]), acc);
       }
     }
@@ -990,85 +996,6 @@ __global__ void __launch_bounds__(RED_THREADS) k_so3_step(OdomDev od, int iter, 
   so3_finish(od, iter);
 }
 
-// ---- coarse levels in one thread-block cluster --------------------------------------------------------------------
-// At the coarse pyramid levels (160x120 and 320x240 of a 640x480 frame) an iteration is a chain of latencies, not work:
-// two dependent launches and a last-CTA ticket cost ~17 us for ~2 us of arithmetic. k_track_cluster runs the start of
-// getIncrementalTransformation (RGBDOdometry.cpp:266-303), the whole SO(3) pre-alignment loop (:305-368), the seeding of
-// the SE(3) estimate (:379-388) and every Gauss-Newton iteration of the levels >= 1 in ONE launch of a single cluster:
-// the CTAs of the cluster split the pixels, hardware cluster barriers (barrier.cluster, release/acquire) replace the kernel
-// boundaries and the ticket, and rank 0 does the final sums and the solve. The arithmetic inside a CTA is that of
-// k_so3_step / k_iter1 / k_iter2 (same device functions); only the pixel-to-CTA partition differs. Level 0 keeps the
-// two-launch form: there the dense pass is real work for all 148 SMs.
-struct GnSchedule {
-  int n;
-  signed char level[32], iter[32];
-};
-constexpr int CL_THREADS = 640;  // 20 warps, one CTA per SM
-
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ unsigned int cluster_rank() {
-  unsigned int r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ unsigned int cluster_size() {
-  unsigned int r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-
-__global__ void __launch_bounds__(CL_THREADS, 1) k_track_cluster(OdomDev od, GnSchedule sch, int rgbOnly, float icpWeight, int so3, int do_rgb,
-                                                                 int do_icp) {
-  pdl_enter();
-  __shared__ Iter2Shared sh;
-  __shared__ double so3_dsm[(CL_THREADS / 32) * 32];
-  GNState* gn = od.gn;
-  const int vb = (int)cluster_rank(), nvb = (int)cluster_size();
-  const bool leader = (vb == 0);
-
-  if (leader && threadIdx.x == 0) gn_begin_body(gn, rgbOnly, icpWeight, so3);
-  cluster_sync_all();
-  if (so3) {
-    for (int i = 0; i < 10; ++i) {
-      if (gn->so3_done) break;  // uniform: written by the leader before the previous barrier
-      so3_partial<CL_THREADS>(od, vb, nvb, sh.sred);
-      cluster_sync_all();
-      if (leader) {
-        so3_final_sum<CL_THREADS>(od.partials, nvb, gn->sum_so3, so3_dsm);
-        if (threadIdx.x == 0) so3_finish(od, i);
-      }
-      cluster_sync_all();
-    }
-  }
-  if (leader && threadIdx.x == 0) gn_seed_body(gn, sch.n ? sch.level[0] : 0);
-  cluster_sync_all();
-
-  const int mode = (do_rgb ? 1 | 8 : 0) | (do_icp ? 2 : 0) | 4;
-  int break_level = -1;
-  for (int s = 0; s < sch.n; ++s) {
-    const int lv = sch.level[s], it = sch.iter[s];
-    const int next_lv = sch.level[s + 1];  // the host appends the level that follows the last cluster iteration (or -1)
-    if (break_level == lv) {
-      // rgbOnly `break`: the rest of the level is skipped; its last slot prepares the next level's warp matrices
-      if (next_lv >= 0 && next_lv != lv) {
-        if (leader && threadIdx.x == 0) gn_prepare_warp(gn, next_lv);
-        cluster_sync_all();
-      }
-      continue;
-    }
-    iter1_body<CL_THREADS>(od, lv, do_rgb, do_icp, vb, nvb, sh.sred);
-    cluster_sync_all();
-    const bool brk = iter2_rows<CL_THREADS>(od, sh, lv, it, next_lv, do_icp ? nvb : 0, mode, 0.f, vb, nvb);
-    cluster_sync_all();
-    if (leader) iter2_final<CL_THREADS>(od, sh, lv, it, next_lv, mode, nvb, brk);
-    cluster_sync_all();
-    if (brk) break_level = lv;
-  }
-}
-
-
 namespace {
 
 inline int red_blocks(const EfContext* ctx, int n_items, int per_thread, int threads, int ctas_per_sm) {
@@ -1098,35 +1025,6 @@ inline int iter2_blocks(int npx, bool rgb, int nb1) {
 namespace ef {
 
 // the device-resident Gauss-Newton schedule; T_wc in/out lives in gn->T_wc
-// Picks the cluster size of k_track_cluster: 16 CTAs (non-portable size, opt-in) when the device can co-schedule them,
-// else 8, else 0 = every iteration as two launches. EF_NO_CLUSTER=1 forces 0 (A/B measurements).
-int odom_cluster_init(EfContext* ctx) {
-  ctx->cluster_size = 0;
-  const char* e = getenv("EF_NO_CLUSTER");
-  if (e && e[0] == '1') return 0;
-  cudaFuncSetAttribute(k_track_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  const int tries[2] = {16, 8};
-  for (int k = 0; k < 2; ++k) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(tries[k]);
-    cfg.blockDim = dim3(CL_THREADS);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = tries[k];
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k_track_cluster, &cfg) == cudaSuccess && n >= 1) {
-      ctx->cluster_size = tries[k];
-      break;
-    }
-  }
-  (void)cudaGetLastError();
-  return 0;
-}
-
 int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom, bool so3) {
   OdomDev& od = ctx->odom[which];
   const bool icp = !rgbOnly && icpWeight > 0;
@@ -1144,46 +1042,14 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
       sched_iter[ns] = j;
       ++ns;
     }
-  int s0 = 0;  // first schedule slot that still has to be launched the two-kernel way
-  if (ctx->cluster_size > 0) {
-    // SO(3) loop + seeding + every iteration of the levels >= 1 in one cluster launch
-    GnSchedule sch;
-    memset(&sch, 0, sizeof(sch));
-    while (s0 < ns && sched_level[s0] >= 1) {
-      sch.level[s0] = (signed char)sched_level[s0];
-      sch.iter[s0] = (signed char)sched_iter[s0];
-      ++s0;
-    }
-    sch.n = s0;
-    sch.level[s0] = (signed char)(s0 < ns ? sched_level[s0] : -1);
-    if (s0 == 0) sch.level[0] = (signed char)(ns ? sched_level[0] : 0);  // level the seeding prepares
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ctx->cluster_size);
-    cfg.blockDim = dim3(CL_THREADS);
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = ctx->cluster_size;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = ctx->pdl ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_track_cluster, od, sch, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0, rgb ? 1 : 0, icp ? 1 : 0);
-    if (e != cudaSuccess) return (int)e;
-    ctx->launches++;
-    ef_stage(ctx, 3);
-  } else {
-    EF_LAUNCH(ctx, k_gn_begin, 1, 32, 0, od.gn, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0);
-    if (so3) {
-      const int nb = red_blocks(ctx, od.rows[2] * od.cols[2], 1, RED_THREADS, 2);
-      for (int i = 0; i < 10; ++i) EF_LAUNCH(ctx, k_so3_step, nb, RED_THREADS, 0, od, i, 1);
-    }
-    ef_stage(ctx, 3);
-    EF_LAUNCH(ctx, k_gn_seed, 1, 32, 0, od.gn, ns ? sched_level[0] : 0);
+  EF_LAUNCH(ctx, k_gn_begin, 1, 32, 0, od.gn, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0);
+  if (so3) {
+    const int nb = red_blocks(ctx, od.rows[2] * od.cols[2], 1, RED_THREADS, 2);
+    for (int i = 0; i < 10; ++i) EF_LAUNCH(ctx, k_so3_step, nb, RED_THREADS, 0, od, i, 1);
   }
-  for (int s = s0; s < ns; ++s) {
+  ef_stage(ctx, 3);
+  EF_LAUNCH(ctx, k_gn_seed, 1, 32, 0, od.gn, ns ? sched_level[0] : 0);
+  for (int s = 0; s < ns; ++s) {
     const int lv = sched_level[s];
     const int npx = od.rows[lv] * od.cols[lv];
     const int next_lv = (s + 1 < ns) ? sched_level[s + 1] : -1;

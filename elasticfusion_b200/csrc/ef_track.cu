@@ -187,8 +187,12 @@ __global__ void k_resize_maps(const float* __restrict__ vin, const float* __rest
   }
 }
 
-// tranformMaps (cudafuncs.cu:221-293), all three levels in one launch (blockIdx.y = level), in place, pose from gn->T_wc
+// tranformMaps (cudafuncs.cu:221-293), all three levels in one launch (blockIdx.y = level), pose from gn->T_wc. The
+// reference transforms in place; here the camera-frame maps are kept (the ICP kernel reads those) and the world-frame
+// copy is only produced for the stage API / inspection.
 struct XformArgs {
+  const float* sv[NUM_PYRS];
+  const float* sn[NUM_PYRS];
   float* v[NUM_PYRS];
   float* n[NUM_PYRS];
   int rows[NUM_PYRS], cols[NUM_PYRS];
@@ -206,23 +210,21 @@ __global__ void k_transform_maps(XformArgs a, const GNState* __restrict__ gn) {
   }
   const m33 Rm = load_m33(R);
   const f3 tv = mk3(t[0], t[1], t[2]);
-  float* vm = a.v[lv];
-  float* nm = a.n[lv];
+  const float* __restrict__ sv = a.sv[lv];
+  const float* __restrict__ sn = a.sn[lv];
+  float* __restrict__ vm = a.v[lv];
+  float* __restrict__ nm = a.n[lv];
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += (size_t)gridDim.x * blockDim.x) {
-    const float vx = vm[p];
-    if (!isnan(vx)) {
-      const f3 d = mul(Rm, mk3(vx, vm[p + np], vm[p + 2 * np])) + tv;
-      vm[p] = d.x;
-      vm[p + np] = d.y;
-      vm[p + 2 * np] = d.z;
-    }
-    const float nx = nm[p];
-    if (!isnan(nx)) {
-      const f3 d = mul(Rm, mk3(nx, nm[p + np], nm[p + 2 * np]));
-      nm[p] = d.x;
-      nm[p + np] = d.y;
-      nm[p + 2 * np] = d.z;
-    }
+    f3 v = mk3(sv[p], sv[p + np], sv[p + 2 * np]);
+    if (!isnan(v.x)) v = mul(Rm, v) + tv;
+    vm[p] = v.x;
+    vm[p + np] = v.y;
+    vm[p + 2 * np] = v.z;
+    f3 n = mk3(sn[p], sn[p + np], sn[p + 2 * np]);
+    if (!isnan(n.x)) n = mul(Rm, n);
+    nm[p] = n.x;
+    nm[p + np] = n.y;
+    nm[p + 2 * np] = n.z;
   }
 }
 
@@ -456,12 +458,15 @@ int odom_init_icp_pred(EfContext* ctx, int which, const float* vtx4, const float
 
 // pose is taken from gn->T_wc (device) — callers that pass an explicit pose upload it first
 int odom_init_icp_model(EfContext* ctx, int which, const float* vtx4, const float* nrm4, const float* vtxB = nullptr,
-                        const float* nrmB = nullptr, const int* flag = nullptr) {
+                        const float* nrmB = nullptr, const int* flag = nullptr, bool with_global = true) {
   OdomDev& od = ctx->odom[which];
-  int rc = copy_and_resize(ctx, od, vtx4, nrm4, od.vmap_g_prev, od.nmap_g_prev, vtxB, nrmB, flag);
+  int rc = copy_and_resize(ctx, od, vtx4, nrm4, od.vmap_c_prev, od.nmap_c_prev, vtxB, nrmB, flag);
   if (rc) return rc;
+  if (!with_global) return 0;  // the frame loop never reads the world-frame copy
   XformArgs a;
   for (int i = 0; i < NUM_PYRS; ++i) {
+    a.sv[i] = od.vmap_c_prev[i];
+    a.sn[i] = od.nmap_c_prev[i];
     a.v[i] = od.vmap_g_prev[i];
     a.n[i] = od.nmap_g_prev[i];
     a.rows[i] = od.rows[i];
@@ -494,7 +499,7 @@ int map_select_model_inputs(EfContext* ctx, const float**, const float**, const 
   OdomDev& od = ctx->odom[0];
   Textures& t = ctx->tex;
   int rc = odom_init_icp_model(ctx, 0, (const float*)t.vertex, (const float*)t.normal, (const float*)t.fill_vertex, (const float*)t.fill_normal,
-                               ctx->map.dense_flag);
+                               ctx->map.dense_flag, false);
   if (rc) return rc;
   return odom_populate(ctx, 0, (const uint8_t*)t.image, od.lastDepth, od.lastImage, true, (const uint8_t*)t.fill_image, ctx->map.dense_flag,
                        ctx->frame_to_frame_rgb);
