@@ -349,11 +349,26 @@ class ElasticFusion {
     ef_destroy(ctx_);
   }
 
+  // Reference signature (Core/ElasticFusion.h:62-75) plus an optional look-ahead: when the caller already holds the NEXT
+  // frame (a log reader does), passing it as nextRgb / nextDepth stages its upload, depth preprocess and pyramids on a side
+  // stream while this frame is tracked and fused (ef_prefetch_frame). The next call must then be for that frame (its
+  // rgb / depth arguments are not read again). Results are identical with or without look-ahead.
   void processFrame(const uint8_t* rgb, const uint16_t* depth, const int64_t& timestamp, const float weightMultiplier,
-                    const ef::SE3d* in_T_wc = 0) {
+                    const ef::SE3d* in_T_wc = 0, const uint8_t* nextRgb = 0, const uint16_t* nextDepth = 0) {
     double T[16];
     if (in_T_wc) ef::toRowMajor(*in_T_wc, T);
-    ef::check(ef_process_frame(ctx_, rgb, depth, timestamp, weightMultiplier, in_T_wc ? T : nullptr), "processFrame");
+    if (!staged_ && !(nextRgb && nextDepth)) {
+      ef::check(ef_process_frame(ctx_, rgb, depth, timestamp, weightMultiplier, in_T_wc ? T : nullptr), "processFrame");
+    } else {
+      if (!staged_) ef::check(ef_prefetch_frame(ctx_, rgb, depth), "processFrame (stage)");
+      ef::check(ef_process_frame_device(ctx_, nullptr, nullptr, timestamp, weightMultiplier, in_T_wc ? T : nullptr), "processFrame");
+      staged_ = false;
+      if (nextRgb && nextDepth) {
+        ef::check(ef_prefetch_frame(ctx_, nextRgb, nextDepth), "processFrame (look-ahead)");
+        staged_ = true;
+      }
+      ef::check(ef_finish_frame(ctx_), "processFrame (finish)");
+    }
     ef::check(ef_get_pose(ctx_, T), "get_T_wc");
     T_wc_curr_ = ef::fromRowMajor(T);
     poseLog_.emplace_back(T, T + 16);
@@ -478,6 +493,7 @@ class ElasticFusion {
   int tick_ = 1;
   int zero_ = 0;
   bool lost_ = false;
+  bool staged_ = false;  // a look-ahead frame is waiting in the library (ef_prefetch_frame)
 };
 
 #endif  // EFUSION_B200_ELASTICFUSION_H_

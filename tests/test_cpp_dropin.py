@@ -41,6 +41,9 @@ def test_core_api_example_runs_and_matches_c_abi(tmp_path, small_K, small_frames
     synth.write_klg(klg, [(f[0], f[1]) for f in small_frames])
     K = small_K
     out = subprocess.check_output([exe, klg, str(K.width), str(K.height), str(K.fx), str(K.fy), str(K.cx), str(K.cy)], text=True)
+    # the same program handing processFrame the next frame as well (look-ahead) must print exactly the same result
+    out_la = subprocess.check_output([exe, klg, str(K.width), str(K.height), str(K.fx), str(K.fy), str(K.cx), str(K.cy), "lookahead"], text=True)
+    assert out_la == out
     pose = np.array([float(x) for x in out.split("POSE")[1].split("\n")[0].split()]).reshape(4, 4)
     count = int(out.split("COUNT")[1].split()[0])
     tick = int(out.split("TICK")[1].split()[0])
