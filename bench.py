@@ -194,6 +194,20 @@ def run_ours(args, rank, world, dist):
     roof = icp_roofline(ctx, stream, flush, K)
     ctx.close()
     del rgb_d, depth_d
+    roof_hi = None
+    if rank == 0 and args.workload == "640x480" and not args.no_hires_roofline:
+        # the same kernel on BASELINE configs[2]'s image size (59 MB per launch): the size at which the pass is bandwidth-
+        # rather than launch-latency-dominated
+        from elasticfusion_b200 import synth
+
+        Kh = synth.K_DEFAULT.scaled(2)
+        rgb_h, depth_h = make_frames(Kh, 3, 42)
+        ctx_h = capi.Context(capi.default_config(Kh.width, Kh.height, Kh.fx, Kh.fy, Kh.cx, Kh.cy, capacity=3_000_000, time_delta=BIG, device=local),
+                             stream=stream.cuda_stream)
+        for i in range(3):
+            ctx_h.process_frame(rgb_h[i], depth_h[i], i)
+        roof_hi = icp_roofline(ctx_h, stream, flush, Kh)
+        ctx_h.close()
 
     # ---------------- e2e: host buffers through the public call ----------------
     ctx2 = capi.Context(cfg, stream=stream.cuda_stream)
@@ -249,6 +263,7 @@ def run_ours(args, rank, world, dist):
                 "d2h_bytes_per_step": 132, "ms_per_step": e2e_ms_max / args.steps},
         "gpu_launches": int(launches), "launches_per_frame": launches / args.steps,
         "clocks": clocks, "roofline": dict(roof, peak=hbm, frac=roof["achieved"] / hbm, peak_source=peak_src),
+        **({"roofline_1280x960": dict(roof_hi, peak=hbm, frac=roof_hi["achieved"] / hbm, peak_source=peak_src)} if roof_hi else {}),
         "frame_ms": {"median": statistics.median(frame_ms), "p10": float(np.percentile(frame_ms, 10)), "p90": float(np.percentile(frame_ms, 90))},
         "wall_s_value_loop": t_wall, "pose_check": float(np.abs(pose - pose2).max()),
     }
@@ -289,17 +304,20 @@ def icp_roofline(ctx, stream, flush, K):
     full_cold = timed(lambda: ctx.icp_step_async(0), True)
     full_warm = timed(lambda: ctx.icp_step_async(0), False)
     nbytes = 48 * K.width * K.height + 116
-    traffic = None
+    traffic = ncu_us = None
     tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(f"k_iter1_{K.width}x{K.height}")
+            tj = json.load(open(tp))
+            traffic = tj.get(f"k_iter1_{K.width}x{K.height}")
+            ncu_us = tj.get(f"k_iter1_{K.width}x{K.height}_ncu_duration_us")
         except Exception:
             traffic = None
     return {"kernel": "k_iter1 (ICP residual + Jacobian + per-CTA 29-term reduction, level 0; ef_reduce.cu)", "bound": "hbm", "unit": "GB/s",
             "achieved": nbytes / (dense_cold * 1e-6) / 1e9, "algorithmic_bytes": nbytes, "duration_us": dense_cold,
             "achieved_warm_l2": nbytes / (dense_warm * 1e-6) / 1e9, "duration_warm_us": dense_warm,
-            "complete_reduction_us": {"cold": full_cold, "warm": full_warm}, "traffic": traffic,
+            "complete_reduction_us": {"cold": full_cold, "warm": full_warm}, "traffic": traffic, "ncu_duration_us": ncu_us,
+            "units_per_launch": f"{K.width * K.height} pixels (one Gauss-Newton iteration of pyramid level 0), 48 B each",
             "timing": "CUDA events on the launching stream around one launch, median of 30, L2 flushed (256 MiB write) before each cold launch"}
 
 
@@ -394,6 +412,7 @@ def main():
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-lookahead", action="store_true", help="process each frame without staging its successor on the side stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hires-roofline", action="store_true", help="skip the 1280x960 measurement of the roofline kernel")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
