@@ -992,7 +992,7 @@ extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, c
       RC(odom_set_pose_async(ctx, 0, (const double*)((char*)ctx->dev_small + 4096)));
       RC(odom_finish_async(ctx, 0, weight_multiplier, false));
     }
-    RC(map_update_pose_async(ctx, nullptr));
+    // (k_gn_finish also refreshed the map kernels' float pose + inverse from the new T_wc)
     ef_stage(ctx, 5);
     if (!ctx->cfg.skip_mid_predict) RC(predict_async(ctx));  // ElasticFusion.cpp:387 (only loop closure reads it)
     if (!ctx->rgb_only) {
@@ -1007,7 +1007,7 @@ extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, c
       ef_stage(ctx, 9);
     }
   }
-  RC(map_update_pose_async(ctx, nullptr));
+  if (ctx->tick == 1) RC(map_update_pose_async(ctx, nullptr));  // later frames: done by k_gn_finish, pose unchanged since
   RC(predict_async(ctx));  // ElasticFusion.cpp:599
   ef_stage(ctx, 10);
   ctx->tick++;

@@ -145,8 +145,13 @@ __global__ void k_update_pose(MapPose* mp, const double* T) {
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_flags(const uint8_t* __restrict__ flags, const int* __restrict__ n_a,
                                                               const int* __restrict__ n_b, int* __restrict__ offsets,
-                                                              unsigned long long* state, unsigned int* counter, int* total_out) {
+                                                              unsigned long long* state, unsigned int* counter, int* total_out,
+                                                              unsigned int epoch) {
+  // Tile states carry the launch's epoch in their upper bits ([63:34] epoch, [33:32] status, [31:0] value), so states left
+  // by earlier scans read as "not published" and nothing has to be cleared between scans; the tile dispenser
+  // (counter[0]) is reset by the last CTA to leave (counter[1] counts exits).
   pdl_enter();
+  const unsigned long long tag = (unsigned long long)epoch << 34;
   const int n = (n_a ? *n_a : 0) + (n_b ? *n_b : 0);
   const int num_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   __shared__ int s_warp[SCAN_THREADS / 32];
@@ -159,7 +164,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_flags(const uint8_t* __re
     if (threadIdx.x == 0) s_tile = (int)atomicAdd(counter, 1u);
     __syncthreads();
     const int tile = s_tile;
-    if (tile >= num_tiles) return;
+    if (tile >= num_tiles) {
+      if (threadIdx.x == 0 && atomicAdd(counter + 1, 1u) == gridDim.x - 1) {
+        counter[0] = 0u;  // every CTA has drawn its terminating ticket: re-arm for the next scan
+        counter[1] = 0u;
+      }
+      return;
+    }
     const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS], sum = 0;
 #pragma unroll
@@ -197,14 +208,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_flags(const uint8_t* __re
       volatile unsigned long long* vstate = state;
       int prefix = 0;
       if (tile == 0) {
-        if (lane == 0) vstate[0] = (2ull << 32) | (unsigned int)aggregate;
+        if (lane == 0) vstate[0] = tag | (2ull << 32) | (unsigned int)aggregate;
       } else {
-        if (lane == 0) vstate[tile] = (1ull << 32) | (unsigned int)aggregate;
+        if (lane == 0) vstate[tile] = tag | (1ull << 32) | (unsigned int)aggregate;
         int look = tile - 1;
         while (true) {
           const int idx = look - lane;
-          const unsigned long long w = (idx >= 0) ? vstate[idx] : (2ull << 32);
-          const unsigned int st = (unsigned int)(w >> 32);
+          const unsigned long long w = (idx >= 0) ? vstate[idx] : (tag | (2ull << 32));
+          const unsigned int st = ((w >> 34) == (unsigned long long)epoch) ? ((unsigned int)(w >> 32) & 3u) : 0u;
           if (__any_sync(0xffffffffu, st == 0)) continue;  // a predecessor has not published yet: re-read
           const unsigned int m2 = __ballot_sync(0xffffffffu, st == 2);
           const int first2 = m2 ? (__ffs(m2) - 1) : 32;
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_flags(const uint8_t* __re
           if (m2) break;
           look -= 32;
         }
-        if (lane == 0) vstate[tile] = (2ull << 32) | (unsigned int)(prefix + aggregate);
+        if (lane == 0) vstate[tile] = tag | (2ull << 32) | (unsigned int)(prefix + aggregate);
       }
       if (lane == 0) {
         s_prefix = prefix;
@@ -312,12 +323,13 @@ __global__ void k_index_scatter(const float4* __restrict__ pos_conf, const float
 }
 
 __global__ void k_index_resolve(const float4* __restrict__ pos_conf, const float4* __restrict__ color_time, const float4* __restrict__ norm_rad,
-                                const MapPose* __restrict__ mp, int n_px, const unsigned long long* __restrict__ zbuf,
+                                const MapPose* __restrict__ mp, int n_px, unsigned long long* __restrict__ zbuf,
                                 uint32_t* __restrict__ index, float4* __restrict__ vert_conf, float4* __restrict__ col_time,
                                 float4* __restrict__ nrm_rad) {
   pdl_enter();
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_px; p += gridDim.x * blockDim.x) {
     const unsigned long long key = zbuf[p];
+    zbuf[p] = kEmptyKey;  // the resolve pass leaves the z-buffer cleared for the next scatter (no memset between passes)
     if (key == kEmptyKey) {
       index[p] = 0;
       vert_conf[p] = col_time[p] = nrm_rad[p] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -705,12 +717,13 @@ __global__ void k_splat_scatter(RayArgs a, const MapPose* __restrict__ mp, const
 
 __global__ void k_splat_resolve(RayArgs a, const MapPose* __restrict__ mp, const float4* __restrict__ pos_conf,
                                 const float4* __restrict__ color_time, const float4* __restrict__ norm_rad,
-                                const unsigned long long* __restrict__ zbuf, uchar4* __restrict__ image, float4* __restrict__ vertex,
+                                unsigned long long* __restrict__ zbuf, uchar4* __restrict__ image, float4* __restrict__ vertex,
                                 float4* __restrict__ normal, uint16_t* __restrict__ time_out, float* __restrict__ depth_out) {
   pdl_enter();
   const int n_px = a.rows * a.cols;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_px; p += gridDim.x * blockDim.x) {
     const unsigned long long key = zbuf[p];
+    zbuf[p] = kEmptyKey;
     if (key == kEmptyKey) {
       if (depth_out) {
         depth_out[p] = 0.f;
@@ -800,6 +813,14 @@ __global__ void k_dense_enough(const uchar4* __restrict__ image, int rows, int c
   if (threadIdx.x == 0) *flag = ((float)s_sum / (float)(drows * dcols) > 0.75f) ? 1 : 0;
 }
 
+// count = *src, *zero = 0 (end of clean: GlobalModel.cpp:667-670)
+__global__ void k_publish_count(int* count, const int* src, int* zero) {
+  pdl_enter();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *count = *src;
+    *zero = 0;
+  }
+}
 __global__ void k_set_int(int* p, int v) {
   pdl_enter();
   if (threadIdx.x == 0 && blockIdx.x == 0) *p = v;
@@ -852,6 +873,8 @@ struct MapBuffers {
   uint8_t *fb_flag_raw, *fb_flag_filt;
   float4* aos;  // staging for download/upload
   size_t aos_cap;
+  unsigned int scan_epoch;  // tag of the current scan's tile states (k_scan_flags)
+  size_t scan_state_bytes;
 };
 
 namespace ef {
@@ -906,6 +929,11 @@ int alloc_map(EfContext* ctx) {
   CU(ctx_alloc(ctx, &m.pose, 1));
   CU(ctx_alloc(ctx, &m.dense_flag, 4));
   CU(ctx_alloc(ctx, &m.tick, 4));
+  B->scan_epoch = 0;
+  B->scan_state_bytes = tiles * 8;
+  CU(cudaMemsetAsync(m.scan_tile_state, 0, tiles * 8, ctx->stream));
+  CU(cudaMemsetAsync(m.scan_counter, 0, 16, ctx->stream));
+  CU(cudaMemsetAsync(m.zbuf, 0xff, n * 8, ctx->stream));  // kept cleared by the resolve passes from here on
   CU(cudaMemsetAsync(m.count, 0, 16, ctx->stream));
   CU(cudaMemsetAsync(m.new_count, 0, 16, ctx->stream));
   CU(cudaMemsetAsync(m.pending, 0xff, cap * 4, ctx->stream));
@@ -920,10 +948,14 @@ int alloc_map(EfContext* ctx) {
 int run_scan(EfContext* ctx, const uint8_t* flags, const int* n_a, const int* n_b, size_t max_items, int* offsets, int* total) {
   MapDev& m = ctx->map;
   const size_t tiles = (max_items + SCAN_TILE - 1) / SCAN_TILE + 1;
-  CU(cudaMemsetAsync(m.scan_tile_state, 0, tiles * 8, ctx->stream));
-  CU(cudaMemsetAsync(m.scan_counter, 0, 4, ctx->stream));
+  MapBuffers& B = mb(ctx);
+  if (++B.scan_epoch >= (1u << 30)) {  // epoch field exhausted (never in practice): start over with clean states
+    CU(cudaMemsetAsync(m.scan_tile_state, 0, B.scan_state_bytes, ctx->stream));
+    B.scan_epoch = 1;
+  }
   size_t nb = tiles < (size_t)ctx->num_sms * 4 ? tiles : (size_t)ctx->num_sms * 4;
-  EF_LAUNCH(ctx, k_scan_flags, (int)nb, SCAN_THREADS, 0, flags, n_a, n_b, offsets, (unsigned long long*)m.scan_tile_state, m.scan_counter, total);
+  EF_LAUNCH(ctx, k_scan_flags, (int)nb, SCAN_THREADS, 0, flags, n_a, n_b, offsets, (unsigned long long*)m.scan_tile_state, m.scan_counter, total,
+            B.scan_epoch);
   LAST();
   return 0;
 }
@@ -966,7 +998,6 @@ int map_initialise_async(EfContext* ctx) {
 int map_predict_indices_async(EfContext* ctx, int time, float max_depth, int time_delta) {
   MapDev& m = ctx->map;
   const int n = m.rows * m.cols;
-  CU(cudaMemsetAsync(m.zbuf, 0xff, (size_t)n * 8, ctx->stream));
   const int cap_guess = ctx->host_count > 0 ? ctx->host_count : m.capacity;
   (void)cap_guess;
   EF_LAUNCH(ctx, k_index_scatter, ctx->num_sms * 8, 256, 0, m.pos_conf, m.color_time, m.count, m.pose, time, max_depth, time_delta, m.rows,
@@ -1044,8 +1075,7 @@ int map_clean_async(EfContext* ctx, int time, float conf_threshold, int time_del
   m.pos_conf = B.pos[other];
   m.color_time = B.col[other];
   m.norm_rad = B.nr[other];
-  CU(cudaMemcpyAsync(m.count, m.new_count + 1, 4, cudaMemcpyDeviceToDevice, ctx->stream));
-  EF_LAUNCH(ctx, k_set_int, 1, 32, 0, m.new_count, 0);
+  EF_LAUNCH(ctx, k_publish_count, 1, 32, 0, m.count, (const int*)(m.new_count + 1), m.new_count);
   LAST();
   return 0;
 }
@@ -1062,7 +1092,6 @@ int map_raycast_async(EfContext* ctx, float max_depth, float conf_threshold, int
   a.time = time;
   a.max_time = max_time;
   a.time_delta = time_delta;
-  CU(cudaMemsetAsync(m.zbuf, 0xff, (size_t)n * 8, ctx->stream));
   EF_LAUNCH(ctx, k_splat_scatter, ctx->num_sms * 8, 256, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.zbuf);
   Textures& t = ctx->tex;
   if (mode == 0)

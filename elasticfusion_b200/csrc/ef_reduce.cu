@@ -143,7 +143,7 @@ __global__ void k_gn_seed(GNState* gn, int first_level) {
 }
 
 // end of getIncrementalTransformation (RGBDOdometry.cpp:555-570) + velocity weighting (ElasticFusion.cpp:369-383)
-__global__ void k_gn_finish(GNState* gn, float weightMultiplier, int have_track) {
+__global__ void k_gn_finish(GNState* gn, float weightMultiplier, int have_track, MapPose* map_pose) {
   pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double Tprev[16];
@@ -179,6 +179,13 @@ __global__ void k_gn_finish(GNState* gn, float weightMultiplier, int have_track)
   const float largest = 0.01f, minWeight = 0.5f;
   if (weighting > largest) weighting = largest;
   gn->weighting = fmaxf(1.0f - (weighting / largest), minWeight) * weightMultiplier;
+  if (map_pose) {
+    // the map kernels' pose "uniforms" (GlobalModel.cpp:405,562): float casts of T_wc and of its rigid inverse
+    for (int k = 0; k < 16; ++k) {
+      map_pose->pose[k] = (float)gn->T_wc[k];
+      map_pose->t_inv[k] = (float)inv[k];
+    }
+  }
 }
 
 // k_gn_finish needs the pre-tracking pose; stash it (tracking overwrites T_wc only at the end, so this is only needed
@@ -419,12 +426,28 @@ __device__ __forceinline__ void accumulate29(const float row[7], float (&acc)[29
   acc[28] += 1.0f;
 }
 
+// a / z and b / z, both correctly rounded: the instruction sequence of an IEEE fp32 division (reciprocal estimate, one
+// Newton step, quotient, remainder, correction) with the refined reciprocal shared by the two quotients. Exact for finite
+// operands away from the denormal / overflow ranges, which is where depths in metres and pixel coordinates live; z == 0
+// (where the reference divides by zero) is rejected by the caller.
+__device__ __forceinline__ void div2_rn(float a, float b, float z, float& qa, float& qb) {
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(z));
+  const float e = __fmaf_rn(-z, r0, 1.0f);
+  const float r = __fmaf_rn(r0, e, r0);
+  const float qa0 = __fmul_rn(a, r), qb0 = __fmul_rn(b, r);
+  qa = __fmaf_rn(r, __fmaf_rn(-z, qa0, a), qa0);
+  qb = __fmaf_rn(r, __fmaf_rn(-z, qb0, b), qb0);
+}
+
 // projective association of one live vertex: s = its position in the previous camera; returns the model pixel or -1
 __device__ __forceinline__ int icp_project(const IcpFrame& F, const f3& vcurr, int rows, int cols, f3& s) {
   s = mul(F.M, vcurr) + F.t;
-  const int ux = __float2int_rn(s.x * F.fx / s.z + F.cx);
-  const int uy = __float2int_rn(s.y * F.fy / s.z + F.cy);
-  if (ux < 0 || uy < 0 || ux >= cols || uy >= rows || s.z < 0) return -1;
+  float px, py;
+  div2_rn(s.x * F.fx, s.y * F.fy, s.z, px, py);
+  const int ux = __float2int_rn(px + F.cx);
+  const int uy = __float2int_rn(py + F.cy);
+  if (ux < 0 || uy < 0 || ux >= cols || uy >= rows || !(s.z > 0)) return -1;
   return uy * cols + ux;
 }
 
@@ -528,19 +551,26 @@ __device__ __forceinline__ void iter1_body(const OdomDev& od, int level, int do_
         const float4 nz4 = *reinterpret_cast<const float4*>(nc + 2 * plane + i0);
         const float vxs[4] = {vx4.x, vx4.y, vx4.z, vx4.w}, vys[4] = {vy4.x, vy4.y, vy4.z, vy4.w}, vzs[4] = {vz4.x, vz4.y, vz4.z, vz4.w};
         const float nxs[4] = {nx4.x, nx4.y, nx4.z, nx4.w}, nys[4] = {ny4.x, ny4.y, ny4.z, ny4.w}, nzs[4] = {nz4.x, nz4.y, nz4.z, nz4.w};
+        // all four projections first, then all 24 gathers in flight together (the pass is bound by memory round trips, not
+        // by issue slots: measured 17.8 -> 15.9 us at 1280x960 against gathering pixel pairs)
+        f3 sv[4];
+        int qv[4];
+        float gm[4][6];
 #pragma unroll
-        for (int h = 0; h < 4; h += 2) {
-          f3 s0, s1;
-          const int q0 = icp_project(F, mk3(vxs[h], vys[h], vzs[h]), rows, cols, s0);
-          const int q1 = icp_project(F, mk3(vxs[h + 1], vys[h + 1], vzs[h + 1]), rows, cols, s1);
-          const int a0 = q0 < 0 ? 0 : q0, a1 = q1 < 0 ? 0 : q1;
-          const float p00 = __ldg(vp + a0), p01 = __ldg(vp + plane + a0), p02 = __ldg(vp + 2 * plane + a0);
-          const float p03 = __ldg(np_ + a0), p04 = __ldg(np_ + plane + a0), p05 = __ldg(np_ + 2 * plane + a0);
-          const float p10 = __ldg(vp + a1), p11 = __ldg(vp + plane + a1), p12 = __ldg(vp + 2 * plane + a1);
-          const float p13 = __ldg(np_ + a1), p14 = __ldg(np_ + plane + a1), p15 = __ldg(np_ + 2 * plane + a1);
-          if (q0 >= 0) icp_accumulate(F, s0, mk3(nxs[h], nys[h], nzs[h]), mk3(p00, p01, p02), mk3(p03, p04, p05), acc);
-          if (q1 >= 0) icp_accumulate(F, s1, mk3(nxs[h + 1], nys[h + 1], nzs[h + 1]), mk3(p10, p11, p12), mk3(p13, p14, p15), acc);
+        for (int h = 0; h < 4; ++h) qv[h] = icp_project(F, mk3(vxs[h], vys[h], vzs[h]), rows, cols, sv[h]);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int a = qv[h] < 0 ? 0 : qv[h];
+          gm[h][0] = __ldg(vp + a);
+          gm[h][1] = __ldg(vp + plane + a);
+          gm[h][2] = __ldg(vp + 2 * plane + a);
+          gm[h][3] = __ldg(np_ + a);
+          gm[h][4] = __ldg(np_ + plane + a);
+          gm[h][5] = __ldg(np_ + 2 * plane + a);
         }
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+          if (qv[h] >= 0) icp_accumulate(F, sv[h], mk3(nxs[h], nys[h], nzs[h]), mk3(gm[h][0], gm[h][1], gm[h][2]), mk3(gm[h][3], gm[h][4], gm[h][5]), acc);
       }
     } else {
       for (int i = gid; i < N; i += gstride) {
@@ -1002,7 +1032,12 @@ inline int red_blocks(const EfContext* ctx, int n_items, int per_thread, int thr
   int b = (n_items + threads * per_thread - 1) / (threads * per_thread);
   int cap = ctx->num_sms * ctas_per_sm;  // one resident wave
   if (cap > MAX_RED_BLOCKS) cap = MAX_RED_BLOCKS;
-  if (b > cap) b = cap;
+  if (b > cap) {
+    // more work than one wave: every thread makes the same number of grid-stride rounds (1280x960: 600 CTAs x 4 rounds
+    // instead of 740 CTAs of which a quarter would run a 4th round alone)
+    const int rounds = (b + cap - 1) / cap;
+    b = (b + rounds - 1) / rounds;
+  }
   if (b < 1) b = 1;
   return b;
 }
@@ -1071,7 +1106,7 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
 
 int odom_finish_async(EfContext* ctx, int which, float weightMultiplier, bool have_track) {
   OdomDev& od = ctx->odom[which];
-  EF_LAUNCH(ctx, k_gn_finish, 1, 32, 0, od.gn, weightMultiplier, have_track ? 1 : 0);
+  EF_LAUNCH(ctx, k_gn_finish, 1, 32, 0, od.gn, weightMultiplier, have_track ? 1 : 0, which == 0 ? ctx->map.pose : (MapPose*)nullptr);
   EF_CHECK_LAST();
   return 0;
 }
