@@ -30,6 +30,7 @@ int launch_rgb_residual_raw(EfContext* ctx, int which, int level);
 int launch_icp_dense_only(EfContext* ctx, int which, int level);
 int launch_so3_raw(EfContext* ctx, int which);
 int launch_sobel(EfContext* ctx, int which);
+int odom_so3_async(EfContext* ctx, int which);
 int preprocess_depth(EfContext* ctx, const uint16_t* raw, float cutoff, uint16_t* filtered, float* metric, float* metric_filtered);
 int rgb_to_rgba(EfContext* ctx, const uint8_t* rgb, uint8_t* rgba);
 
@@ -182,6 +183,11 @@ static int alloc_odom(EfContext* ctx, OdomDev& od) {
   CU(A->alloc(&od.vmaps_tmp, 4 * n0));
   CU(cudaMemsetAsync(od.vmaps_tmp, 0, 4 * n0 * sizeof(float), ctx->stream));
   CU(A->alloc(&od.gn, 1));
+  CU(A->alloc(&od.so3s, 1));
+  CU(A->alloc(&od.so3_partials, (size_t)MAX_RGB_BLOCKS * PARTIAL_STRIDE));
+  CU(A->alloc(&od.so3_counter, 4));
+  CU(cudaMemsetAsync(od.so3s, 0, sizeof(So3State), ctx->stream));
+  CU(cudaMemsetAsync(od.so3_counter, 0, 16, ctx->stream));
   CU(A->alloc(&od.partials, (size_t)MAX_RED_BLOCKS * PARTIAL_STRIDE));
   CU(A->alloc(&od.partials_rgb, (size_t)MAX_RGB_BLOCKS * 32));
   CU(A->alloc(&od.partials2, (size_t)MAX_RGB_BLOCKS * 32));
@@ -270,6 +276,7 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
     ctx->own_stream = true;
   }
   ctx->launches = 0;
+  ctx->so3_ready = false;
   {
     const char* e = getenv("EF_NO_PDL");
     ctx->pdl = !(e && e[0] == '1');
@@ -347,11 +354,15 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
         cudaMemsetAsync(la.nmap_curr[i], 0xff, 3 * ni * sizeof(float), ctx->stream);
       }
     }
+    TA(la.so3s, 1);
+    TA(la.so3_partials, (size_t)MAX_RGB_BLOCKS * PARTIAL_STRIDE);
+    TA(la.so3_counter, 4);
     if (!rc) {
       cudaError_t e = cudaStreamCreateWithFlags(&la.stream, cudaStreamNonBlocking);
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(&la.ready, cudaEventDisableTiming);
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(&la.spare_free, cudaEventDisableTiming);
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(&la.h2d_done, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&la.image_ready, cudaEventDisableTiming);
       if (e == cudaSuccess) e = cudaMallocHost((void**)&la.pin_rgb, n * 3);
       if (e == cudaSuccess) e = cudaMallocHost((void**)&la.pin_depth, n * 2);
       if (e != cudaSuccess) rc = (int)e;
@@ -369,6 +380,7 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
   if (!rc) {
     cudaError_t e = cudaEventRecord(ctx->la.spare_free, ctx->stream);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->la.h2d_done, ctx->la.stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->la.image_ready, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = (int)e;
   }
@@ -391,6 +403,7 @@ extern "C" int ef_destroy(EfContext* ctx) {
   if (ctx->la.ready) cudaEventDestroy(ctx->la.ready);
   if (ctx->la.spare_free) cudaEventDestroy(ctx->la.spare_free);
   if (ctx->la.h2d_done) cudaEventDestroy(ctx->la.h2d_done);
+  if (ctx->la.image_ready) cudaEventDestroy(ctx->la.image_ready);
   if (ctx->la.pin_rgb) cudaFreeHost(ctx->la.pin_rgb);
   if (ctx->la.pin_depth) cudaFreeHost(ctx->la.pin_depth);
   map_free_host(ctx);
@@ -699,13 +712,17 @@ extern "C" int ef_rgb_step(EfContext* ctx, int which, int level, float sigma, fl
 extern "C" int ef_so3_step(EfContext* ctx, int which, const float* image_basis, const float* kinv, const float* krlr, float* A9, float* b3,
                            float* residual2) {
   if (!ctx || !WHICH_OK(which) || !image_basis || !kinv || !krlr || !A9 || !b3 || !residual2) return EF_EINVAL;
-  RC(upload_gn(ctx, which, offsetof(GNState, imageBasis), image_basis, 36));
-  RC(upload_gn(ctx, which, offsetof(GNState, kinv), kinv, 36));
-  RC(upload_gn(ctx, which, offsetof(GNState, krlr), krlr, 36));
+  char* sdev = (char*)ctx->odom[which].so3s;
+  CU(cudaMemcpyAsync(sdev + offsetof(So3State, imageBasis), image_basis, 36, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(sdev + offsetof(So3State, kinv), kinv, 36, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(sdev + offsetof(So3State, krlr), krlr, 36, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   RC(launch_so3_raw(ctx, which));
-  GNState g;
-  RC(download_gn(ctx, which, &g));
+  struct {
+    float sum_so3[12];
+  } g;
+  CU(cudaMemcpyAsync(g.sum_so3, sdev + offsetof(So3State, sum_so3), sizeof(g.sum_so3), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   int shift = 0;
   for (int i = 0; i < 3; ++i)
     for (int j = i; j < 4; ++j) {
@@ -870,6 +887,14 @@ static int frame_input_side(EfContext* ctx, const uint8_t* rgb_dev, const uint16
   // frameToModel.initICP(filtered depth) and the intensity half of initRGB, ElasticFusion.cpp:318-319
   RC(odom_init_icp_depth(ctx, 0, t.depth_filtered, ctx->max_depth_processed));
   RC(odom_populate(ctx, 0, t.rgba, nullptr, ctx->odom[0].nextImage, false));
+  // SO(3) pre-alignment (RGBDOdometry.cpp:305-368): needs only this intensity pyramid and the previous frame's
+  // (lastNextImage), so it belongs to the input side. Not for the first frame (nothing is tracked, ElasticFusion.cpp:290).
+  ctx->so3_ready = false;
+  if (ctx->so3 && ctx->tick > 1) {
+    RC(odom_so3_async(ctx, 0));
+    ctx->so3_ready = true;
+  }
+  CU(cudaEventRecord(ctx->la.image_ready, ctx->stream));  // this pyramid is the next frame's lastNextImage
   return 0;
 }
 
@@ -889,6 +914,10 @@ static void swap_sides(EfContext* ctx) {
     std::swap(od.nmap_curr[i], la.nmap_curr[i]);
     std::swap(od.nextImage[i], la.image[i]);
   }
+  std::swap(od.so3s, la.so3s);
+  std::swap(od.so3_partials, la.so3_partials);
+  std::swap(od.so3_counter, la.so3_counter);
+  std::swap(ctx->so3_ready, la.so3_ready);
 }
 
 // rgb/depth: device pointers, or pinned host staging when from_host
@@ -901,6 +930,7 @@ static int prefetch_common(EfContext* ctx, const uint8_t* rgb, const uint16_t* d
   ctx->stream = la.stream;
   int rc = 0;
   cudaError_t e = cudaStreamWaitEvent(la.stream, la.spare_free, 0);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(la.stream, la.image_ready, 0);  // previous frame's intensity pyramid (SO(3) input)
   if (e == cudaSuccess && from_host) {
     e = cudaMemcpyAsync(ctx->tex.rgb, rgb, n * 3, cudaMemcpyHostToDevice, la.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->tex.depth_raw, depth, n * 2, cudaMemcpyHostToDevice, la.stream);
@@ -989,6 +1019,7 @@ extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, c
       CU(cudaStreamSynchronize(ctx->stream));
       memcpy((char*)ctx->pin_small + 4096, in_T_wc, sizeof(double) * 16);
       CU(cudaMemcpyAsync((char*)ctx->dev_small + 4096, (char*)ctx->pin_small + 4096, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
+      ctx->so3_ready = false;  // no tracking for this frame: the SO(3) result of its input side is not used
       RC(odom_set_pose_async(ctx, 0, (const double*)((char*)ctx->dev_small + 4096)));
       RC(odom_finish_async(ctx, 0, weight_multiplier, false));
     }

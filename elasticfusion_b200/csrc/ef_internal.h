@@ -33,18 +33,13 @@ struct GNState {
   float Rcurr[9], tcurr[3];
   float Mcp[9], tcp[3];  // current camera -> previous camera: R_prev^-1 R_curr, R_prev^-1 (t_curr - t_prev) (= the inverse increment)
   double resultRt[16];
-  double resultR[9], lastResultR[9];
-  float R_lr[9];
-  float so3_lastError, so3_lastCount;
-  int so3_done;
   int break_level;  // rgbOnly early exit of one pyramid level's loop (-1: none)
 
   float krkinv[9], kt[3];                  // inputs of the next photometric residual pass
-  float imageBasis[9], kinv[9], krlr[9];   // inputs of the next SO3 pass
   float sigmaVal;
   int rgbSize, sigma;
 
-  float sum_icp[32], sum_rgb[32], sum_so3[12];  // last reduced systems (reference JtJJtrSE3 / JtJJtrSO3 order)
+  float sum_icp[32], sum_rgb[32];  // last reduced systems (reference JtJJtrSE3 order)
   int sum_res[2];                               // last {count, sigma} of the residual pass
   unsigned int res_acc[2];                      // accumulators of the running residual pass (re-armed by k_iter2)
 
@@ -58,6 +53,22 @@ struct GNState {
   float rgbErrBuf[2];           // rgbError of the previous / current iteration (double-buffered across CTAs)
   float weighting;  // velocity weighting for fusion (ElasticFusion.cpp:369-383)
   long long dbg[32];  // phase timestamps (clock64) when built with -DEF_PROFILE_PHASES
+};
+
+// State of the SO(3) pre-alignment loop (RGBDOdometry.cpp:305-368). The loop depends only on the two intensity pyramids
+// (previous and current frame, level 2) -- not on the map, not on the pose -- so it has its own block, one per buffer set,
+// and runs with the rest of the frame's input side (on the look-ahead stream when the frame was prefetched).
+constexpr int SO3_MAX_ITER = 10;
+struct So3State {
+  double resultR[9], lastResultR[9];
+  float R_lr[9];
+  float imageBasis[9], kinv[9], krlr[9];  // inputs of the next pass
+  float so3_lastError, so3_lastCount;
+  int so3_done;
+  float sum_so3[12];                      // last reduced system (reference JtJJtrSO3 order)
+  float lastSO3Error, lastSO3Count;
+  int trace_n;
+  EfSolveTrace trace[SO3_MAX_ITER];
 };
 
 // pose matrices consumed by the map kernels (float, as the reference's shader uniforms)
@@ -89,6 +100,9 @@ struct OdomDev {
   int level_start[NUM_PYRS + 1];  // flat pixel offset of each level
 
   GNState* gn;
+  So3State* so3s;             // SO(3) loop state + its own partials / ticket (it may run concurrently with the GN loop of
+  float* so3_partials;        // the previous frame)
+  unsigned int* so3_counter;
   float* partials;        // MAX_RED_BLOCKS * PARTIAL_STRIDE (geometric system, one slot per CTA of the dense pass)
   double* partials2;      // MAX_RGB_BLOCKS * 32: second-level sums of `partials`, one slot per CTA of the candidate pass
   float* partials_rgb;    // MAX_RGB_BLOCKS * 32 (photometric system, one slot per CTA of the candidate pass)
@@ -149,6 +163,7 @@ struct Lookahead {
   cudaEvent_t ready;       // side stream: the spare set is complete
   cudaEvent_t spare_free;  // main stream: every reader of the spare set precedes this point
   cudaEvent_t h2d_done;    // side stream: the pinned staging buffers may be rewritten
+  cudaEvent_t image_ready; // whichever stream built the newest intensity pyramid (the next frame's SO(3) loop reads it)
   bool pending;            // a prefetched frame is waiting to be consumed
   uint8_t *rgb, *rgba;
   uint16_t *depth_raw, *depth_filtered;
@@ -156,6 +171,10 @@ struct Lookahead {
   uint16_t* depth_tmp[NUM_PYRS];
   float *vmap_curr[NUM_PYRS], *nmap_curr[NUM_PYRS];
   uint8_t* image[NUM_PYRS];
+  So3State* so3s;
+  float* so3_partials;
+  unsigned int* so3_counter;
+  bool so3_ready;          // the spare set holds a finished SO(3) loop for its frame
   uint8_t* pin_rgb;
   uint16_t* pin_depth;
 };
@@ -178,6 +197,7 @@ struct EfContext {
   ef::MapDev map;
   ef::Textures tex;
   ef::Lookahead la;
+  bool so3_ready;  // the live set of odom[0] holds a finished SO(3) loop for the frame about to be tracked
 
   // host mirrors
   int tick;

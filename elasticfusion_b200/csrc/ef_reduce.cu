@@ -73,16 +73,32 @@ __device__ void gn_prepare_warp(GNState* gn, int level) {
 }
 
 // homography etc. for the next SO3 pass (RGBDOdometry.cpp:309-321)
-__device__ void so3_prepare(GNState* gn) {
+__device__ void so3_prepare(So3State* s, const GNState* gn) {
   double K[9], Kinv[9], tmp[9], H[9];
-  level_K(gn, 2, K, Kinv);
-  efm::mul3(K, gn->resultR, tmp);
+  level_K(gn, 2, K, Kinv);  // (constant after context creation)
+  efm::mul3(K, s->resultR, tmp);
   efm::mul3(tmp, Kinv, H);
   for (int k = 0; k < 9; ++k) {
-    gn->imageBasis[k] = (float)H[k];
-    gn->kinv[k] = (float)Kinv[k];
-    gn->krlr[k] = (float)tmp[k];
+    s->imageBasis[k] = (float)H[k];
+    s->kinv[k] = (float)Kinv[k];
+    s->krlr[k] = (float)tmp[k];
   }
+}
+// start of the SO(3) loop (RGBDOdometry.cpp:284-303)
+__global__ void k_so3_begin(So3State* s, const GNState* gn) {
+  pdl_enter();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int k = 0; k < 9; ++k) {
+    s->resultR[k] = I3[k];
+    s->lastResultR[k] = I3[k];
+    s->R_lr[k] = (float)I3[k];
+  }
+  s->so3_lastError = FLT_MAX / 2;
+  s->so3_lastCount = FLT_MAX / 2;
+  s->so3_done = 0;
+  s->trace_n = 0;
+  so3_prepare(s, gn);
 }
 
 // start of getIncrementalTransformation (RGBDOdometry.cpp:266-273,284-303)
@@ -101,31 +117,36 @@ __device__ void gn_begin_body(GNState* gn, int rgbOnly, float icpWeight, int so3
   for (int k = 0; k < 9; ++k) gn->Mcp[k] = (k % 4 == 0) ? 1.f : 0.f;  // Rcurr = Rprev, tcurr = tprev
   for (int k = 0; k < 3; ++k) gn->tcp[k] = 0.f;
   efm::inv3<float>(gn->Rprev, gn->Rprev_inv);
-  const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-  for (int k = 0; k < 9; ++k) {
-    gn->resultR[k] = I3[k];
-    gn->lastResultR[k] = I3[k];
-    gn->R_lr[k] = (float)I3[k];
-  }
-  gn->so3_lastError = FLT_MAX / 2;
-  gn->so3_lastCount = FLT_MAX / 2;
-  gn->so3_done = 0;
   gn->break_level = -1;
   gn->trace_n = 0;
-  if (so3) so3_prepare(gn);
 }
-__global__ void k_gn_begin(GNState* gn, int rgbOnly, float icpWeight, int so3) {
+// One warp: lane 0 starts getIncrementalTransformation; all lanes copy the records and results of the SO(3) loop (which ran
+// before, possibly on the look-ahead stream) into the tracker's trace / statistics.
+__global__ void k_gn_begin(GNState* gn, int rgbOnly, float icpWeight, int so3, const So3State* s, EfSolveTrace* trace) {
   pdl_enter();
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  gn_begin_body(gn, rgbOnly, icpWeight, so3);
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  if (threadIdx.x == 0) {
+    gn_begin_body(gn, rgbOnly, icpWeight, so3);
+    if (so3) {
+      gn->lastSO3Error = s->lastSO3Error;
+      gn->lastSO3Count = s->lastSO3Count;
+      gn->trace_n = trace ? s->trace_n : 0;
+    }
+  }
+  if (so3 && trace) {
+    const int words = s->trace_n * (int)(sizeof(EfSolveTrace) / 4);
+    const int* src = reinterpret_cast<const int*>(s->trace);
+    int* dst = reinterpret_cast<int*>(trace);
+    for (int k = threadIdx.x; k < words; k += 32) dst[k] = src[k];
+  }
 }
 
 // after the SO3 loop: seed resultRt (RGBDOdometry.cpp:379-388) and prepare the first SE3 iteration
-__device__ void gn_seed_body(GNState* gn, int first_level) {
+__device__ void gn_seed_body(GNState* gn, int first_level, const So3State* s) {
   for (int k = 0; k < 16; ++k) gn->resultRt[k] = (k % 5 == 0) ? 1.0 : 0.0;
   if (gn->so3)
     for (int x = 0; x < 3; x++)
-      for (int y = 0; y < 3; y++) gn->resultRt[x * 4 + y] = gn->resultR[x * 3 + y];
+      for (int y = 0; y < 3; y++) gn->resultRt[x * 4 + y] = s->resultR[x * 3 + y];
   gn->lastRGBError = FLT_MAX;
   if (!gn->rgb) {
     gn->rgbSize = 0;
@@ -136,10 +157,10 @@ __device__ void gn_seed_body(GNState* gn, int first_level) {
   }
   gn_prepare_warp(gn, first_level);
 }
-__global__ void k_gn_seed(GNState* gn, int first_level) {
+__global__ void k_gn_seed(GNState* gn, int first_level, const So3State* s) {
   pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  gn_seed_body(gn, first_level);
+  gn_seed_body(gn, first_level, s);
 }
 
 // end of getIncrementalTransformation (RGBDOdometry.cpp:555-570) + velocity weighting (ElasticFusion.cpp:369-383)
@@ -905,7 +926,7 @@ __device__ __forceinline__ void so3_gradient(const uint8_t* img, int cols, int x
 // per-CTA partial of one SO3 step (11 floats into od.partials[vb])
 template <int THREADS>
 __device__ __forceinline__ void so3_partial(const OdomDev& od, int vb, int nvb, float* sred) {
-  GNState* gn = od.gn;
+  const So3State* gn = od.so3s;
   const int level = 2;
   const int rows = od.rows[level], cols = od.cols[level];
   const int N = rows * cols;
@@ -951,12 +972,12 @@ __device__ __forceinline__ void so3_partial(const OdomDev& od, int vb, int nvb, 
     }
   }
   block_reduce_sum<11, THREADS>(acc, sred);
-  if (threadIdx.x < 11) od.partials[(size_t)vb * PARTIAL_STRIDE + threadIdx.x] = acc[0];
+  if (threadIdx.x < 11) od.so3_partials[(size_t)vb * PARTIAL_STRIDE + threadIdx.x] = acc[0];
 }
 
 // solve + convergence logic of one SO3 step on the reduced system in gn->sum_so3 (one thread)
 __device__ void so3_finish(const OdomDev& od, int iter) {
-  GNState* gn = od.gn;
+  So3State* gn = od.so3s;
   float jtj[9], jtr[3];
   {
     int shift = 0;
@@ -970,8 +991,8 @@ __device__ void so3_finish(const OdomDev& od, int iter) {
       }
   }
   const float res0 = gn->sum_so3[9], res1 = gn->sum_so3[10];
-  if (od.trace && gn->trace_n < MAX_TRACE) {
-    EfSolveTrace& t = od.trace[gn->trace_n++];
+  if (gn->trace_n < SO3_MAX_ITER) {
+    EfSolveTrace& t = gn->trace[gn->trace_n++];
     t.kind = 1;
     t.level = 2;
     t.iter = iter;
@@ -1008,20 +1029,20 @@ __device__ void so3_finish(const OdomDev& od, int iter) {
     gn->R_lr[k] = nr[k];
     gn->resultR[k] = nr[k];
   }
-  so3_prepare(gn);
+  so3_prepare(gn, od.gn);
 }
 
 __global__ void __launch_bounds__(RED_THREADS) k_so3_step(OdomDev od, int iter, int solve) {
   pdl_enter();
-  GNState* gn = od.gn;
-  if (solve && gn->so3_done) return;
+  So3State* st = od.so3s;
+  if (solve && st->so3_done) return;
   __shared__ float sred[32 * (RED_THREADS / 32)];
   __shared__ double dsm[(RED_THREADS / 32) * 32];
   so3_partial<RED_THREADS>(od, blockIdx.x, gridDim.x, sred);
-  if (!last_block_done(od.counter)) return;
-  so3_final_sum<RED_THREADS>(od.partials, gridDim.x, gn->sum_so3, dsm);
+  if (!last_block_done(od.so3_counter)) return;
+  so3_final_sum<RED_THREADS>(od.so3_partials, gridDim.x, st->sum_so3, dsm);
   if (threadIdx.x != 0) return;
-  *od.counter = 0;
+  *od.so3_counter = 0;
   if (!solve) return;
   so3_finish(od, iter);
 }
@@ -1060,6 +1081,16 @@ inline int iter2_blocks(int npx, bool rgb, int nb1) {
 namespace ef {
 
 // the device-resident Gauss-Newton schedule; T_wc in/out lives in gn->T_wc
+// The SO(3) pre-alignment loop of tracker `which` on ctx->stream (its state block, partials and ticket are its own)
+int odom_so3_async(EfContext* ctx, int which) {
+  OdomDev& od = ctx->odom[which];
+  EF_LAUNCH(ctx, k_so3_begin, 1, 32, 0, od.so3s, (const GNState*)od.gn);
+  const int nb = red_blocks(ctx, od.rows[2] * od.cols[2], 1, RED_THREADS, 2);
+  for (int i = 0; i < SO3_MAX_ITER; ++i) EF_LAUNCH(ctx, k_so3_step, nb, RED_THREADS, 0, od, i, 1);
+  EF_CHECK_LAST();
+  return 0;
+}
+
 int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom, bool so3) {
   OdomDev& od = ctx->odom[which];
   const bool icp = !rgbOnly && icpWeight > 0;
@@ -1077,13 +1108,18 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
       sched_iter[ns] = j;
       ++ns;
     }
-  EF_LAUNCH(ctx, k_gn_begin, 1, 32, 0, od.gn, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0);
   if (so3) {
-    const int nb = red_blocks(ctx, od.rows[2] * od.cols[2], 1, RED_THREADS, 2);
-    for (int i = 0; i < 10; ++i) EF_LAUNCH(ctx, k_so3_step, nb, RED_THREADS, 0, od, i, 1);
+    // already done with the frame's input side (frame loop: on the look-ahead stream when the frame was prefetched)?
+    const bool ready = (which == 0) && ctx->so3_ready;
+    if (!ready) {
+      int rc = odom_so3_async(ctx, which);
+      if (rc) return rc;
+    }
   }
+  if (which == 0) ctx->so3_ready = false;
+  EF_LAUNCH(ctx, k_gn_begin, 1, 32, 0, od.gn, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0, (const So3State*)od.so3s, od.trace);
   ef_stage(ctx, 3);
-  EF_LAUNCH(ctx, k_gn_seed, 1, 32, 0, od.gn, ns ? sched_level[0] : 0);
+  EF_LAUNCH(ctx, k_gn_seed, 1, 32, 0, od.gn, ns ? sched_level[0] : 0, (const So3State*)od.so3s);
   for (int s = 0; s < ns; ++s) {
     const int lv = sched_level[s];
     const int npx = od.rows[lv] * od.cols[lv];
