@@ -459,6 +459,7 @@ def main():
         return
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         import torch
         import torch.distributed as dist_mod
 
