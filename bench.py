@@ -96,18 +96,32 @@ def load_peaks():
 
 
 def make_frames(K, n, seed):
+    """First n frames of the synthetic sequence (frame i depends only on (seed, i), so a longer cached run serves any
+    shorter request: the reference arm and repeated runs on one box do not render again)."""
     from elasticfusion_b200 import synth
 
-    cache = f"/tmp/ef_bench_{K.width}x{K.height}_{seed}_{n}.npz"
+    cache = os.path.join(os.environ.get("EF_BENCH_CACHE", "/tmp"), f"ef_bench_{K.width}x{K.height}_{seed}.npz")
+    have_rgb = have_depth = None
     if os.path.exists(cache):
-        z = np.load(cache)
-        return z["rgb"], z["depth"]
+        try:
+            z = np.load(cache)
+            have_rgb, have_depth = z["rgb"], z["depth"]
+        except Exception:
+            have_rgb = have_depth = None
+    m = 0 if have_rgb is None else len(have_rgb)
+    if m >= n:
+        return have_rgb[:n], have_depth[:n]
     rgb = np.empty((n, K.height, K.width, 3), np.uint8)
     depth = np.empty((n, K.height, K.width), np.uint16)
-    for i, (c, d, _) in enumerate(synth.sequence(n, K, seed=seed, noise=True)):
-        rgb[i], depth[i] = c, d
+    if m:
+        rgb[:m], depth[:m] = have_rgb, have_depth
+    traj = synth.trajectory(n, seed=seed)
+    for i in range(m, n):
+        rgb[i], depth[i] = synth.render(traj[i], K, noise_seed=seed * 100003 + i)[:2]
     try:
-        np.savez(cache, rgb=rgb, depth=depth)
+        tmp = cache + f".{os.getpid()}.tmp.npz"
+        np.savez(tmp, rgb=rgb, depth=depth)
+        os.replace(tmp, cache)
     except Exception:
         pass
     return rgb, depth
