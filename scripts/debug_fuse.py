@@ -1,5 +1,6 @@
 import sys, numpy as np
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, '/root/repo/tests')
 from elasticfusion_b200 import synth, capi
 from oracle import ef_oracle as eo
 from util import run_oracle

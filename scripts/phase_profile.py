@@ -1,6 +1,8 @@
-"""Phase timestamps of k_iter1 / k_iter2 at level 0 (library built with -DEF_PROFILE_PHASES)."""
+"""Phase timestamps (%globaltimer) of k_iter1 / k_iter2 at level 0. Needs an instrumented build of the library:
+   EF_OUT=build/libefusion_prof.so ./build.sh -DEF_PROFILE_PHASES ; EF_LIB=build/libefusion_prof.so python scripts/phase_profile.py"""
 import sys, ctypes as C, numpy as np
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from elasticfusion_b200 import synth, capi
 K = synth.K_DEFAULT
 frames = list(synth.sequence(6, K, seed=42, noise=True))
@@ -30,4 +32,3 @@ print("k_iter2 block0: stats %d, rgb+presum %d" % (d[9]-d[8], d[10]-d[9]))
 print("k2 block0 done -> last block has ticket: %d" % (d[11]-d[10]))
 print("k_iter2 last block: final sums %d, stage+lastA %d, ldlt %d, rodrigues %d, rest %d" % (d[12]-d[11], d[13]-d[12], d[14]-d[13], d[15]-d[14], d[16]-d[15]))
 print("k1.start -> k2.end: %d" % (d[16]-d[0]))
-print("persistent loop (block 0): phase A %d, barrier %d, rows %d, rows end->ticket/flag wait start %d, flag wait %d, total iteration %d" % (d[4]-d[0], d[5]-d[4], d[10]-d[5], d[6]-d[10], d[7]-d[6], d[7]-d[0]))

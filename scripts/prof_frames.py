@@ -1,6 +1,7 @@
 """Runs N frames of the 640x480 sequence through ef_process_frame (for ncu captures of the per-frame kernels)."""
 import sys, numpy as np
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from elasticfusion_b200 import synth, capi
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 K = synth.K_DEFAULT

@@ -1,6 +1,7 @@
 """Tracks a few frames at the given resolution, then issues ICP-reduction launches at level 0 (for ncu --set full captures)."""
 import sys, numpy as np
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from elasticfusion_b200 import synth, capi
 scale = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 K = synth.K_DEFAULT.scaled(scale)

@@ -1,6 +1,7 @@
 """Sets up a tracked 640x480 state and runs one full getIncrementalTransformation (for ncu captures)."""
 import sys, numpy as np
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from elasticfusion_b200 import synth, capi
 K = synth.K_DEFAULT
 frames = list(synth.sequence(4, K, seed=42, noise=True))
