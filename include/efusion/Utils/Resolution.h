@@ -1,24 +1,35 @@
-// Drop-in for the reference's Core/Utils/Resolution.h (process-global singleton: the first getInstance(w, h) wins,
-// later arguments are ignored — reference Core/Utils/Resolution.cpp).
+// Image size holder with the reference's call syntax (Core/Utils/Resolution.h: Resolution::getInstance(w, h) once,
+// Resolution::getInstance().width() / rows() / numPixels() afterwards). Process-global; the first call that carries a size
+// fixes it, later arguments are ignored; reading before a size was given aborts with a message.
 #ifndef EFUSION_B200_RESOLUTION_H_
 #define EFUSION_B200_RESOLUTION_H_
-#include <cassert>
+
+#include <cstdio>
+#include <cstdlib>
+
 class Resolution {
+  int dims_[3];  // columns, rows, columns * rows
+  Resolution(int w, int h) : dims_{w, h, w * h} {}
+
+  static const Resolution& fixed(int w, int h) {
+    if (w <= 0 || h <= 0) {
+      std::fprintf(stderr, "Resolution::getInstance(): no image size was given before the first use\n");
+      std::abort();
+    }
+    static const Resolution theOne(w, h);
+    return theOne;
+  }
+
  public:
   static const Resolution& getInstance(int width = 0, int height = 0) {
-    static const Resolution instance(width, height);
-    return instance;
+    static const Resolution& ref = fixed(width, height);
+    return ref;
   }
-  const int& width() const { return imgWidth; }
-  const int& height() const { return imgHeight; }
-  const int& cols() const { return imgWidth; }
-  const int& rows() const { return imgHeight; }
-  const int& numPixels() const { return imgNumPixels; }
-
- private:
-  Resolution(int width, int height) : imgWidth(width), imgHeight(height), imgNumPixels(width * height) {
-    assert(width > 0 && height > 0 && "You haven't initialised the Resolution class!");
-  }
-  const int imgWidth, imgHeight, imgNumPixels;
+  const int& width() const { return dims_[0]; }
+  const int& cols() const { return dims_[0]; }
+  const int& height() const { return dims_[1]; }
+  const int& rows() const { return dims_[1]; }
+  const int& numPixels() const { return dims_[2]; }
 };
-#endif
+
+#endif  // EFUSION_B200_RESOLUTION_H_
