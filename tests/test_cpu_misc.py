@@ -44,6 +44,10 @@ def test_abi_argument_validation_without_gpu():
     assert lib.ef_create(ctypes.byref(cfg), None, ctypes.byref(out)) == -1  # loop closure is out of scope
     assert lib.ef_error_string(-1).decode() == "invalid argument"
     assert lib.ef_sync(None) == -1 and lib.ef_process_frame(None, None, None, 0, ctypes.c_float(1), None) == -1
+    # look-ahead entry points validate their arguments before touching the device as well
+    assert lib.ef_prefetch_frame(None, None, None) == -1 and lib.ef_prefetch_frame_device(None, None, None) == -1
+    assert lib.ef_finish_frame(None) == -1 and lib.ef_process_frame_device(None, None, None, 0, ctypes.c_float(1), None) == -1
+    assert lib.ef_error_string(-3).decode() == "invalid state"
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
