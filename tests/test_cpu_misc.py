@@ -241,3 +241,36 @@ def test_sharding_and_aggregation_gloo_world2():
     assert res[0][1] == [0, 2, 4] and res[1][1] == [1, 3]
     for _, _, agg in res:
         assert agg["frames"] == 50 and agg["seconds"] == 1.0 and agg["fps"] == 50.0
+
+
+def test_every_kernel_waits_on_its_predecessor():
+    """Programmatic dependent launch keeps stream order only if EVERY kernel executes griddepcontrol.wait before it touches
+    memory (ef_device.cuh: pdl_enter): a kernel that skipped it would let its successor start before the predecessor's
+    writes are visible. Source-level guard: the first statement of every __global__ function is pdl_enter()."""
+    import glob
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = 0
+    for path in sorted(glob.glob(os.path.join(root, "elasticfusion_b200", "csrc", "*.cu"))):
+        src = open(path).read()
+        for m in re.finditer(r"__global__", src):
+            depth, k = 0, m.end()
+            while True:  # first '{' outside the parameter list
+                c = src[k]
+                if c == "(":
+                    depth += 1
+                elif c == ")":
+                    depth -= 1
+                elif c == "{" and depth == 0:
+                    break
+                elif c == ";" and depth == 0:
+                    k = -1
+                    break
+                k += 1
+            if k < 0:
+                continue  # declaration
+            body = src[k + 1:k + 200].lstrip()
+            assert body.startswith("pdl_enter();"), (os.path.basename(path), src[m.start():m.start() + 120].split("\n")[0])
+            n += 1
+    assert n >= 35
