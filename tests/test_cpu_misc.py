@@ -270,7 +270,7 @@ def test_every_kernel_waits_on_its_predecessor():
                 k += 1
             if k < 0:
                 continue  # declaration
-            body = src[k + 1:k + 200].lstrip()
+            body = re.sub(r"//[^\n]*\n|/\*.*?\*/", "", src[k + 1:k + 1200], flags=re.S).lstrip()  # comments may precede it
             assert body.startswith("pdl_enter();"), (os.path.basename(path), src[m.start():m.start() + 120].split("\n")[0])
             n += 1
     assert n >= 35
