@@ -120,11 +120,14 @@ __device__ void gn_begin_body(GNState* gn, int rgbOnly, float icpWeight, int so3
   gn->break_level = -1;
   gn->trace_n = 0;
 }
-// One warp: lane 0 starts getIncrementalTransformation; all lanes copy the records and results of the SO(3) loop (which ran
-// before, possibly on the look-ahead stream) into the tracker's trace / statistics.
-__global__ void k_gn_begin(GNState* gn, int rgbOnly, float icpWeight, int so3, const So3State* s, EfSolveTrace* trace) {
+// One CTA: thread 0 starts getIncrementalTransformation; all threads copy the records of the SO(3) loop (which ran before,
+// possibly on the look-ahead stream) into the tracker's trace (a few hundred words: one or two per thread, so the copy is
+// one memory round trip instead of a serial chain).
+constexpr int GN_BEGIN_THREADS = 256;
+__global__ void __launch_bounds__(GN_BEGIN_THREADS) k_gn_begin(GNState* gn, int rgbOnly, float icpWeight, int so3, const So3State* s,
+                                                               EfSolveTrace* trace) {
   pdl_enter();
-  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  if (blockIdx.x != 0) return;
   if (threadIdx.x == 0) {
     gn_begin_body(gn, rgbOnly, icpWeight, so3);
     if (so3) {
@@ -137,7 +140,7 @@ __global__ void k_gn_begin(GNState* gn, int rgbOnly, float icpWeight, int so3, c
     const int words = s->trace_n * (int)(sizeof(EfSolveTrace) / 4);
     const int* src = reinterpret_cast<const int*>(s->trace);
     int* dst = reinterpret_cast<int*>(trace);
-    for (int k = threadIdx.x; k < words; k += 32) dst[k] = src[k];
+    for (int k = threadIdx.x; k < words; k += GN_BEGIN_THREADS) dst[k] = src[k];
   }
 }
 
@@ -1117,7 +1120,7 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
     }
   }
   if (which == 0) ctx->so3_ready = false;
-  EF_LAUNCH(ctx, k_gn_begin, 1, 32, 0, od.gn, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0, (const So3State*)od.so3s, od.trace);
+  EF_LAUNCH(ctx, k_gn_begin, 1, GN_BEGIN_THREADS, 0, od.gn, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0, (const So3State*)od.so3s, od.trace);
   ef_stage(ctx, 3);
   EF_LAUNCH(ctx, k_gn_seed, 1, 32, 0, od.gn, ns ? sched_level[0] : 0, (const So3State*)od.so3s);
   for (int s = 0; s < ns; ++s) {
