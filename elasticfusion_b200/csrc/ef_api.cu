@@ -265,15 +265,23 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
   EfContext* ctx = full;
   ctx->cfg = *cfg;
   ctx->device = cfg->device;
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, cfg->device));
-  ctx->num_sms = prop.multiProcessorCount;
-  if (stream) {
-    ctx->stream = (cudaStream_t)stream;
+  {
+    int sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    ctx->num_sms = sms;
     ctx->own_stream = false;
-  } else {
-    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    ctx->own_stream = true;
+    if (e == cudaSuccess) {
+      if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+      } else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        ctx->own_stream = (e == cudaSuccess);
+      }
+    }
+    if (e != cudaSuccess) {  // nothing else has been allocated yet
+      delete full;
+      return (int)e;
+    }
   }
   ctx->launches = 0;
   ctx->so3_ready = false;
@@ -647,11 +655,11 @@ extern "C" int ef_icp_step_async(EfContext* ctx, int which, int level, const flo
   if (!ctx || !WHICH_OK(which) || level < 0 || level >= NUM_PYRS) return EF_EINVAL;
   if (Rcurr) {
     float* s = (float*)ctx->pin_small;
+    CU(cudaStreamSynchronize(ctx->stream));  // the H2D copies of the previous call may still be reading the staging buffer
     memcpy(s, Rcurr, 36);
     memcpy(s + 9, tcurr, 12);
     memcpy(s + 12, Rprev_inv, 36);
     memcpy(s + 21, tprev, 12);
-    CU(cudaStreamSynchronize(ctx->stream));  // staging buffer reuse
     RC(upload_gn(ctx, which, offsetof(GNState, Rcurr), s, 36));
     RC(upload_gn(ctx, which, offsetof(GNState, tcurr), s + 9, 12));
     RC(upload_gn(ctx, which, offsetof(GNState, Rprev_inv), s + 12, 36));
@@ -1064,6 +1072,7 @@ extern "C" int ef_process_frame(EfContext* ctx, const uint8_t* rgb, const uint16
     RC(ef_process_frame_device(ctx, nullptr, nullptr, timestamp, weight_multiplier, in_T_wc));  // prefetched frame
     return ef_finish_frame(ctx);
   }
+  if (ctx->la.pending) return EF_ESTATE;  // a prefetched frame must be consumed first; nothing has been touched yet
   const size_t n = (size_t)ctx->cfg.width * ctx->cfg.height;
   // the staging buffers may still be in flight from the previous frame
   CU(cudaStreamSynchronize(ctx->stream));

@@ -318,7 +318,10 @@ __global__ void k_index_scatter(const float4* __restrict__ pos_conf, const float
     if (px < 0 || py < 0 || px >= cols || py >= rows) continue;
     const unsigned int d24 = depth24(0.5f * zn + 0.5f);
     if (d24 >= 16777215u) continue;
-    atomicMin(&zbuf[(size_t)py * cols + px], ((unsigned long long)d24 << 32) | (unsigned int)id);
+    const unsigned long long key = ((unsigned long long)d24 << 32) | (unsigned int)id;
+    unsigned long long* slot = &zbuf[(size_t)py * cols + px];
+    if (__ldcg(slot) <= key) continue;  // cannot win (the slot only ever decreases): no atomic
+    atomicMin(slot, key);
   }
 }
 
@@ -583,50 +586,207 @@ __device__ __forceinline__ bool clean_test(const CleanArgs& a, const MapPose* mp
   return test > 0;
 }
 
-__global__ void k_clean_flags(CleanArgs a, const MapPose* __restrict__ mp, const float4* __restrict__ pos_conf,
-                              const float4* __restrict__ color_time, const float4* __restrict__ norm_rad, const int* __restrict__ count,
-                              const float4* __restrict__ new_pos, const float4* __restrict__ new_col, const float4* __restrict__ new_nr,
-                              const int* __restrict__ new_count, uint8_t* __restrict__ flags) {
-  pdl_enter();
-  const int n_old = *count, total = n_old + *new_count;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
-    float4 pos, col, nr;
-    if (k < n_old) {
-      pos = pos_conf[k];
-      col = color_time[k];
-      nr = norm_rad[k];
-    } else {
-      pos = new_pos[k - n_old];
-      col = new_col[k - n_old];
-      nr = new_nr[k - n_old];
-    }
-    flags[k] = clean_test(a, mp, pos, col, nr) ? 1 : 0;
-  }
+// ---- TMA-style 1-D bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier, used to stage surfel tiles in shared memory ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is signalled on `bar` (complete_tx)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
-__global__ void k_clean_scatter(int time, const float4* __restrict__ pos_conf, const float4* __restrict__ color_time,
-                                const float4* __restrict__ norm_rad, const int* __restrict__ count, const float4* __restrict__ new_pos,
-                                const float4* __restrict__ new_col, const float4* __restrict__ new_nr, const int* __restrict__ new_count,
-                                const uint8_t* __restrict__ flags, const int* __restrict__ offsets, const int* __restrict__ total_kept,
-                                int capacity, float4* __restrict__ out_pos, float4* __restrict__ out_col, float4* __restrict__ out_nr,
-                                int* __restrict__ out_count) {
+// clean in ONE launch: copy_unstable.vert's keep/cull test, the order-preserving compaction (transform feedback) and the
+// append of this frame's new surfels, as a single-pass decoupled look-back stream compaction over tiles of CC_TILE surfels.
+//  * persistent CTAs draw tiles from a dispenser; each tile (3 x 16 KB of float4, or its old-map / new-surfel parts) is
+//    staged in shared memory by 1-D bulk copies (cp.async.bulk + mbarrier complete_tx), double buffered: the next tile's
+//    copies are in flight while the current one is tested;
+//  * IN PLACE: tile t publishes its aggregate only after its input is resident in shared memory, and a tile learns its
+//    output offset only from the published states of all its predecessors -- so when it writes [prefix, prefix + kept), which
+//    lies inside the input ranges of tiles <= t, every one of those has already been read. Surfels that do not move (nothing
+//    culled before them: the common case for the old, stable bulk of a map sorted by init time) are not written at all:
+//    48 B read per surfel and no write, against 48 + 48 for the reference's VBO-to-VBO pass (GlobalModel.cpp:527-671);
+//  * the last CTA to leave publishes the new count and clears the new-surfel count (GlobalModel.cpp:667-670).
+constexpr int CC_THREADS = 256, CC_ITEMS = 4, CC_TILE = CC_THREADS * CC_ITEMS;
+struct CcStage {
+  float4 pos[CC_TILE], col[CC_TILE], nr[CC_TILE];
+};
+struct CcShared {
+  CcStage st[2];
+  unsigned long long bar[2];
+  int warp_cnt[CC_ITEMS * (CC_THREADS / 32)];
+  int warp_excl[CC_ITEMS * (CC_THREADS / 32)];
+  int next_tile, prefix, aggregate;
+};
+
+__global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const MapPose* __restrict__ mp, float4* pos_conf, float4* color_time,
+                                                              float4* norm_rad, int* count, const float4* __restrict__ new_pos,
+                                                              const float4* __restrict__ new_col, const float4* __restrict__ new_nr,
+                                                              int* new_count, int capacity, unsigned long long* state, unsigned int* counter,
+                                                              int* total_out, unsigned int epoch) {
   pdl_enter();
+  extern __shared__ __align__(128) unsigned char cc_smem_raw[];
+  CcShared& S = *reinterpret_cast<CcShared*>(cc_smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n_old = *count, total = n_old + *new_count;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = min(*total_kept, capacity);
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
-    if (!flags[k]) continue;
-    const int o = offsets[k];
-    if (o >= capacity) continue;
-    if (k < n_old) {
-      out_pos[o] = pos_conf[k];
-      out_col[o] = color_time[k];
-      out_nr[o] = norm_rad[k];
-    } else {
-      float4 col = new_col[k - n_old];
-      if (col.w == -2) col.w = (float)time;  // copy_unstable.vert:114-117
-      out_pos[o] = new_pos[k - n_old];
-      out_col[o] = col;
-      out_nr[o] = new_nr[k - n_old];
+  const int num_tiles = (total + CC_TILE - 1) / CC_TILE;
+  const unsigned long long tag = (unsigned long long)epoch << 34;
+  if (tid == 0) {
+    mbar_init(&S.bar[0], 1);
+    mbar_init(&S.bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // stage tile `t` into buffer `s` (one thread): the part below n_old comes from the map, the rest from the new-surfel arrays
+  auto issue = [&](int t, int s) {
+    const int g0 = t * CC_TILE;
+    const int n_in = min(CC_TILE, total - g0);
+    int n_a = n_old - g0;
+    n_a = n_a < 0 ? 0 : (n_a > n_in ? n_in : n_a);
+    const int n_b = n_in - n_a;
+    mbar_expect_tx(&S.bar[s], (uint32_t)n_in * 48u);
+    CcStage& st = S.st[s];
+    if (n_a > 0) {
+      bulk_g2s(st.pos, pos_conf + g0, (uint32_t)n_a * 16u, &S.bar[s]);
+      bulk_g2s(st.col, color_time + g0, (uint32_t)n_a * 16u, &S.bar[s]);
+      bulk_g2s(st.nr, norm_rad + g0, (uint32_t)n_a * 16u, &S.bar[s]);
+    }
+    if (n_b > 0) {
+      const int b0 = g0 + n_a - n_old;
+      bulk_g2s(st.pos + n_a, new_pos + b0, (uint32_t)n_b * 16u, &S.bar[s]);
+      bulk_g2s(st.col + n_a, new_col + b0, (uint32_t)n_b * 16u, &S.bar[s]);
+      bulk_g2s(st.nr + n_a, new_nr + b0, (uint32_t)n_b * 16u, &S.bar[s]);
+    }
+  };
+
+  int cur = 0;
+  if (tid == 0) {
+    cur = (int)atomicAdd(counter, 1u);
+    S.next_tile = cur;
+    if (cur < num_tiles) issue(cur, 0);
+  }
+  __syncthreads();
+  cur = S.next_tile;
+  int stage = 0;
+  uint32_t parity[2] = {0u, 0u};
+  while (cur < num_tiles) {
+    __syncthreads();  // S.next_tile has been read by everyone; the other stage's readers (previous iteration) are done
+    if (tid == 0) {
+      const int nx = (int)atomicAdd(counter, 1u);
+      S.next_tile = nx;
+      if (nx < num_tiles) issue(nx, stage ^ 1);
+    }
+    while (!mbar_try_wait(&S.bar[stage], parity[stage])) {
+    }
+    parity[stage] ^= 1u;
+    const CcStage& st = S.st[stage];
+    const int g0 = cur * CC_TILE;
+    const int n_in = min(CC_TILE, total - g0);
+
+    // keep / cull test (copy_unstable.vert:60-130) for this thread's CC_ITEMS surfels; item index k * CC_THREADS + tid keeps
+    // the shared-memory reads conflict-free and the order (k, warp, lane) = map order
+    unsigned int ballots[CC_ITEMS];
+    bool keep[CC_ITEMS];
+#pragma unroll
+    for (int k = 0; k < CC_ITEMS; ++k) {
+      const int idx = k * CC_THREADS + tid;
+      keep[k] = false;
+      if (idx < n_in) {
+        float4 col = st.col[idx];
+        keep[k] = clean_test(a, mp, st.pos[idx], col, st.nr[idx]);
+      }
+      ballots[k] = __ballot_sync(0xffffffffu, keep[k]);
+      if (lane == 0) S.warp_cnt[k * (CC_THREADS / 32) + wid] = __popc(ballots[k]);
+    }
+    __syncthreads();
+    if (wid == 0) {
+      // exclusive scan of the CC_ITEMS x 8 warp counts (32 values, one per lane), then the decoupled look-back
+      static_assert(CC_ITEMS * (CC_THREADS / 32) == 32, "one warp scans the slab x warp counts");
+      const int c = S.warp_cnt[lane];
+      int incl = c;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+      }
+      S.warp_excl[lane] = incl - c;
+      const int aggregate = __shfl_sync(0xffffffffu, incl, 31);
+      volatile unsigned long long* vstate = state;
+      int prefix = 0;
+      if (cur == 0) {
+        if (lane == 0) vstate[0] = tag | (2ull << 32) | (unsigned int)aggregate;
+      } else {
+        if (lane == 0) vstate[cur] = tag | (1ull << 32) | (unsigned int)aggregate;
+        int look = cur - 1;
+        while (true) {
+          const int idx = look - lane;
+          const unsigned long long w = (idx >= 0) ? vstate[idx] : (tag | (2ull << 32));
+          const unsigned int stt = ((w >> 34) == (unsigned long long)epoch) ? ((unsigned int)(w >> 32) & 3u) : 0u;
+          if (__any_sync(0xffffffffu, stt == 0)) continue;
+          const unsigned int m2 = __ballot_sync(0xffffffffu, stt == 2);
+          const int first2 = m2 ? (__ffs(m2) - 1) : 32;
+          int val = (lane <= first2) ? (int)(unsigned int)(w & 0xffffffffull) : 0;
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
+          prefix += val;
+          if (m2) break;
+          look -= 32;
+        }
+        if (lane == 0) vstate[cur] = tag | (2ull << 32) | (unsigned int)(prefix + aggregate);
+      }
+      if (lane == 0) {
+        S.prefix = prefix;
+        S.aggregate = aggregate;
+        if (cur == num_tiles - 1) *total_out = prefix + aggregate;
+      }
+    }
+    __syncthreads();
+    const int prefix = S.prefix;
+    // scatter: kept surfels go to prefix + rank. Old surfels that stay where they are are not written.
+    if (!(prefix == g0 && S.aggregate == n_in && g0 + n_in <= n_old)) {
+#pragma unroll
+      for (int k = 0; k < CC_ITEMS; ++k) {
+        if (!keep[k]) continue;
+        const int idx = k * CC_THREADS + tid;
+        const int g = g0 + idx;
+        const int o = prefix + S.warp_excl[k * (CC_THREADS / 32) + wid] + __popc(ballots[k] & ((1u << lane) - 1u));
+        if (o >= capacity || (o == g && g < n_old)) continue;
+        float4 col = st.col[idx];
+        if (g >= n_old && col.w == -2) col.w = (float)a.time;  // copy_unstable.vert:114-117
+        pos_conf[o] = st.pos[idx];
+        color_time[o] = col;
+        norm_rad[o] = st.nr[idx];
+      }
+    }
+    cur = S.next_tile;
+    stage ^= 1;
+  }
+  // leave: the last CTA to draw its terminating ticket re-arms the dispenser and publishes the counts
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(counter + 1, 1u) == gridDim.x - 1) {
+      __threadfence();
+      counter[0] = 0u;
+      counter[1] = 0u;
+      const int kept = (num_tiles > 0) ? *(volatile int*)total_out : 0;
+      *count = kept < capacity ? kept : capacity;
+      *new_count = 0;
     }
   }
 }
@@ -689,29 +849,89 @@ __device__ __forceinline__ bool splat_fragment(const Splat& sp, const Cam& c, in
   return !(dot(diff, diff) > sqrRad);
 }
 
-__global__ void k_splat_scatter(RayArgs a, const MapPose* __restrict__ mp, const float4* __restrict__ pos_conf,
-                                const float4* __restrict__ color_time, const float4* __restrict__ norm_rad, const int* __restrict__ count,
-                                unsigned long long* __restrict__ zbuf) {
+// Point-sprite rasterisation, warp-cooperative and load-balanced. The vertex stage runs one surfel per lane (most of a large
+// map is culled there: out of the frustum, unstable, outside the time window). The fragments of the warp's surviving sprites
+// (side 1 .. 2047 px, so 1 .. 4 M fragments each) are then enumerated as ONE list that all 32 lanes walk together -- fragment
+// f belongs to the sprite whose exclusive fragment-count prefix brackets f -- so a single large sprite is rasterised by the
+// whole warp and small ones do not leave lanes idle. A fragment that cannot win (the z-buffer already holds a smaller key;
+// keys only ever decrease) skips its atomic. The z-buffer result is order independent (atomicMin on depth24 << 32 | id), so
+// the image is identical to the serial rasteriser's.
+constexpr int SPLAT_THREADS = 256;
+struct SplatWarp {
+  float4 pr[32];   // pos.xyz, radius
+  float4 nz[32];   // normal.xyz, (unused)
+  int4 box[32];    // x0, y0, width, surfel id
+  int start[33];   // exclusive prefix of the fragment counts
+};
+
+__global__ void __launch_bounds__(SPLAT_THREADS) k_splat_scatter(RayArgs a, const MapPose* __restrict__ mp, const float4* __restrict__ pos_conf,
+                                                                 const float4* __restrict__ color_time, const float4* __restrict__ norm_rad,
+                                                                 const int* __restrict__ count, unsigned long long* __restrict__ zbuf) {
   pdl_enter();
+  __shared__ SplatWarp sw_all[SPLAT_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  SplatWarp& W = sw_all[wid];
   const int n = *count;
-  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+  const int gw = blockIdx.x * (SPLAT_THREADS / 32) + wid, nw = gridDim.x * (SPLAT_THREADS / 32);
+  for (int base = gw * 32; base < n; base += nw * 32) {
+    const int id = base + lane;
     Splat sp;
-    if (!splat_vertex(a, mp, pos_conf[id], color_time[id], norm_rad, id, sp)) continue;
-    const float half = sp.size * 0.5f;
-    int x0 = (int)ceilf((sp.xw - half) - 0.5f), x1 = (int)ceilf((sp.xw + half) - 0.5f) - 1;
-    int y0 = (int)ceilf((sp.yw - half) - 0.5f), y1 = (int)ceilf((sp.yw + half) - 0.5f) - 1;
-    x0 = max(x0, 0);
-    y0 = max(y0, 0);
-    x1 = min(x1, a.cols - 1);
-    y1 = min(y1, a.rows - 1);
-    for (int py = y0; py <= y1; ++py)
-      for (int px = x0; px <= x1; ++px) {
-        f3 cp;
-        if (!splat_fragment(sp, a.c, px, py, cp)) continue;
-        const unsigned int d24 = depth24((cp.z / (2 * a.max_depth)) + 0.5f);
-        if (d24 >= 16777215u) continue;
-        atomicMin(&zbuf[(size_t)py * a.cols + px], ((unsigned long long)d24 << 32) | (unsigned int)id);
+    int x0 = 0, y0 = 0, bw = 0, nfrag = 0;
+    if (id < n && splat_vertex(a, mp, pos_conf[id], color_time[id], norm_rad, id, sp)) {
+      const float half = sp.size * 0.5f;
+      x0 = (int)ceilf((sp.xw - half) - 0.5f);
+      y0 = (int)ceilf((sp.yw - half) - 0.5f);
+      int x1 = (int)ceilf((sp.xw + half) - 0.5f) - 1, y1 = (int)ceilf((sp.yw + half) - 0.5f) - 1;
+      x0 = max(x0, 0);
+      y0 = max(y0, 0);
+      x1 = min(x1, a.cols - 1);
+      y1 = min(y1, a.rows - 1);
+      if (x1 >= x0 && y1 >= y0) {
+        bw = x1 - x0 + 1;
+        nfrag = bw * (y1 - y0 + 1);
       }
+    }
+    if (!__any_sync(0xffffffffu, nfrag > 0)) continue;
+    int incl = nfrag;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    W.start[lane] = incl - nfrag;
+    if (lane == 31) W.start[32] = total;
+    if (nfrag > 0) {
+      W.pr[lane] = make_float4(sp.pos.x, sp.pos.y, sp.pos.z, sp.rad);
+      W.nz[lane] = make_float4(sp.nrm.x, sp.nrm.y, sp.nrm.z, 0.f);
+      W.box[lane] = make_int4(x0, y0, bw, id);
+    }
+    __syncwarp();
+    for (int f = lane; f < total; f += 32) {
+      // sprite of fragment f: the last s with start[s] <= f (sprites without fragments share their successor's start)
+      int s = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1)
+        if (W.start[s + step] <= f) s += step;
+      const int4 bx = W.box[s];
+      const int local = f - W.start[s];
+      const int ry = local / bx.z;
+      const int px = bx.x + (local - ry * bx.z), py = bx.y + ry;
+      const float4 pr = W.pr[s], nz = W.nz[s];
+      Splat q;
+      q.pos = mk3(pr.x, pr.y, pr.z);
+      q.nrm = mk3(nz.x, nz.y, nz.z);
+      q.rad = pr.w;
+      f3 cp;
+      if (!splat_fragment(q, a.c, px, py, cp)) continue;
+      const unsigned int d24 = depth24((cp.z / (2 * a.max_depth)) + 0.5f);
+      if (d24 >= 16777215u) continue;
+      const unsigned long long key = ((unsigned long long)d24 << 32) | (unsigned int)bx.w;
+      unsigned long long* slot = &zbuf[(size_t)py * a.cols + px];
+      if (__ldcg(slot) <= key) continue;  // cannot win: the slot only ever decreases
+      atomicMin(slot, key);
+    }
+    __syncwarp();
   }
 }
 
@@ -813,14 +1033,6 @@ __global__ void k_dense_enough(const uchar4* __restrict__ image, int rows, int c
   if (threadIdx.x == 0) *flag = ((float)s_sum / (float)(drows * dcols) > 0.75f) ? 1 : 0;
 }
 
-// count = *src, *zero = 0 (end of clean: GlobalModel.cpp:667-670)
-__global__ void k_publish_count(int* count, const int* src, int* zero) {
-  pdl_enter();
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    *count = *src;
-    *zero = 0;
-  }
-}
 __global__ void k_set_int(int* p, int v) {
   pdl_enter();
   if (threadIdx.x == 0 && blockIdx.x == 0) *p = v;
@@ -863,10 +1075,7 @@ inline Cam cam_of(const EfContext* ctx) { return Cam{ctx->cfg.cx, ctx->cfg.cy, c
     if (e__ != cudaSuccess) return (int)e__;  \
   } while (0)
 
-// surfel buffers are ping-ponged by clean (the reference's two VBOs, GlobalModel.cpp:71-87)
 struct MapBuffers {
-  float4 *pos[2], *col[2], *nr[2];
-  int cur;
   int *offsets;
   int *totals;  // [4] scan totals
   int *fb_off_raw, *fb_off_filt;
@@ -896,15 +1105,12 @@ int alloc_map(EfContext* ctx) {
   MapBuffers* B = new MapBuffers();
   memset(B, 0, sizeof(*B));
   ctx->map_host = B;
-  for (int s = 0; s < 2; ++s) {
-    CU(ctx_alloc(ctx, &B->pos[s], cap));
-    CU(ctx_alloc(ctx, &B->col[s], cap));
-    CU(ctx_alloc(ctx, &B->nr[s], cap));
-  }
-  B->cur = 0;
-  m.pos_conf = B->pos[0];
-  m.color_time = B->col[0];
-  m.norm_rad = B->nr[0];
+  // ONE buffer set: fuse updates matched surfels in place and clean compacts in place (the reference ping-pongs two VBOs,
+  // GlobalModel.cpp:71-87, and rewrites the whole map twice per frame)
+  CU(ctx_alloc(ctx, &m.pos_conf, cap));
+  CU(ctx_alloc(ctx, &m.color_time, cap));
+  CU(ctx_alloc(ctx, &m.norm_rad, cap));
+  CU(cudaFuncSetAttribute(k_clean_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CcShared)));
   CU(ctx_alloc(ctx, &m.count, 4));
   CU(ctx_alloc(ctx, &m.new_pos, n));
   CU(ctx_alloc(ctx, &m.new_col, n));
@@ -913,14 +1119,16 @@ int alloc_map(EfContext* ctx) {
   CU(ctx_alloc(ctx, &m.assoc_id, n));
   CU(ctx_alloc(ctx, &m.pending, cap));
   CU(ctx_alloc(ctx, &m.zbuf, n));
-  const size_t max_items = (cap + n) > 2 * n ? (cap + n) : 2 * n;
-  const size_t tiles = (max_items + SCAN_TILE - 1) / SCAN_TILE + 1;
+  // look-back tile states: the clean pass walks capacity + n surfels in tiles of CC_TILE, the image-sized compactions
+  // (first-frame feedback, new surfels, the tracker's candidate list) <= 2 n items in tiles of SCAN_TILE
+  const size_t max_items = cap + n;
+  const size_t tiles = (max_items + CC_TILE - 1) / CC_TILE + (2 * n + SCAN_TILE - 1) / SCAN_TILE + 2;
   unsigned long long* st = nullptr;
   CU(ctx_alloc(ctx, &st, tiles));
   m.scan_tile_state = reinterpret_cast<int*>(st);
   CU(ctx_alloc(ctx, &m.scan_counter, 4));
-  CU(ctx_alloc(ctx, &m.flags, max_items));
-  CU(ctx_alloc(ctx, &B->offsets, max_items));
+  CU(ctx_alloc(ctx, &m.flags, 2 * n));
+  CU(ctx_alloc(ctx, &B->offsets, 2 * n));
   CU(ctx_alloc(ctx, &B->totals, 4));
   CU(ctx_alloc(ctx, &B->fb_off_raw, n));
   CU(ctx_alloc(ctx, &B->fb_off_filt, n));
@@ -1062,20 +1270,22 @@ int map_clean_async(EfContext* ctx, int time, float conf_threshold, int time_del
   a.time = time;
   a.conf_threshold = conf_threshold;
   a.time_delta = time_delta;
+  // one launch: test + order-preserving in-place compaction + append of the new surfels + count publication
   const size_t max_items = (size_t)m.capacity + (size_t)m.rows * m.cols;
-  EF_LAUNCH(ctx, k_clean_flags, ctx->num_sms * 8, 256, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos, m.new_col, m.new_nr,
-            m.new_count, m.flags);
-  int rc = run_scan(ctx, m.flags, m.count, m.new_count, max_items, B.offsets, B.totals + 3);
-  if (rc) return rc;
-  const int other = 1 - B.cur;
-  EF_LAUNCH(ctx, k_clean_scatter, ctx->num_sms * 8, 256, 0, time, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos, m.new_col, m.new_nr,
-            m.new_count, m.flags, B.offsets, B.totals + 3, m.capacity, B.pos[other], B.col[other], B.nr[other], m.new_count + 1);
-  // swap (GlobalModel.cpp:667) and publish the new count
-  B.cur = other;
-  m.pos_conf = B.pos[other];
-  m.color_time = B.col[other];
-  m.norm_rad = B.nr[other];
-  EF_LAUNCH(ctx, k_publish_count, 1, 32, 0, m.count, (const int*)(m.new_count + 1), m.new_count);
+  const size_t tiles = (max_items + CC_TILE - 1) / CC_TILE;
+  if (++B.scan_epoch >= (1u << 30)) {
+    CU(cudaMemsetAsync(m.scan_tile_state, 0, B.scan_state_bytes, ctx->stream));
+    B.scan_epoch = 1;
+  }
+  // grid from the surfel count the host last saw (any value is correct: the kernel reads the device-resident counts and its
+  // CTAs draw tiles until none are left); two 97 KB CTAs fit per SM
+  const size_t guess = (size_t)(ctx->host_count > 0 ? ctx->host_count : 0) + (size_t)m.rows * m.cols / 4;
+  size_t nb = (guess + CC_TILE - 1) / CC_TILE;
+  if (nb > tiles) nb = tiles;
+  if (nb > (size_t)ctx->num_sms * 2) nb = (size_t)ctx->num_sms * 2;
+  if (nb < 1) nb = 1;
+  EF_LAUNCH(ctx, k_clean_compact, (int)nb, CC_THREADS, sizeof(CcShared), a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos, m.new_col,
+            m.new_nr, m.new_count, m.capacity, (unsigned long long*)m.scan_tile_state, m.scan_counter, B.totals + 3, B.scan_epoch);
   LAST();
   return 0;
 }
@@ -1092,7 +1302,7 @@ int map_raycast_async(EfContext* ctx, float max_depth, float conf_threshold, int
   a.time = time;
   a.max_time = max_time;
   a.time_delta = time_delta;
-  EF_LAUNCH(ctx, k_splat_scatter, ctx->num_sms * 8, 256, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.zbuf);
+  EF_LAUNCH(ctx, k_splat_scatter, ctx->num_sms * 8, SPLAT_THREADS, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.zbuf);
   Textures& t = ctx->tex;
   if (mode == 0)
     EF_LAUNCH(ctx, k_splat_resolve, sblocks(ctx, n), 256, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.zbuf, t.image, t.vertex, t.normal,

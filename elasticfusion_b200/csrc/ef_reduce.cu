@@ -758,10 +758,7 @@ __device__ __forceinline__ bool iter2_rows(const OdomDev& od, Iter2Shared& sh, i
         if (solve) {
           gn->rgbSize = rgbSize;
           gn->sigma = sigma;
-          if (brk) {
-            gn->break_level = level;
-            if (next_level >= 0 && next_level != level) gn_prepare_warp(gn, next_level);
-          } else {
+          if (!brk) {
             gn->rgbErrBuf[iter & 1] = rgbError;
             gn->lastRGBError = rgbError;
             gn->lastRGBCount = (float)rgbSize;
@@ -813,7 +810,16 @@ __device__ __forceinline__ void iter2_final(const OdomDev& od, Iter2Shared& sh, 
     gn->res_acc[0] = 0u;
     gn->res_acc[1] = 0u;
   }
-  if (brk) return;
+  if (brk) {
+    // rgbOnly `break` (RGBDOdometry.cpp:452-455). Published only here, by the CTA that took the LAST ticket: every CTA of
+    // this launch has passed the entry check of k_iter2 by now, so none can see the flag and skip its ticket (the counter
+    // and the residual accumulators above are always re-armed exactly once per launch).
+    if (solve && threadIdx.x == 0) {
+      gn->break_level = level;
+      if (next_level >= 0 && next_level != level) gn_prepare_warp(gn, next_level);
+    }
+    return;
+  }
   {
     const int v = lane, sl = wid;
     double a0 = 0, a1 = 0;

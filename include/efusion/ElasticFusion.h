@@ -107,11 +107,12 @@ inline SE3d fromRowMajor(const double* in) {
 }
 #endif
 
-// The reference prints and exit(0)s on CUDA errors (Core/Cuda/convenience.cuh:64-70); the wrappers keep that policy.
+// The reference prints and exits on CUDA errors (Core/Cuda/convenience.cuh:64-70, with status 0); the wrappers keep the
+// print-and-terminate policy but report failure to the parent process (status 1).
 inline void check(int rc, const char* what) {
   if (rc != 0) {
     std::fprintf(stderr, "Error: %s: %s\n", ef_error_string(rc), what);
-    std::exit(0);
+    std::exit(1);
   }
 }
 }  // namespace ef
@@ -296,7 +297,7 @@ class ElasticFusion {
       std::fprintf(stderr,
                    "ElasticFusion(b200): loop closure / relocalisation (Ferns, Deformation) are outside this library's scope; "
                    "construct with closeLoops=false, reloc=false (the reference's -o open-loop mode).\n");
-      std::exit(0);
+      std::exit(1);
     }
     EfConfig cfg;
     ef_default_config(&cfg, Resolution::getInstance().width(), Resolution::getInstance().height(), Intrinsics::getInstance().fx(),
