@@ -346,6 +346,19 @@ class Context:
         _chk(lib().ef_map_download_new(self.h_ctx, _p(out), self.w * self.h, C.byref(cnt)))
         return out[:cnt.value].copy()
 
+    def map_upload_range(self, surfels, first):
+        s = np.ascontiguousarray(surfels, np.float32)
+        _chk(lib().ef_map_upload_range(self.h_ctx, _p(s), int(first), len(s)))
+
+    def join_lookahead(self):
+        _chk(lib().ef_join_lookahead(self.h_ctx))
+
+    def stage_ms(self):
+        """EF_STAGE_TIMING=1 (set before the context is created): ms per stage of the last frame, index as in the header."""
+        out = (C.c_float * 16)()
+        n = lib().ef_debug_stage_ms(self.h_ctx, out)
+        return [out[i] for i in range(n)]
+
     def map_upload(self, surfels):
         s = np.ascontiguousarray(surfels, np.float32)
         _chk(lib().ef_map_upload(self.h_ctx, _p(s), len(s)))

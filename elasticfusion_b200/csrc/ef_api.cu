@@ -795,6 +795,7 @@ extern "C" int ef_set_depth_cutoff(EfContext* ctx, float v) { if (!ctx) return E
 namespace ef {
 int map_download(EfContext* ctx, const float4* a, const float4* b, const float4* c, int n, float* out);
 int map_upload(EfContext* ctx, const float* in, int n);
+int map_upload_range(EfContext* ctx, const float* in, int first, int n);
 void map_free_host(EfContext* ctx);
 }
 
@@ -861,6 +862,10 @@ extern "C" int ef_map_download_new(EfContext* ctx, float* out12, int32_t max_sur
   if (n > max_surfels) n = max_surfels;
   return map_download(ctx, ctx->map.new_pos, ctx->map.new_col, ctx->map.new_nr, n, out12);
 }
+extern "C" int ef_map_upload_range(EfContext* ctx, const float* in12, int32_t first, int32_t count) {
+  if (!ctx || !in12 || first < 0 || count <= 0) return EF_EINVAL;
+  return map_upload_range(ctx, in12, first, count);
+}
 extern "C" int ef_map_upload(EfContext* ctx, const float* in12, int32_t count) {
   if (!ctx || (!in12 && count > 0) || count < 0) return EF_EINVAL;
   return map_upload(ctx, in12, count);
@@ -892,6 +897,7 @@ static int frame_input_side(EfContext* ctx, const uint8_t* rgb_dev, const uint16
   RC(rgb_to_rgba(ctx, t.rgb, t.rgba));
   // filterDepth + metriciseDepth, ElasticFusion.cpp:284-285
   RC(preprocess_depth(ctx, t.depth_raw, ctx->depth_cutoff, t.depth_filtered, t.depth_metric, t.depth_metric_filtered));
+  if (ctx->stream != ctx->la.stream) ef_stage(ctx, 1);  // (stage events live on the main stream only)
   // frameToModel.initICP(filtered depth) and the intensity half of initRGB, ElasticFusion.cpp:318-319
   RC(odom_init_icp_depth(ctx, 0, t.depth_filtered, ctx->max_depth_processed));
   RC(odom_populate(ctx, 0, t.rgba, nullptr, ctx->odom[0].nextImage, false));
@@ -991,7 +997,7 @@ extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, c
     if (la.pending) return EF_ESTATE;  // a prefetched frame must be consumed first (pass NULL, NULL)
     RC(frame_input_side(ctx, rgb_dev, depth_dev));
   }
-  ef_stage(ctx, 1);
+  ef_stage(ctx, 2);
 
   if (ctx->tick == 1) {
     // ElasticFusion.cpp:290-296; initFirstRGB: the intensity pyramid of the first frame is the SO(3) "last" image
@@ -1017,7 +1023,7 @@ extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, c
       } else {
         RC(odom_populate(ctx, 0, t.rgba, od.nextDepth, od.nextImage, true, nullptr, nullptr, false, false));
       }
-      ef_stage(ctx, 2);
+      ef_stage(ctx, 3);
       int rc = odom_track_async(ctx, 0, ctx->rgb_only, ctx->icp_weight, ctx->pyramid, ctx->fast_odom, ctx->so3);
       if (alias)
         for (int i = 0; i < NUM_PYRS; ++i) od.nextDepth[i] = saved[i];
@@ -1032,24 +1038,32 @@ extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, c
       RC(odom_finish_async(ctx, 0, weight_multiplier, false));
     }
     // (k_gn_finish also refreshed the map kernels' float pose + inverse from the new T_wc)
-    ef_stage(ctx, 5);
+    ef_stage(ctx, 6);
     if (!ctx->cfg.skip_mid_predict) RC(predict_async(ctx));  // ElasticFusion.cpp:387 (only loop closure reads it)
     if (!ctx->rgb_only) {
       // ElasticFusion.cpp:536-585
       RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta));
-      ef_stage(ctx, 6);
-      RC(map_fuse_async(ctx, ctx->tick, ctx->max_depth_processed, -1.0f));
       ef_stage(ctx, 7);
-      RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta));
+      RC(map_fuse_async(ctx, ctx->tick, ctx->max_depth_processed, -1.0f));
       ef_stage(ctx, 8);
-      RC(map_clean_async(ctx, ctx->tick, ctx->confidence, ctx->cfg.time_delta, ctx->max_depth_processed));
+      RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta));
       ef_stage(ctx, 9);
+      RC(map_clean_async(ctx, ctx->tick, ctx->confidence, ctx->cfg.time_delta, ctx->max_depth_processed));
+      ef_stage(ctx, 10);
     }
   }
   if (ctx->tick == 1) RC(map_update_pose_async(ctx, nullptr));  // later frames: done by k_gn_finish, pose unchanged since
   RC(predict_async(ctx));  // ElasticFusion.cpp:599
-  ef_stage(ctx, 10);
+  ef_stage(ctx, 11);
   ctx->tick++;
+  return 0;
+}
+
+// Makes the main stream wait for the side stream's staged frame (a no-op without a pending frame): after this call every
+// kernel enqueued so far, on either stream, precedes whatever the caller records on ef_stream() next.
+extern "C" int ef_join_lookahead(EfContext* ctx) {
+  if (!ctx) return EF_EINVAL;
+  if (ctx->la.pending) CU(cudaStreamWaitEvent(ctx->stream, ctx->la.ready, 0));
   return 0;
 }
 
@@ -1086,8 +1100,10 @@ extern "C" int ef_process_frame(EfContext* ctx, const uint8_t* rgb, const uint16
 }
 
 // debug exports (phase profiling builds)
-// EF_STAGE_TIMING=1: milliseconds between consecutive stage events of the last frame (0 start, 1 preprocess, 2 pyramids,
-// 3 so3, 4 gauss-newton, 5 finish, 6 index map, 7 fuse, 8 index map, 9 clean, 10 predict); returns the event count
+// EF_STAGE_TIMING=1: milliseconds between consecutive stage events of the last frame (0 start, 1 upload + RGBA + bilateral/metric,
+// 2 live pyramids + SO(3) loop, 3 model pyramids, 4 sobel + candidates + begin, 5 Gauss-Newton loop, 6 finish, 7 index map, 8 fuse,
+// 9 index map, 10 clean, 11 predict); returns the event count. Stages 2..6 are what the reference does inside
+// RGBDOdometry::init* + getIncrementalTransformation.
 extern "C" int ef_debug_stage_ms(EfContext* ctx, float* out) {
   if (!ctx || !ctx->stage_timing) return 0;
   cudaStreamSynchronize(ctx->stream);
@@ -1098,7 +1114,7 @@ extern "C" int ef_debug_stage_ms(EfContext* ctx, float* out) {
     if (prev >= 0) cudaEventElapsedTime(&out[i], ctx->stage_ev[prev], ctx->stage_ev[i]);
     prev = i;
   }
-  return 11;
+  return 12;
 }
 extern "C" void* ef_debug_gn(EfContext* ctx, int which) { return ctx ? (void*)ctx->odom[which].gn : nullptr; }
 extern "C" int ef_debug_gn_size() { return (int)sizeof(GNState); }

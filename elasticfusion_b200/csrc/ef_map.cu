@@ -1369,6 +1369,26 @@ int map_upload(EfContext* ctx, const float* in, int n) {
   return 0;
 }
 
+// overwrites surfels [first, first + n) of the resident map (count unchanged; the range must lie inside it)
+int map_upload_range(EfContext* ctx, const float* in, int first, int n) {
+  MapDev& m = ctx->map;
+  MapBuffers& B = mb(ctx);
+  int cnt = 0;
+  CU(cudaMemcpyAsync(&cnt, m.count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if ((long long)first + n > cnt) return EF_EINVAL;
+  if ((size_t)n > B.aos_cap) {
+    if (B.aos) cudaFree(B.aos);
+    B.aos = nullptr;
+    CU(cudaMalloc((void**)&B.aos, (size_t)n * 48));
+    B.aos_cap = n;
+  }
+  CU(cudaMemcpyAsync(B.aos, in, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
+  EF_LAUNCH(ctx, k_unpack_aos, sblocks(ctx, n), 256, 0, (const float4*)B.aos, n, m.pos_conf + first, m.color_time + first, m.norm_rad + first);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 // scan scratch shared with the tracker's per-frame candidate compaction (same stream, never concurrent)
 int scan_flags_shared(EfContext* ctx, const int* n_dev, size_t max_items, uint8_t** flags, int** offsets, int* total_dev) {
   MapBuffers& B = mb(ctx);

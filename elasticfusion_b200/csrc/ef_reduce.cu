@@ -1127,7 +1127,7 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
   }
   if (which == 0) ctx->so3_ready = false;
   EF_LAUNCH(ctx, k_gn_begin, 1, GN_BEGIN_THREADS, 0, od.gn, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0, (const So3State*)od.so3s, od.trace);
-  ef_stage(ctx, 3);
+  ef_stage(ctx, 4);
   EF_LAUNCH(ctx, k_gn_seed, 1, 32, 0, od.gn, ns ? sched_level[0] : 0, (const So3State*)od.so3s);
   for (int s = 0; s < ns; ++s) {
     const int lv = sched_level[s];
@@ -1138,7 +1138,7 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
     const int nb2 = iter2_blocks(npx, rgb, icp ? nb1 : 0);
     EF_LAUNCH(ctx, k_iter2, nb2, IT2_THREADS, 0, od, lv, sched_iter[s], next_lv, nb1, (rgb ? 1 | 8 : 0) | (icp ? 2 : 0) | 4, 0.f);
   }
-  ef_stage(ctx, 4);
+  ef_stage(ctx, 5);
   if (so3)
     for (int i = 0; i < NUM_PYRS; ++i) {  // RGBDOdometry.cpp:560-564: handle swap
       uint8_t* t = od.lastNextImage[i];

@@ -177,3 +177,46 @@ def ate_rmse(est: np.ndarray, gt: np.ndarray) -> float:
     """Absolute trajectory error (translation RMSE, no alignment: both start at identity)."""
     d = est[:, :3, 3] - gt[:, :3, 3]
     return float(np.sqrt((d * d).sum(axis=1).mean()))
+
+
+def room_surfels(n_target: int, T_w_room: np.ndarray, view_depth: float = 1.5, focal: float = 528.0, conf: float = 20.0,
+                 time: float = 1.0) -> np.ndarray:
+    """About n_target stable surfels tiling the six walls of the room on a regular grid, in the reference's 12-float Vertex
+    layout (Core/Shaders/Vertex.cpp:22-41): pos.xyz conf | colour 0 initTime lastTime | normal.xyz radius, expressed in the
+    world frame T_w_room maps the room into. Used by bench.py to make a map of the size BASELINE's configs state (5 M / 20 M)
+    resident before timing. Colours come from `texture`, normals point away from the room's interior (the convention of
+    geometry.glsl's central-difference normals: away from the viewer), the radius is what surfels.glsl assigns to a
+    fronto-parallel surface seen from `view_depth` with focal length `focal`, widened so neighbouring discs overlap. All
+    init times are equal, so any order satisfies the map-order invariant (App. A-22)."""
+    ext = ROOM_MAX - ROOM_MIN
+    area = 2.0 * (ext[0] * ext[1] + ext[0] * ext[2] + ext[1] * ext[2])
+    s = float(np.sqrt(area / max(n_target, 1)))
+    radius = max(view_depth / focal * np.sqrt(2.0), 0.95 * s)
+    parts = []
+    for axis in range(3):
+        a1, a2 = [a for a in range(3) if a != axis]
+        n1, n2 = max(1, int(round(ext[a1] / s))), max(1, int(round(ext[a2] / s)))
+        u = ROOM_MIN[a1] + (np.arange(n1, dtype=np.float64) + 0.5) * (ext[a1] / n1)
+        v = ROOM_MIN[a2] + (np.arange(n2, dtype=np.float64) + 0.5) * (ext[a2] / n2)
+        uu, vv = np.meshgrid(u, v, indexing="ij")
+        for bound, sign in ((ROOM_MIN[axis], -1.0), (ROOM_MAX[axis], 1.0)):
+            p = np.empty((n1 * n2, 3))
+            p[:, axis] = bound
+            p[:, a1] = uu.ravel()
+            p[:, a2] = vv.ravel()
+            nrm = np.zeros(3)
+            nrm[axis] = sign
+            out = np.empty((n1 * n2, 12), np.float32)
+            for c0 in range(0, len(p), 1 << 20):  # texture() in chunks: bounded temporaries
+                c1 = min(len(p), c0 + (1 << 20))
+                rgb = texture(p[c0:c1]).astype(np.int64)
+                out[c0:c1, 4] = ((rgb[:, 0] << 16) + (rgb[:, 1] << 8) + rgb[:, 2]).astype(np.float32)
+            out[:, 0:3] = (p @ T_w_room[:3, :3].T + T_w_room[:3, 3]).astype(np.float32)
+            out[:, 3] = conf
+            out[:, 5] = 0.0
+            out[:, 6] = time
+            out[:, 7] = time
+            out[:, 8:11] = (T_w_room[:3, :3] @ nrm).astype(np.float32)
+            out[:, 11] = radius
+            parts.append(out)
+    return np.ascontiguousarray(np.concatenate(parts, axis=0))

@@ -86,6 +86,9 @@ int ef_sync(EfContext* ctx);
  *   ef_finish_frame(); }                                                                                          */
 int ef_prefetch_frame(EfContext* ctx, const uint8_t* rgb, const uint16_t* depth);                /* HOST buffers   */
 int ef_prefetch_frame_device(EfContext* ctx, const uint8_t* rgb_dev, const uint16_t* depth_dev); /* DEVICE buffers */
+/* orders the main stream after the side stream's staged frame (so an event recorded on ef_stream() afterwards covers the
+ * look-ahead work too); no-op when nothing is staged */
+int ef_join_lookahead(EfContext* ctx);
 /* waits for the frame enqueued by ef_process_frame_device and refreshes the host mirrors (pose, surfel count) */
 int ef_finish_frame(EfContext* ctx);
 /* ElasticFusion::predict (Core/ElasticFusion.cpp:621-653) */
@@ -190,6 +193,9 @@ int ef_dense_enough(EfContext* ctx, int32_t* out);
 int ef_map_count(EfContext* ctx, int32_t* count);
 int ef_map_download(EfContext* ctx, float* out12, int32_t max_surfels, int32_t* count);
 int ef_map_upload(EfContext* ctx, const float* in12, int32_t count);
+/* overwrites surfels [first, first+count) of the resident map in place (count unchanged; EF_EINVAL if the range leaves it).
+ * No reference counterpart (the reference never edits its VBO from the host); used to build large maps piecewise. */
+int ef_map_upload_range(EfContext* ctx, const float* in12, int32_t first, int32_t count);
 /* unstable surfels appended by the last ef_map_fuse (the reference's newUnstableVbo) */
 int ef_map_download_new(EfContext* ctx, float* out12, int32_t max_surfels, int32_t* count);
 
@@ -242,6 +248,10 @@ int ef_upload(EfContext* ctx, int32_t id, int32_t level, const void* host, size_
 int ef_download(EfContext* ctx, int32_t id, int32_t level, void* host, size_t bytes);
 /* number of kernels launched by this context since creation (bench.py's gpu_launches) */
 int ef_launch_count(EfContext* ctx, int64_t* n);
+/* EF_STAGE_TIMING=1 in the environment at ef_create: milliseconds between the stage events of the last frame, out[16]:
+ * [1] upload + RGBA + bilateral/metric, [2] live pyramids + SO(3), [3] model pyramids, [4] sobel + candidates, [5] Gauss-Newton
+ * loop, [6] finish, [7] index map, [8] fuse, [9] index map, [10] clean, [11] predict. Returns the number of slots (0 if off). */
+int ef_debug_stage_ms(EfContext* ctx, float* out16);
 
 #ifdef __cplusplus
 }

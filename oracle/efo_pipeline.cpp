@@ -67,8 +67,8 @@ extern "C" EfoFusion* efo_fusion_create(const EfoConfig* cfg) {
   f->depthFiltered.assign(n, 0);
   f->depthMetric.assign(n, 0.f);
   f->depthMetricFiltered.assign(n, 0.f);
-  f->map.assign((size_t)cfg->capacity * 12, 0.f);
-  f->mapTmp.assign((size_t)cfg->capacity * 12, 0.f);
+  f->map.assign(((size_t)cfg->capacity + n) * 12, 0.f);
+  f->mapTmp.assign(((size_t)cfg->capacity + n) * 12, 0.f);  // clean may emit count + new surfels before the capacity cut
   f->newUnstable.assign(n * 12, 0.f);
   f->rawFb.assign(n * 12, 0.f);
   f->filtFb.assign(n * 12, 0.f);
@@ -133,6 +133,7 @@ extern "C" void efo_fusion_process_frame(EfoFusion* f, const uint8_t* rgb, const
     int filtN = efo_feedback_buffer(f->rgb.data(), f->depthMetricFiltered.data(), f->rows, f->cols, f->cam4, f->tick,
                                     f->maxDepthProcessed, f->filtFb.data());
     f->count = efo_map_initialise(f->rawFb.data(), rawN, f->filtFb.data(), filtN, (int)n, f->map.data());
+    if (f->count > f->cfg.capacity) f->count = f->cfg.capacity;
     if (f->has_ext)
       f->ext.init_first_rgb(f->ext.handle, f->rgba.data());
     else
@@ -198,10 +199,12 @@ extern "C" void efo_fusion_process_frame(EfoFusion* f, const uint8_t* rgb, const
       efo_predict_indices(f->map.data(), f->count, f->T_wc, f->tick, f->maxDepthProcessed, f->cfg.time_delta, f->rows,
                           f->cols, f->cam4, f->indexTex.data(), f->vertConf.data(), f->colorTime.data(),
                           f->normRad.data());
-      if (f->count + newN > f->cfg.capacity) newN = f->cfg.capacity - f->count;
+      // Transform feedback into a full buffer stops recording primitives (GL 4.x spec, "Transform Feedback": primitives that
+      // do not fit are not written and not counted): the map keeps the first `capacity` surfels clean emits, in order.
       f->count = efo_clean(f->map.data(), f->count, f->newUnstable.data(), newN, f->T_wc, f->tick, f->indexTex.data(),
                            f->vertConf.data(), f->colorTime.data(), f->normRad.data(), f->cfg.confidence,
                            f->cfg.time_delta, f->maxDepthProcessed, f->rows, f->cols, f->cam4, f->mapTmp.data());
+      if (f->count > f->cfg.capacity) f->count = f->cfg.capacity;
       f->map.swap(f->mapTmp);
     }
     f->timers[2] += now_s() - t3;

@@ -10,7 +10,7 @@ BIG = 2147483647 // 2
 ctx = capi.Context(capi.default_config(K.width, K.height, K.fx, K.fy, K.cx, K.cy, capacity=5000000, time_delta=BIG))
 lib = capi.lib()
 lib.ef_debug_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
-names = ["", "preprocess", "pyramids", "sobel+so3", "gauss-newton", "finish", "index#1", "fuse", "index#2", "clean", "predict"]
+names = ["", "upload+bilateral", "pyramids+so3", "model pyramids", "sobel+cand", "gauss-newton", "finish", "index#1", "fuse", "index#2", "clean", "predict"]
 rows = []
 for i, (rgb, d, _) in enumerate(frames):
     ctx.process_frame(rgb, d, i)
