@@ -29,6 +29,11 @@ class EfConfig(C.Structure):
                 ("skip_mid_predict", C.c_int32)]
 
 
+class EfLoopResult(C.Structure):
+    _fields_ = [("ran", C.c_int32), ("accepted", C.c_int32), ("n_constraints", C.c_int32), ("lastICPError", C.c_float),
+                ("lastICPCount", C.c_float), ("cov_diag", C.c_double * 6), ("T_wc_est", C.c_double * 16)]
+
+
 TRACE_DTYPE = np.dtype([
     ("kind", "<i4"), ("level", "<i4"), ("iter", "<i4"), ("rgb_count", "<i4"), ("rgb_sigma", "<i4"),
     ("sigma_val", "<f4"),
@@ -197,6 +202,28 @@ class Context:
         _chk(lib().ef_process_frame_device(self.h_ctx, C.c_void_p(rgb_ptr), C.c_void_p(depth_ptr), C.c_int64(timestamp),
                                            _f(weight_multiplier), _p(_T(T_wc))))
 
+    def process_frame_begin(self, rgb, depth, timestamp=0, weight_multiplier=1.0, T_wc=None):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        _chk(lib().ef_process_frame_begin(self.h_ctx, _p(rgb), _p(depth), C.c_int64(timestamp), _f(weight_multiplier), _p(_T(T_wc))))
+
+    def process_frame_end(self, T_override=None, nodes=None, fern_accepted=False):
+        nd = None if nodes is None else np.ascontiguousarray(nodes, np.float32).reshape(-1, 16)
+        _chk(lib().ef_process_frame_end(self.h_ctx, _p(_T(T_override)), _p(nd), 0 if nd is None else len(nd), int(fern_accepted)))
+
+    def local_loop_result(self):
+        """(info dict, src (n,3), dst (n,3), times (n,)) of the last frame's local loop closure front half."""
+        res = EfLoopResult()
+        cap = (self.w // 20) * (self.h // 20)
+        src = np.zeros((cap, 3), np.float64)
+        dst = np.zeros((cap, 3), np.float64)
+        tm = np.zeros(cap, np.int32)
+        n = C.c_int32()
+        _chk(lib().ef_local_loop_result(self.h_ctx, C.byref(res), _p(src), _p(dst), _p(tm), cap, C.byref(n)))
+        info = dict(ran=res.ran, accepted=res.accepted, n_constraints=res.n_constraints, lastICPError=res.lastICPError,
+                    lastICPCount=res.lastICPCount, cov_diag=np.array(res.cov_diag[:]), T_wc_est=np.array(res.T_wc_est[:]).reshape(4, 4))
+        return info, src[:n.value].copy(), dst[:n.value].copy(), tm[:n.value].copy()
+
     def predict(self):
         _chk(lib().ef_predict(self.h_ctx))
 
@@ -315,6 +342,11 @@ class Context:
 
     def map_clean(self, T_wc, time, conf_threshold, time_delta, max_depth):
         _chk(lib().ef_map_clean(self.h_ctx, _p(_T(T_wc)), int(time), _f(conf_threshold), int(time_delta), _f(max_depth)))
+
+    def map_clean_deform(self, T_wc, time, conf_threshold, time_delta, max_depth, nodes, is_fern=False):
+        nd = np.ascontiguousarray(nodes, np.float32).reshape(-1, 16)
+        _chk(lib().ef_map_clean_deform(self.h_ctx, _p(_T(T_wc)), int(time), _f(conf_threshold), int(time_delta), _f(max_depth), _p(nd), len(nd),
+                                       int(is_fern)))
 
     def map_raycast(self, T_wc, max_depth, conf_threshold, time, max_time, time_delta, mode=0):
         _chk(lib().ef_map_raycast(self.h_ctx, _p(_T(T_wc)), _f(max_depth), _f(conf_threshold), int(time), int(max_time),

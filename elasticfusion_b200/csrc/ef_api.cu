@@ -38,7 +38,11 @@ int map_initialise_async(EfContext* ctx);
 int map_update_pose_async(EfContext* ctx, const double* T_host_or_null);
 int map_predict_indices_async(EfContext* ctx, int time_or_neg, float max_depth, int time_delta);
 int map_fuse_async(EfContext* ctx, int time_or_neg, float max_depth, float weighting_or_neg);
-int map_clean_async(EfContext* ctx, int time_or_neg, float conf_threshold, int time_delta, float max_depth);
+int map_clean_async(EfContext* ctx, int time_or_neg, float conf_threshold, int time_delta, float max_depth, int n_nodes = 0, bool is_fern = false);
+int map_set_graph(EfContext* ctx, const float* nodes16, int n_nodes);
+int map_loop_constraints_async(EfContext* ctx, int count_thresh, float err_thresh, float cov_thresh);
+int map_loop_reset_async(EfContext* ctx);
+int odom_copy_pose_async(EfContext* ctx, int dst, int src);
 int map_raycast_async(EfContext* ctx, float max_depth, float conf_threshold, int time, int max_time, int time_delta, int mode,
                       bool use_device_tick);
 int map_fill_in_async(EfContext* ctx, bool passthrough_geometry, bool passthrough_image);
@@ -253,11 +257,14 @@ template cudaError_t ctx_alloc<uint16_t>(EfContext*, uint16_t**, size_t);
 template cudaError_t ctx_alloc<uchar4>(EfContext*, uchar4**, size_t);
 template cudaError_t ctx_alloc<MapPose>(EfContext*, MapPose**, size_t);
 template cudaError_t ctx_alloc<int4>(EfContext*, int4**, size_t);
+template cudaError_t ctx_alloc<LoopDev>(EfContext*, LoopDev**, size_t);
 }  // namespace ef
 
 extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
   if (!cfg || !out || cfg->width <= 0 || cfg->height <= 0 || cfg->capacity <= 0) return EF_EINVAL;
-  if (cfg->close_loops || cfg->reloc) return EF_EINVAL;  // loop closure is outside the hot path
+  // close_loops = 1 runs the LOCAL loop closure front half every frame (ElasticFusion.cpp:447-505; results through
+  // ef_local_loop_result). Ferns / relocalisation and the deformation solve stay outside this library.
+  if (cfg->reloc) return EF_EINVAL;
   if ((cfg->width >> 2) < 8 || (cfg->height >> 2) < 8) return EF_EINVAL;
   CU(cudaSetDevice(cfg->device));
   EfContextFull* full = new (std::nothrow) EfContextFull();
@@ -306,6 +313,7 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
   ctx->depth_cutoff = cfg->depth_cutoff;
   ctx->max_depth_processed = 20.0f;  // reference Core/ElasticFusion.cpp:83
   ctx->host_count = 0;
+  ctx->frame_open = false;
 
   int rc = alloc_odom(ctx, ctx->odom[0]);
   if (!rc) rc = alloc_odom(ctx, ctx->odom[1]);
@@ -824,6 +832,13 @@ extern "C" int ef_map_clean(EfContext* ctx, const double* T, int32_t time, float
   RC(map_update_pose_async(ctx, T));
   return map_clean_async(ctx, time, conf_threshold, time_delta, max_depth);
 }
+extern "C" int ef_map_clean_deform(EfContext* ctx, const double* T, int32_t time, float conf_threshold, int32_t time_delta, float max_depth,
+                                   const float* graph_nodes16, int32_t n_nodes, int32_t is_fern) {
+  if (!ctx || n_nodes < 0 || (n_nodes > 0 && !graph_nodes16)) return EF_EINVAL;
+  RC(map_set_graph(ctx, graph_nodes16, n_nodes));
+  RC(map_update_pose_async(ctx, T));
+  return map_clean_async(ctx, time, conf_threshold, time_delta, max_depth, n_nodes, is_fern != 0);
+}
 extern "C" int ef_map_raycast(EfContext* ctx, const double* T, float max_depth, float conf_threshold, int32_t time, int32_t max_time,
                               int32_t time_delta, int32_t mode) {
   if (!ctx || mode < 0 || mode > 2) return EF_EINVAL;
@@ -979,12 +994,30 @@ extern "C" int ef_prefetch_frame(EfContext* ctx, const uint8_t* rgb, const uint1
   return prefetch_common(ctx, ctx->la.pin_rgb, ctx->la.pin_depth, true);
 }
 
-extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, const uint16_t* depth_dev, int64_t timestamp,
-                                       float weight_multiplier, const double* in_T_wc) {
-  (void)timestamp;
-  if (!ctx || ((rgb_dev == nullptr) != (depth_dev == nullptr))) return EF_EINVAL;
+// Local loop closure front half (ElasticFusion.cpp:447-505, the branch taken when no fern matched): INACTIVE prediction,
+// modelToModel in the reference's order (initICPModel -> initRGBModel -> initICP(pred, pred) -> initRGB, App. A-2),
+// getIncrementalTransformation(rgbOnly = false, icpWeight = 10, so3 = false), acceptance test and constraint sampling.
+// Everything stays on the device (LoopDev); nothing is applied to the map or the pose.
+static int local_loop_async(EfContext* ctx) {
+  Textures& t = ctx->tex;
+  OdomDev& od = ctx->odom[1];
+  RC(map_raycast_async(ctx, ctx->max_depth_processed, ctx->confidence, 0, ctx->tick - ctx->cfg.time_delta, ctx->cfg.time_delta, 1, false));
+  RC(odom_copy_pose_async(ctx, 1, 0));
+  RC(odom_init_icp_model(ctx, 1, (const float*)t.old_vertex, (const float*)t.old_normal));
+  RC(odom_populate(ctx, 1, (const uint8_t*)t.old_image, od.lastDepth, od.lastImage, true));
+  RC(odom_init_icp_pred(ctx, 1, (const float*)t.vertex, (const float*)t.normal));
+  RC(odom_populate(ctx, 1, (const uint8_t*)t.image, od.nextDepth, od.nextImage, true));
+  RC(odom_track_async(ctx, 1, false, 10.0f, ctx->pyramid, ctx->fast_odom, false));
+  RC(odom_finish_async(ctx, 1, 1.0f, true));
+  return map_loop_constraints_async(ctx, ctx->cfg.count_thresh, ctx->cfg.err_thresh, ctx->cfg.cov_thresh);
+}
+
+// First half of processFrame (ElasticFusion.cpp:270-534): input side, first-frame map / tracking, velocity weighting, the
+// mid-frame predict() and the local loop closure front half. Asynchronous.
+static int frame_begin_device(EfContext* ctx, const uint8_t* rgb_dev, const uint16_t* depth_dev, float weight_multiplier, const double* in_T_wc) {
   Textures& t = ctx->tex;
   Lookahead& la = ctx->la;
+  if (ctx->frame_open) return EF_ESTATE;  // ef_process_frame_end has not been called for the previous frame
   ef_stage(ctx, 0);
   if (!rgb_dev) {
     // consume the prefetched frame: its buffer set becomes live, the previous live set becomes the spare one
@@ -998,64 +1031,147 @@ extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, c
     RC(frame_input_side(ctx, rgb_dev, depth_dev));
   }
   ef_stage(ctx, 2);
+  ctx->frame_open = true;
+  if (ctx->cfg.close_loops) RC(map_loop_reset_async(ctx));
 
   if (ctx->tick == 1) {
     // ElasticFusion.cpp:290-296; initFirstRGB: the intensity pyramid of the first frame is the SO(3) "last" image
     RC(map_initialise_async(ctx));
     for (int i = 0; i < NUM_PYRS; ++i) std::swap(ctx->odom[0].nextImage[i], ctx->odom[0].lastNextImage[i]);
-  } else {
-    OdomDev& od = ctx->odom[0];
-    if (!in_T_wc) {
-      // ElasticFusion.cpp:302-323. The fill-in decision stays on the device: both candidate inputs are handed to the
-      // pyramid kernels together with the flag.
-      RC(map_dense_enough_async(ctx));
-      RC(map_select_model_inputs(ctx, nullptr, nullptr, nullptr));
-      // initRGB's depth half (populateRGBDData -> verticesToDepth(vmaps_tmp), RGBDOdometry.cpp:212-222) reads the SAME
-      // vmaps_tmp initICPModel just filled, so in frame-to-model mode nextDepth is identical to lastDepth: alias it for
-      // the tracking call instead of building the pyramid twice.
-      float* saved[NUM_PYRS];
-      const bool alias = !ctx->frame_to_frame_rgb;
-      if (alias) {
-        for (int i = 0; i < NUM_PYRS; ++i) {
-          saved[i] = od.nextDepth[i];
-          od.nextDepth[i] = od.lastDepth[i];
-        }
-      } else {
-        RC(odom_populate(ctx, 0, t.rgba, od.nextDepth, od.nextImage, true, nullptr, nullptr, false, false));
+    return 0;
+  }
+  OdomDev& od = ctx->odom[0];
+  if (!in_T_wc) {
+    // ElasticFusion.cpp:302-323. The fill-in decision stays on the device: both candidate inputs are handed to the
+    // pyramid kernels together with the flag.
+    RC(map_dense_enough_async(ctx));
+    RC(map_select_model_inputs(ctx, nullptr, nullptr, nullptr));
+    // initRGB's depth half (populateRGBDData -> verticesToDepth(vmaps_tmp), RGBDOdometry.cpp:212-222) reads the SAME
+    // vmaps_tmp initICPModel just filled, so in frame-to-model mode nextDepth is identical to lastDepth: alias it for
+    // the tracking call instead of building the pyramid twice.
+    float* saved[NUM_PYRS];
+    const bool alias = !ctx->frame_to_frame_rgb;
+    if (alias) {
+      for (int i = 0; i < NUM_PYRS; ++i) {
+        saved[i] = od.nextDepth[i];
+        od.nextDepth[i] = od.lastDepth[i];
       }
-      ef_stage(ctx, 3);
-      int rc = odom_track_async(ctx, 0, ctx->rgb_only, ctx->icp_weight, ctx->pyramid, ctx->fast_odom, ctx->so3);
-      if (alias)
-        for (int i = 0; i < NUM_PYRS; ++i) od.nextDepth[i] = saved[i];
-      RC(rc);
-      RC(odom_finish_async(ctx, 0, weight_multiplier, true));
     } else {
-      CU(cudaStreamSynchronize(ctx->stream));
-      memcpy((char*)ctx->pin_small + 4096, in_T_wc, sizeof(double) * 16);
-      CU(cudaMemcpyAsync((char*)ctx->dev_small + 4096, (char*)ctx->pin_small + 4096, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
-      ctx->so3_ready = false;  // no tracking for this frame: the SO(3) result of its input side is not used
-      RC(odom_set_pose_async(ctx, 0, (const double*)((char*)ctx->dev_small + 4096)));
-      RC(odom_finish_async(ctx, 0, weight_multiplier, false));
+      RC(odom_populate(ctx, 0, t.rgba, od.nextDepth, od.nextImage, true, nullptr, nullptr, false, false));
     }
-    // (k_gn_finish also refreshed the map kernels' float pose + inverse from the new T_wc)
-    ef_stage(ctx, 6);
-    if (!ctx->cfg.skip_mid_predict) RC(predict_async(ctx));  // ElasticFusion.cpp:387 (only loop closure reads it)
-    if (!ctx->rgb_only) {
-      // ElasticFusion.cpp:536-585
-      RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta));
-      ef_stage(ctx, 7);
-      RC(map_fuse_async(ctx, ctx->tick, ctx->max_depth_processed, -1.0f));
-      ef_stage(ctx, 8);
-      RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta));
-      ef_stage(ctx, 9);
-      RC(map_clean_async(ctx, ctx->tick, ctx->confidence, ctx->cfg.time_delta, ctx->max_depth_processed));
-      ef_stage(ctx, 10);
-    }
+    ef_stage(ctx, 3);
+    int rc = odom_track_async(ctx, 0, ctx->rgb_only, ctx->icp_weight, ctx->pyramid, ctx->fast_odom, ctx->so3);
+    if (alias)
+      for (int i = 0; i < NUM_PYRS; ++i) od.nextDepth[i] = saved[i];
+    RC(rc);
+    RC(odom_finish_async(ctx, 0, weight_multiplier, true));
+  } else {
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy((char*)ctx->pin_small + 4096, in_T_wc, sizeof(double) * 16);
+    CU(cudaMemcpyAsync((char*)ctx->dev_small + 4096, (char*)ctx->pin_small + 4096, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->so3_ready = false;  // no tracking for this frame: the SO(3) result of its input side is not used
+    RC(odom_set_pose_async(ctx, 0, (const double*)((char*)ctx->dev_small + 4096)));
+    RC(odom_finish_async(ctx, 0, weight_multiplier, false));
+  }
+  // (k_gn_finish also refreshed the map kernels' float pose + inverse from the new T_wc)
+  ef_stage(ctx, 6);
+  // ElasticFusion.cpp:387: only loop closure reads this prediction
+  if (!ctx->cfg.skip_mid_predict || ctx->cfg.close_loops) RC(predict_async(ctx));
+  if (ctx->cfg.close_loops && !ctx->rgb_only) RC(local_loop_async(ctx));
+  return 0;
+}
+
+// Second half of processFrame (ElasticFusion.cpp:536-607): index map, fuse, index map, clean (with the deformation graph stored by
+// ef_set_deformation_graph when n_nodes > 0), predict, tick++.
+static int frame_end_device(EfContext* ctx, int n_nodes, bool fern_accepted) {
+  if (!ctx->frame_open) return EF_ESTATE;
+  if (ctx->tick > 1 && !ctx->rgb_only) {
+    RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta));
+    ef_stage(ctx, 7);
+    RC(map_fuse_async(ctx, ctx->tick, ctx->max_depth_processed, -1.0f));
+    ef_stage(ctx, 8);
+    RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta));
+    ef_stage(ctx, 9);
+    if (n_nodes > 0 && !fern_accepted)  // ElasticFusion.cpp:559-569: the time-stamp refresh of deformed surfels reads this depth
+      RC(map_raycast_async(ctx, ctx->max_depth_processed, ctx->confidence, ctx->tick, ctx->tick - ctx->cfg.time_delta, 65535, 2, false));
+    RC(map_clean_async(ctx, ctx->tick, ctx->confidence, ctx->cfg.time_delta, ctx->max_depth_processed, n_nodes, fern_accepted));
+    ef_stage(ctx, 10);
   }
   if (ctx->tick == 1) RC(map_update_pose_async(ctx, nullptr));  // later frames: done by k_gn_finish, pose unchanged since
   RC(predict_async(ctx));  // ElasticFusion.cpp:599
   ef_stage(ctx, 11);
   ctx->tick++;
+  ctx->frame_open = false;
+  return 0;
+}
+
+extern "C" int ef_process_frame_device(EfContext* ctx, const uint8_t* rgb_dev, const uint16_t* depth_dev, int64_t timestamp,
+                                       float weight_multiplier, const double* in_T_wc) {
+  (void)timestamp;
+  if (!ctx || ((rgb_dev == nullptr) != (depth_dev == nullptr))) return EF_EINVAL;
+  RC(frame_begin_device(ctx, rgb_dev, depth_dev, weight_multiplier, in_T_wc));
+  return frame_end_device(ctx, 0, false);
+}
+
+// processFrame split at the point where the reference hands control to its CPU deformation solver (ElasticFusion.cpp:505-526):
+// begin = everything up to and including the local loop closure front half, end = fuse / clean / predict. Between the two
+// the host may read ef_local_loop_result, run Deformation::constrain (unchanged reference code) and hand its output back:
+// T_wc_override (T_wc_curr = T_wc_est) and the graph nodes applied inside clean.
+extern "C" int ef_process_frame_begin(EfContext* ctx, const uint8_t* rgb, const uint16_t* depth, int64_t timestamp, float weight_multiplier,
+                                      const double* in_T_wc) {
+  (void)timestamp;
+  if (!ctx || !rgb || !depth) return EF_EINVAL;
+  if (ctx->la.pending || ctx->frame_open) return EF_ESTATE;
+  const size_t n = (size_t)ctx->cfg.width * ctx->cfg.height;
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(ctx->pin_rgb, rgb, n * 3);
+  memcpy(ctx->pin_depth, depth, n * 2);
+  CU(cudaMemcpyAsync(ctx->tex.rgb, ctx->pin_rgb, n * 3, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->tex.depth_raw, ctx->pin_depth, n * 2, cudaMemcpyHostToDevice, ctx->stream));
+  RC(frame_begin_device(ctx, ctx->tex.rgb, ctx->tex.depth_raw, weight_multiplier, in_T_wc));
+  return ef_finish_frame(ctx);  // pose (and the loop-closure result) are final on return
+}
+
+extern "C" int ef_process_frame_end(EfContext* ctx, const double* T_wc_override, const float* graph_nodes16, int32_t n_nodes, int32_t fern_accepted) {
+  if (!ctx || n_nodes < 0 || (n_nodes > 0 && !graph_nodes16)) return EF_EINVAL;
+  if (!ctx->frame_open) return EF_ESTATE;
+  if (T_wc_override) {
+    RC(ef_set_pose(ctx, T_wc_override));
+    RC(map_update_pose_async(ctx, nullptr));
+  }
+  RC(map_set_graph(ctx, graph_nodes16, n_nodes));
+  RC(frame_end_device(ctx, n_nodes, fern_accepted != 0));
+  return ef_finish_frame(ctx);
+}
+
+extern "C" int ef_local_loop_result(EfContext* ctx, EfLoopResult* out, double* src3, double* dst3, int32_t* times, int32_t max_constraints,
+                                    int32_t* n_out) {
+  if (!ctx || !out || max_constraints < 0) return EF_EINVAL;
+  LoopDev* L = ctx->map.loop;
+  struct Head {
+    int ran, accepted, n_constraints;
+    float lastICPError, lastICPCount;
+    double cov_diag[6];
+    double T_wc_est[16];
+  } h;
+  static_assert(offsetof(LoopDev, src) >= sizeof(Head), "LoopDev header layout");
+  CU(cudaMemcpyAsync(&h, L, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  out->ran = h.ran;
+  out->accepted = h.accepted;
+  out->n_constraints = h.n_constraints;
+  out->lastICPError = h.lastICPError;
+  out->lastICPCount = h.lastICPCount;
+  memcpy(out->cov_diag, h.cov_diag, sizeof(h.cov_diag));
+  memcpy(out->T_wc_est, h.T_wc_est, sizeof(h.T_wc_est));
+  int n = h.n_constraints < max_constraints ? h.n_constraints : max_constraints;
+  if (n_out) *n_out = n;
+  if (n > 0) {
+    if (src3) CU(cudaMemcpyAsync(src3, (char*)L + offsetof(LoopDev, src), sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dst3) CU(cudaMemcpyAsync(dst3, (char*)L + offsetof(LoopDev, dst), sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (times) CU(cudaMemcpyAsync(times, (char*)L + offsetof(LoopDev, times), sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
   return 0;
 }
 

@@ -111,6 +111,19 @@ struct OdomDev {
   EfSolveTrace* trace;    // MAX_TRACE records (device)
 };
 
+constexpr int MAX_GRAPH_NODES = 1024;      // GlobalModel::MAX_NODES = 16384 / 16 (GlobalModel.cpp:25-26)
+constexpr int MAX_LOOP_CONSTRAINTS = 4096;  // (W/20) x (H/20): 768 at 640x480, 3072 at 1280x960
+
+// device-resident result of the local loop closure front half (ElasticFusion.cpp:447-505)
+struct LoopDev {
+  int ran, accepted, n_constraints;
+  float lastICPError, lastICPCount;
+  double cov_diag[6];
+  double T_wc_est[16];
+  double src[MAX_LOOP_CONSTRAINTS * 3], dst[MAX_LOOP_CONSTRAINTS * 3];
+  int times[MAX_LOOP_CONSTRAINTS];
+};
+
 struct MapDev {
   int rows, cols;
   float cx, cy, fx, fy;
@@ -136,6 +149,8 @@ struct MapDev {
   MapPose* pose;          // device
   int* dense_flag;        // device: 1 if the predicted image is dense enough (no fill-in)
   int* tick;              // device-resident tick
+  float* nodes;           // deformation graph of the current frame, 16 floats per node
+  LoopDev* loop;
 };
 
 struct Textures {
@@ -207,6 +222,7 @@ struct EfContext {
   bool pyramid, fast_odom, so3, frame_to_frame_rgb;
   float confidence, depth_cutoff, max_depth_processed;
   int host_count;  // last count read back
+  bool frame_open; // ef_process_frame_begin has run, ef_process_frame_end has not
 
   // pinned staging
   uint8_t* pin_rgb;

@@ -542,7 +542,121 @@ struct CleanArgs {
   int time;
   float conf_threshold;
   int time_delta;
+  // deformation graph (copy_unstable.vert:132-322); n_nodes == 0: none
+  const float* nodes;   // 16 floats per node: position 3, rotation 9 (column-major), translation 3, time
+  int n_nodes;
+  const float* depth;   // IndexMap::depthTex() (synthesizeDepth), read by the time-stamp refresh
+  float max_depth;
+  int is_fern;
 };
+
+// copy_unstable.vert:132-322. The surfel is moved by the weighted rigid motions of the k = 4 nearest of the <= 20 graph nodes
+// around its init time (binary search on the node time stamps: 10 back, then forward up to 20 in total), its normal by the
+// inverse-transpose rotations; a stable surfel that lands in front of (or < 10 cm behind) the synthesised model depth gets
+// lastTime = time. GLSL pow(x, 2) is x * x here (x >= 0 for the k nearest); texel fetches of the node texture (nearest, clamp to
+// edge) are array reads with the index clamped at 0.
+__device__ __noinline__ void deform_surfel(const CleanArgs& a, const MapPose* mp, float4& pos, float4& col, float4& nr) {
+  constexpr int k = 4, lookBack = 20;
+  int nearNodes[lookBack];
+  float nearDists[lookBack];
+#pragma unroll
+  for (int i = 0; i < lookBack; i++) {
+    nearNodes[i] = -1;
+    nearDists[i] = 16777216.0f;
+  }
+  const float* __restrict__ nodes = a.nodes;
+  const int n_nodes = a.n_nodes;
+  const int poseTime = (int)col.z;
+  int foundIndex = 0;
+  int imin = 0, imax = n_nodes - 1, imid = (imin + imax) / 2;
+  while (imax >= imin) {
+    imid = (imin + imax) / 2;
+    const int nodeTime = (int)nodes[(size_t)imid * 16 + 15];
+    if (nodeTime < poseTime)
+      imin = imid + 1;
+    else if (nodeTime > poseTime)
+      imax = imid - 1;
+    else
+      break;
+  }
+  imin = min(imin, n_nodes - 1);
+  const int nodeMin = (int)nodes[(size_t)imin * 16 + 15], nodeMid = (int)nodes[(size_t)imid * 16 + 15],
+            nodeMax = (int)nodes[(size_t)max(imax, 0) * 16 + 15];
+  if (abs(nodeMin - poseTime) <= abs(nodeMid - poseTime) && abs(nodeMin - poseTime) <= abs(nodeMax - poseTime))
+    foundIndex = imin;
+  else if (abs(nodeMid - poseTime) <= abs(nodeMin - poseTime) && abs(nodeMid - poseTime) <= abs(nodeMax - poseTime))
+    foundIndex = imid;
+  else
+    foundIndex = imax;
+  if (foundIndex == n_nodes) foundIndex = n_nodes - 1;
+  const f3 v = mk3(pos.x, pos.y, pos.z);
+  int nearNodeIndex = 0, distanceBack = 0;
+  for (int j = foundIndex; j >= 0; j--) {
+    const f3 d = v - mk3(nodes[(size_t)j * 16], nodes[(size_t)j * 16 + 1], nodes[(size_t)j * 16 + 2]);
+    nearNodes[nearNodeIndex] = j;
+    nearDists[nearNodeIndex] = sqrtf(dot(d, d));
+    nearNodeIndex++;
+    if (++distanceBack == lookBack / 2) break;
+  }
+  for (int j = foundIndex + 1; j < n_nodes; j++) {
+    const f3 d = v - mk3(nodes[(size_t)j * 16], nodes[(size_t)j * 16 + 1], nodes[(size_t)j * 16 + 2]);
+    nearNodes[nearNodeIndex] = j;
+    nearDists[nearNodeIndex] = sqrtf(dot(d, d));
+    nearNodeIndex++;
+    if (++distanceBack == lookBack) break;
+  }
+  for (int i = 0; i < lookBack - 1; ++i)
+    for (int j = i + 1; j < lookBack; ++j)
+      if (nearDists[j] < nearDists[i]) {
+        const float t = nearDists[i];
+        nearDists[i] = nearDists[j];
+        nearDists[j] = t;
+        const int t2 = nearNodes[i];
+        nearNodes[i] = nearNodes[j];
+        nearNodes[j] = t2;
+      }
+  const float dMax = nearDists[k];
+  float w[k], wsum = 0;
+  for (int j = 0; j < k; j++) {
+    const float* nd = nodes + (size_t)max(nearNodes[j], 0) * 16;
+    const f3 d = v - mk3(nd[0], nd[1], nd[2]);
+    const float b = 1.0f - (sqrtf(dot(d, d)) / dMax);
+    w[j] = b * b;
+    wsum += w[j];
+  }
+  for (int j = 0; j < k; j++) w[j] /= wsum;
+  f3 newPos = mk3(0, 0, 0), newNorm = mk3(0, 0, 0);
+  const f3 nrm = mk3(nr.x, nr.y, nr.z);
+  for (int i = 0; i < k; i++) {
+    const float* nd = nodes + (size_t)max(nearNodes[i], 0) * 16;
+    const f3 position = mk3(nd[0], nd[1], nd[2]);
+    const f3 c0 = mk3(nd[3], nd[4], nd[5]), c1 = mk3(nd[6], nd[7], nd[8]), c2 = mk3(nd[9], nd[10], nd[11]);
+    const f3 translation = mk3(nd[12], nd[13], nd[14]);
+    const f3 d = v - position;
+    const f3 rd = mk3(c0.x * d.x + c1.x * d.y + c2.x * d.z, c0.y * d.x + c1.y * d.y + c2.y * d.z, c0.z * d.x + c1.z * d.y + c2.z * d.z);
+    newPos = newPos + ((rd + position) + translation) * w[i];
+    const f3 k0 = cross(c1, c2), k1 = cross(c2, c0), k2 = cross(c0, c1);  // cofactors: transpose(inverse(R)) = cof(R) / det(R)
+    const float det = dot(c0, k0);
+    const f3 tn = mk3((k0.x * nrm.x + k1.x * nrm.y + k2.x * nrm.z) / det, (k0.y * nrm.x + k1.y * nrm.y + k2.y * nrm.z) / det,
+                      (k0.z * nrm.x + k1.z * nrm.y + k2.z * nrm.z) / det);
+    newNorm = newNorm + tn * w[i];
+  }
+  pos.x = newPos.x;
+  pos.y = newPos.y;
+  pos.z = newPos.z;
+  const f3 nn = normalized(newNorm);
+  nr.x = nn.x;
+  nr.y = nn.y;
+  nr.z = nn.z;
+  if (pos.w > a.conf_threshold && a.is_fern == 0) {
+    const f3 lp = xform(mp->t_inv, newPos);
+    const float x = ((a.c.fx * lp.x) / lp.z) + a.c.cx, y = ((a.c.fy * lp.y) / lp.z) + a.c.cy;
+    if (lp.z > 0 && lp.z < a.max_depth && x > 0 && y > 0 && x < (float)a.cols && y < (float)a.rows) {
+      const float currentDepth = a.depth[(size_t)texel(y / (float)a.rows, a.rows) * a.cols + texel(x / (float)a.cols, a.cols)];
+      if (currentDepth > 0.0f && lp.z < currentDepth + 0.1f) col.w = (float)a.time;
+    }
+  }
+}
 
 __device__ __forceinline__ bool clean_test(const CleanArgs& a, const MapPose* mp, const float4& pos, float4& col, const float4& nr) {
   const float fcols = (float)a.cols, frows = (float)a.rows;
@@ -695,7 +809,7 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
     while (!mbar_try_wait(&S.bar[stage], parity[stage])) {
     }
     parity[stage] ^= 1u;
-    const CcStage& st = S.st[stage];
+    CcStage& st = S.st[stage];
     const int g0 = cur * CC_TILE;
     const int n_in = min(CC_TILE, total - g0);
 
@@ -703,6 +817,7 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
     // the shared-memory reads conflict-free and the order (k, warp, lane) = map order
     unsigned int ballots[CC_ITEMS];
     bool keep[CC_ITEMS];
+    unsigned int deformed = 0;  // bit k: item k was moved by the deformation graph (always rewritten)
 #pragma unroll
     for (int k = 0; k < CC_ITEMS; ++k) {
       const int idx = k * CC_THREADS + tid;
@@ -710,6 +825,15 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
       if (idx < n_in) {
         float4 col = st.col[idx];
         keep[k] = clean_test(a, mp, st.pos[idx], col, st.nr[idx]);
+        if (keep[k] && a.n_nodes > 0 && col.z != (float)a.time) {
+          // (col.w was refreshed by the test for new surfels: the shader works on the updated vColor as well)
+          float4 pos = st.pos[idx], nr = st.nr[idx];
+          deform_surfel(a, mp, pos, col, nr);
+          st.pos[idx] = pos;
+          st.col[idx] = col;
+          st.nr[idx] = nr;
+          deformed |= 1u << k;
+        }
       }
       ballots[k] = __ballot_sync(0xffffffffu, keep[k]);
       if (lane == 0) S.warp_cnt[k * (CC_THREADS / 32) + wid] = __popc(ballots[k]);
@@ -759,14 +883,14 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
     __syncthreads();
     const int prefix = S.prefix;
     // scatter: kept surfels go to prefix + rank. Old surfels that stay where they are are not written.
-    if (!(prefix == g0 && S.aggregate == n_in && g0 + n_in <= n_old)) {
+    if (!(prefix == g0 && S.aggregate == n_in && g0 + n_in <= n_old) || a.n_nodes > 0) {
 #pragma unroll
       for (int k = 0; k < CC_ITEMS; ++k) {
         if (!keep[k]) continue;
         const int idx = k * CC_THREADS + tid;
         const int g = g0 + idx;
         const int o = prefix + S.warp_excl[k * (CC_THREADS / 32) + wid] + __popc(ballots[k] & ((1u << lane) - 1u));
-        if (o >= capacity || (o == g && g < n_old)) continue;
+        if (o >= capacity || (o == g && g < n_old && !(deformed >> k & 1u))) continue;
         float4 col = st.col[idx];
         if (g >= n_old && col.w == -2) col.w = (float)a.time;  // copy_unstable.vert:114-117
         pos_conf[o] = st.pos[idx];
@@ -1137,6 +1261,9 @@ int alloc_map(EfContext* ctx) {
   CU(ctx_alloc(ctx, &m.pose, 1));
   CU(ctx_alloc(ctx, &m.dense_flag, 4));
   CU(ctx_alloc(ctx, &m.tick, 4));
+  CU(ctx_alloc(ctx, &m.nodes, (size_t)MAX_GRAPH_NODES * 16));
+  CU(ctx_alloc(ctx, &m.loop, 1));
+  CU(cudaMemsetAsync(m.loop, 0, sizeof(LoopDev), ctx->stream));
   B->scan_epoch = 0;
   B->scan_state_bytes = tiles * 8;
   CU(cudaMemsetAsync(m.scan_tile_state, 0, tiles * 8, ctx->stream));
@@ -1256,8 +1383,8 @@ int map_fuse_async(EfContext* ctx, int time, float max_depth, float weighting) {
   return 0;
 }
 
-int map_clean_async(EfContext* ctx, int time, float conf_threshold, int time_delta, float max_depth) {
-  (void)max_depth;
+// n_nodes > 0: the deformation graph previously stored by map_set_graph is applied to every kept surfel
+int map_clean_async(EfContext* ctx, int time, float conf_threshold, int time_delta, float max_depth, int n_nodes, bool is_fern) {
   MapDev& m = ctx->map;
   MapBuffers& B = mb(ctx);
   CleanArgs a;
@@ -1270,6 +1397,11 @@ int map_clean_async(EfContext* ctx, int time, float conf_threshold, int time_del
   a.time = time;
   a.conf_threshold = conf_threshold;
   a.time_delta = time_delta;
+  a.nodes = m.nodes;
+  a.n_nodes = n_nodes;
+  a.depth = ctx->tex.synth_depth;
+  a.max_depth = max_depth;
+  a.is_fern = is_fern ? 1 : 0;
   // one launch: test + order-preserving in-place compaction + append of the new surfels + count publication
   const size_t max_items = (size_t)m.capacity + (size_t)m.rows * m.cols;
   const size_t tiles = (max_items + CC_TILE - 1) / CC_TILE;
@@ -1386,6 +1518,120 @@ int map_upload_range(EfContext* ctx, const float* in, int first, int n) {
   CU(cudaMemcpyAsync(B.aos, in, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
   EF_LAUNCH(ctx, k_unpack_aos, sblocks(ctx, n), 256, 0, (const float4*)B.aos, n, m.pos_conf + first, m.color_time + first, m.norm_rad + first);
   CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// deformation graph for the next clean (GlobalModel.cpp:542-546: glTexSubImage2D of the node texture); nodes: HOST, 16 floats each
+int map_set_graph(EfContext* ctx, const float* nodes16, int n_nodes) {
+  MapDev& m = ctx->map;
+  if (n_nodes < 0 || n_nodes >= MAX_GRAPH_NODES) return EF_EINVAL;  // assert(graph.size() / 16 < MAX_NODES), GlobalModel.cpp:540
+  if (n_nodes == 0) return 0;
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpyAsync(m.nodes, nodes16, (size_t)n_nodes * 16 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // nodes16 is caller memory
+  return 0;
+}
+
+// ---- local loop closure front half, last step (ElasticFusion.cpp:473-505): acceptance test on the model-to-model result and
+// the constraint pairs sampled on the W/20 x H/20 grid (Resize::vertex / Resize::time = nearest sampling at texel centres)
+__global__ void __launch_bounds__(256) k_loop_constraints(const GNState* __restrict__ gn_curr, const GNState* __restrict__ gn_est,
+                                                          const float4* __restrict__ vertex, const uint16_t* __restrict__ old_time, int rows,
+                                                          int cols, float max_depth, int count_thresh, float err_thresh, float cov_thresh,
+                                                          LoopDev* out) {
+  pdl_enter();
+  if (blockIdx.x != 0) return;
+  __shared__ int s_accept, s_base, s_warp[8];
+  if (threadIdx.x == 0) {
+    double cov[36];
+    efm::inv_n<6>(gn_est->lastA, cov);  // lastA.lu().inverse(), RGBDOdometry.cpp:573-575
+    bool covOk = true;
+    for (int i = 0; i < 6; ++i) {
+      out->cov_diag[i] = cov[i * 6 + i];
+      if (cov[i * 6 + i] > (double)cov_thresh) covOk = false;
+    }
+    out->lastICPError = gn_est->lastICPError;
+    out->lastICPCount = gn_est->lastICPCount;
+    for (int k = 0; k < 16; ++k) out->T_wc_est[k] = gn_est->T_wc[k];
+    const int ok = (covOk && gn_est->lastICPCount > (float)count_thresh && gn_est->lastICPError < err_thresh) ? 1 : 0;
+    out->ran = 1;
+    out->accepted = ok;
+    s_accept = ok;
+    s_base = 0;
+  }
+  __syncthreads();
+  if (!s_accept) {
+    if (threadIdx.x == 0) out->n_constraints = 0;
+    return;
+  }
+  const int dcols = cols / 20, drows = rows / 20, n = dcols * drows;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int q0 = 0; q0 < n; q0 += 256) {  // order: i (columns) outer, j (rows) inner, as the reference's loops
+    const int q = q0 + threadIdx.x;
+    bool ok = false;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int t = 0;
+    if (q < n) {
+      const int i = q / drows, j = q - i * drows;
+      const int sx = texel(((float)i + 0.5f) / (float)dcols, cols), sy = texel(((float)j + 0.5f) / (float)drows, rows);
+      v = vertex[(size_t)sy * cols + sx];
+      t = old_time[(size_t)sy * cols + sx];
+      ok = v.z > 0 && v.z < max_depth && t > 0;
+    }
+    const unsigned int b = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_warp[wid] = __popc(b);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < wid; ++w) off += s_warp[w];
+    if (ok) {
+      const int o = off + __popc(b & ((1u << lane) - 1u));
+      const double x = v.x, y = v.y, z = v.z;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        out->src[o * 3 + r] = gn_curr->T_wc[r * 4 + 0] * x + gn_curr->T_wc[r * 4 + 1] * y + gn_curr->T_wc[r * 4 + 2] * z + gn_curr->T_wc[r * 4 + 3];
+        out->dst[o * 3 + r] = gn_est->T_wc[r * 4 + 0] * x + gn_est->T_wc[r * 4 + 1] * y + gn_est->T_wc[r * 4 + 2] * z + gn_est->T_wc[r * 4 + 3];
+      }
+      out->times[o] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += s_warp[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out->n_constraints = s_base;
+}
+
+__global__ void k_loop_reset(LoopDev* out) {
+  pdl_enter();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out->ran = 0;
+    out->accepted = 0;
+    out->n_constraints = 0;
+  }
+}
+// T_wc of tracker `dst` = T_wc of tracker `src` (modelToModel starts from T_wc_curr: Sophus::SE3d T_wc_est = T_wc_curr)
+__global__ void k_copy_pose(GNState* dst, const GNState* src) {
+  pdl_enter();
+  if (blockIdx.x == 0 && threadIdx.x < 16) dst->T_wc[threadIdx.x] = src->T_wc[threadIdx.x];
+}
+
+int map_loop_constraints_async(EfContext* ctx, int count_thresh, float err_thresh, float cov_thresh) {
+  MapDev& m = ctx->map;
+  EF_LAUNCH(ctx, k_loop_constraints, 1, 256, 0, (const GNState*)ctx->odom[0].gn, (const GNState*)ctx->odom[1].gn, (const float4*)ctx->tex.vertex,
+            (const uint16_t*)ctx->tex.old_time, m.rows, m.cols, ctx->max_depth_processed, count_thresh, err_thresh, cov_thresh, m.loop);
+  LAST();
+  return 0;
+}
+int map_loop_reset_async(EfContext* ctx) {
+  EF_LAUNCH(ctx, k_loop_reset, 1, 32, 0, ctx->map.loop);
+  LAST();
+  return 0;
+}
+int odom_copy_pose_async(EfContext* ctx, int dst, int src) {
+  EF_LAUNCH(ctx, k_copy_pose, 1, 32, 0, ctx->odom[dst].gn, (const GNState*)ctx->odom[src].gn);
+  LAST();
   return 0;
 }
 

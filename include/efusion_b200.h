@@ -41,7 +41,8 @@ typedef struct {
   int32_t count_thresh;   /* 35000  (loop closure only; kept for API parity) */
   float err_thresh;       /* 5e-05  (loop closure only) */
   float cov_thresh;       /* 1e-05  (loop closure only) */
-  int32_t close_loops;    /* must be 0: Ferns / deformation graph are out of scope */
+  int32_t close_loops;    /* 1: run the local loop closure front half every frame (results: ef_local_loop_result); the
+                             deformation solve and Ferns stay with the host */
   int32_t iclnuim;
   int32_t reloc;          /* must be 0 */
   float photo_thresh;     /* 115 (ferns only) */
@@ -91,6 +92,29 @@ int ef_prefetch_frame_device(EfContext* ctx, const uint8_t* rgb_dev, const uint1
 int ef_join_lookahead(EfContext* ctx);
 /* waits for the frame enqueued by ef_process_frame_device and refreshes the host mirrors (pose, surfel count) */
 int ef_finish_frame(EfContext* ctx);
+/* processFrame split where the reference hands control to its CPU deformation solver (Core/ElasticFusion.cpp:505-526).
+ * ef_process_frame_begin: upload, filter, track, velocity weighting, mid-frame predict and -- with cfg.close_loops -- the local
+ * loop closure FRONT HALF (:447-505: INACTIVE prediction, modelToModel registration, acceptance test, constraint sampling);
+ * results are final on return. ef_process_frame_end: optional pose override (T_wc_curr = T_wc_est, :524) and deformation graph
+ * (16 floats per node: position 3, rotation 9 column-major, translation 3, time -- Core/Deformation.cpp:175-189) applied inside
+ * clean (Core/Shaders/copy_unstable.vert:132-322), then index map / fuse / index map / clean / predict, tick++.
+ * ef_process_frame == begin + end(NULL, NULL, 0, 0). EF_ESTATE if the calls are not paired. */
+int ef_process_frame_begin(EfContext* ctx, const uint8_t* rgb, const uint16_t* depth, int64_t timestamp, float weight_multiplier,
+                           const double* in_T_wc);
+int ef_process_frame_end(EfContext* ctx, const double* T_wc_override, const float* graph_nodes16, int32_t n_nodes,
+                         int32_t fern_accepted);
+/* result of the last frame's local loop closure front half (cfg.close_loops = 1); src3 / dst3: vert_w_curr / vert_w_est of
+ * each constraint (what localDeformation.addConstraint receives, ElasticFusion.cpp:493-503), times: the INACTIVE view's stamp */
+typedef struct {
+  int32_t ran;            /* 0: first frame, rgbOnly, or close_loops off */
+  int32_t accepted;       /* covariance diagonal <= cov_thresh && lastICPCount > count_thresh && lastICPError < err_thresh */
+  int32_t n_constraints;
+  float lastICPError, lastICPCount;
+  double cov_diag[6];
+  double T_wc_est[16];
+} EfLoopResult;
+int ef_local_loop_result(EfContext* ctx, EfLoopResult* out, double* src3, double* dst3, int32_t* times, int32_t max_constraints,
+                         int32_t* n_out);
 /* ElasticFusion::predict (Core/ElasticFusion.cpp:621-653) */
 int ef_predict(EfContext* ctx);
 
@@ -181,6 +205,10 @@ int ef_map_fuse(EfContext* ctx, const double* T_wc16, int32_t time, float max_de
 /* GlobalModel::clean — GlobalModel.cpp:527-671 (no deformation graph) */
 int ef_map_clean(EfContext* ctx, const double* T_wc16, int32_t time, float conf_threshold, int32_t time_delta,
                  float max_depth);
+/* GlobalModel::clean with a deformation graph (GlobalModel.cpp:527-671, graph.size() > 0; copy_unstable.vert:132-322); the
+ * time-stamp refresh reads EF_BUF_SYNTH_DEPTH (ef_map_raycast mode 2). graph_nodes16: HOST, 16 floats per node. */
+int ef_map_clean_deform(EfContext* ctx, const double* T_wc16, int32_t time, float conf_threshold, int32_t time_delta,
+                        float max_depth, const float* graph_nodes16, int32_t n_nodes, int32_t is_fern);
 /* IndexMap::combinedPredict (mode 0 ACTIVE, 1 INACTIVE) / synthesizeDepth (mode 2) — IndexMap.cpp:293-476 */
 int ef_map_raycast(EfContext* ctx, const double* T_wc16, float max_depth, float conf_threshold, int32_t time,
                    int32_t max_time, int32_t time_delta, int32_t mode);

@@ -125,6 +125,12 @@ int efo_clean(const float* map, int count, const float* new_unstable, int new_co
               int time, const uint32_t* index, const float* vert_conf4, const float* color_time4,
               const float* norm_rad4, float conf_threshold, int time_delta, float max_depth, int rows, int cols,
               const float* cam4, float* out);
+/* clean with a deformation graph (copy_unstable.vert:132-322): nodes = 16 floats each (position 3, rotation 9 column-major,
+ * translation 3, time — Deformation.cpp:175-189), depth = IndexMap::depthTex() (synthesizeDepth). n_nodes == 0: efo_clean. */
+int efo_clean_deform(const float* map, int count, const float* new_unstable, int new_count, const double* T_wc16, int time,
+                     const uint32_t* index, const float* vert_conf4, const float* color_time4, float conf_threshold,
+                     int time_delta, float max_depth, int rows, int cols, const float* cam4, const float* nodes, int n_nodes,
+                     const float* depth, int is_fern, float* out);
 /* combinedPredict: image RGBA8, vertex float4, normal float4, time u16; depth_only!=0 -> depth_out (float) only */
 void efo_combined_predict(const float* map, int count, const double* T_wc16, float max_depth, float conf_threshold,
                           int time, int max_time, int time_delta, int rows, int cols, const float* cam4,
@@ -151,6 +157,25 @@ typedef struct {
   int capacity;        /* max surfels */
 } EfoConfig;
 EfoFusion* efo_fusion_create(const EfoConfig* cfg);
+/* Local loop closure FRONT HALF (ElasticFusion.cpp:447-505): INACTIVE prediction, model-to-model registration, acceptance
+ * test, constraint sampling. Enabled per frame by efo_fusion_set_loop_closure; the deformation solve is out of scope, so
+ * nothing is applied to the map or pose — the results of the last frame are read with efo_fusion_loop_result. */
+typedef struct {
+  int32_t ran;            /* the front half ran for the last frame (tick > 1, not rgbOnly) */
+  int32_t accepted;       /* covOk && lastICPCount > icpCountThresh && lastICPError < icpErrThresh */
+  int32_t n_constraints;
+  float lastICPError, lastICPCount;
+  double cov_diag[6];
+  double T_wc_est[16];
+} EfoLoopResult;
+void efo_fusion_set_loop_closure(EfoFusion* f, int enabled, int count_thresh, float err_thresh, float cov_thresh);
+/* src / dst: 3 doubles per constraint (vert_w_curr, vert_w_est), times: the INACTIVE view's time stamp; returns the count */
+int efo_fusion_loop_result(const EfoFusion* f, EfoLoopResult* out, double* src3, double* dst3, int32_t* times, int max_constraints);
+/* second-half variant: processFrame with a deformation graph applied in clean and an optional pose override after tracking
+ * (what the reference does when localDeformation.constrain() succeeded: ElasticFusion.cpp:519-526, 559-586) */
+void efo_fusion_process_frame_deform(EfoFusion* f, const uint8_t* rgb, const uint16_t* depth, int64_t timestamp,
+                                     float weight_multiplier, const double* in_T_wc16, const double* T_override16,
+                                     const float* nodes, int n_nodes, int fern_accepted);
 void efo_fusion_destroy(EfoFusion* f);
 void efo_fusion_process_frame(EfoFusion* f, const uint8_t* rgb, const uint16_t* depth, int64_t timestamp,
                               float weight_multiplier, const double* in_T_wc16);

@@ -81,6 +81,11 @@ class Config(C.Structure):
                 ("pyramid", C.c_int), ("rgb_only", C.c_int), ("capacity", C.c_int)]
 
 
+class LoopResult(C.Structure):
+    _fields_ = [("ran", C.c_int32), ("accepted", C.c_int32), ("n_constraints", C.c_int32), ("lastICPError", C.c_float),
+                ("lastICPCount", C.c_float), ("cov_diag", C.c_double * 6), ("T_wc_est", C.c_double * 16)]
+
+
 def _p(a, t=None):
     if a is None:
         return None
@@ -365,6 +370,21 @@ def clean(surfels, new_unstable, T_wc, time, index, vc, ct, nr, conf_threshold, 
     return out[:n].copy()
 
 
+def clean_deform(surfels, new_unstable, T_wc, time, index, vc, ct, conf_threshold, time_delta, max_depth, K, nodes, depth, is_fern=False):
+    """clean with a deformation graph: nodes (n, 16) float32, depth = synthesizeDepth output."""
+    r, c = K.height, K.width
+    out = np.zeros((len(surfels) + len(new_unstable), 12), np.float32)
+    T = np.ascontiguousarray(T_wc, np.float64)
+    cam = _cam4(K)
+    s = np.ascontiguousarray(surfels, np.float32)
+    nu = np.ascontiguousarray(new_unstable, np.float32).reshape(-1, 12)
+    nd = np.ascontiguousarray(nodes, np.float32).reshape(-1, 16)
+    d = np.ascontiguousarray(depth, np.float32)
+    n = lib().efo_clean_deform(_p(s), len(s), _p(nu), len(nu), _p(T), int(time), _p(index), _p(vc), _p(ct), _f(conf_threshold),
+                               int(time_delta), _f(max_depth), r, c, _p(cam), _p(nd), len(nd), _p(d), int(is_fern), _p(out))
+    return out[:n].copy()
+
+
 def combined_predict(surfels, T_wc, max_depth, conf_threshold, time, max_time, time_delta, K, depth_only=False):
     r, c = K.height, K.width
     T = np.ascontiguousarray(T_wc, np.float64)
@@ -438,6 +458,30 @@ class Fusion:
         depth = np.ascontiguousarray(depth, np.uint16)
         T = None if T_wc is None else np.ascontiguousarray(T_wc, np.float64)
         lib().efo_fusion_process_frame(self.hnd, _p(rgb), _p(depth), C.c_int64(timestamp), _f(weight_multiplier), _p(T))
+
+    def process_frame_deform(self, rgb, depth, timestamp=0, weight_multiplier=1.0, T_wc=None, T_override=None, nodes=None, fern_accepted=False):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        T = None if T_wc is None else np.ascontiguousarray(T_wc, np.float64)
+        To = None if T_override is None else np.ascontiguousarray(T_override, np.float64)
+        nd = None if nodes is None else np.ascontiguousarray(nodes, np.float32).reshape(-1, 16)
+        lib().efo_fusion_process_frame_deform(self.hnd, _p(rgb), _p(depth), C.c_int64(timestamp), _f(weight_multiplier), _p(T), _p(To),
+                                              _p(nd), 0 if nd is None else len(nd), int(fern_accepted))
+
+    def set_loop_closure(self, enabled=True, count_thresh=35000, err_thresh=5e-05, cov_thresh=1e-05):
+        lib().efo_fusion_set_loop_closure(self.hnd, int(enabled), int(count_thresh), _f(err_thresh), _f(cov_thresh))
+
+    def loop_result(self):
+        """(info dict, src (n,3), dst (n,3), times (n,)) of the last frame's local loop closure front half."""
+        res = LoopResult()
+        cap = (self.K.width // 20) * (self.K.height // 20)
+        src = np.zeros((cap, 3), np.float64)
+        dst = np.zeros((cap, 3), np.float64)
+        tm = np.zeros(cap, np.int32)
+        n = lib().efo_fusion_loop_result(self.hnd, C.byref(res), _p(src), _p(dst), _p(tm), cap)
+        info = dict(ran=res.ran, accepted=res.accepted, n_constraints=res.n_constraints, lastICPError=res.lastICPError,
+                    lastICPCount=res.lastICPCount, cov_diag=np.array(res.cov_diag[:]), T_wc_est=np.array(res.T_wc_est[:]).reshape(4, 4))
+        return info, src[:n].copy(), dst[:n].copy(), tm[:n].copy()
 
     @property
     def pose(self):

@@ -509,6 +509,139 @@ inline bool clean_test(float* s /* may update s[7] */, const Pose& t_inv, const 
 }
 }  // namespace
 
+// copy_unstable.vert:132-322 — the deformation-graph branch of clean: the surfel is moved by the weighted rigid motions of
+// the k = 4 nearest of <= 20 temporally neighbouring graph nodes (binary search on the node time stamps, 10 back / up to 20 total),
+// its normal by the inverse-transpose rotations, and its lastTime is refreshed when the moved surfel is stable and lies in
+// front of (or within 10 cm behind) the synthesised model depth at its new projection. nodes: 16 floats each — position 3,
+// rotation 9 (column-major, Eigen storage order), translation 3, time (Deformation.cpp:175-189; the node texture is sampled
+// at texel centres with nearest filtering, i.e. plain array reads). GLSL pow(x, 2) is evaluated as x * x (x >= 0 here).
+static void deform_surfel(float* s, const float* nodes, int n_nodes, const Pose& t_inv, const Cam& c, int time, float conf_threshold,
+                          float max_depth, int is_fern, const float* depth, int rows, int cols) {
+  const int k = 4, lookBack = 20;
+  int nearNodes[lookBack];
+  float nearDists[lookBack];
+  for (int i = 0; i < lookBack; i++) {
+    nearNodes[i] = -1;
+    nearDists[i] = 16777216.0f;
+  }
+  auto ntime = [&](int i) { return (int)nodes[(size_t)i * 16 + 15]; };
+  auto npos = [&](int i) { return mk3(nodes[(size_t)i * 16 + 0], nodes[(size_t)i * 16 + 1], nodes[(size_t)i * 16 + 2]); };
+  const int poseTime = (int)s[6];
+  int foundIndex = 0;
+  int imin = 0, imax = n_nodes - 1, imid = (imin + imax) / 2;
+  while (imax >= imin) {
+    imid = (imin + imax) / 2;
+    const int nodeTime = ntime(imid);
+    if (nodeTime < poseTime)
+      imin = imid + 1;
+    else if (nodeTime > poseTime)
+      imax = imid - 1;
+    else
+      break;
+  }
+  imin = std::min(imin, n_nodes - 1);
+  // imax can reach -1 (every node is later than the surfel): the texture fetch clamps to texel 0 (CLAMP_TO_EDGE)
+  const int nodeMin = ntime(imin), nodeMid = ntime(imid), nodeMax = ntime(std::max(imax, 0));
+  if (std::abs(nodeMin - poseTime) <= std::abs(nodeMid - poseTime) && std::abs(nodeMin - poseTime) <= std::abs(nodeMax - poseTime))
+    foundIndex = imin;
+  else if (std::abs(nodeMid - poseTime) <= std::abs(nodeMin - poseTime) && std::abs(nodeMid - poseTime) <= std::abs(nodeMax - poseTime))
+    foundIndex = imid;
+  else
+    foundIndex = imax;
+  if (foundIndex == n_nodes) foundIndex = n_nodes - 1;
+  const f3 v = mk3(s[0], s[1], s[2]);
+  int nearNodeIndex = 0, distanceBack = 0;
+  for (int j = foundIndex; j >= 0; j--) {
+    const f3 d = v - npos(j);
+    nearNodes[nearNodeIndex] = j;
+    nearDists[nearNodeIndex] = sqrtf(dot(d, d));
+    nearNodeIndex++;
+    if (++distanceBack == lookBack / 2) break;
+  }
+  for (int j = foundIndex + 1; j < n_nodes; j++) {
+    const f3 d = v - npos(j);
+    nearNodes[nearNodeIndex] = j;
+    nearDists[nearNodeIndex] = sqrtf(dot(d, d));
+    nearNodeIndex++;
+    if (++distanceBack == lookBack) break;
+  }
+  for (int i = 0; i < lookBack - 1; ++i)
+    for (int j = i + 1; j < lookBack; ++j)
+      if (nearDists[j] < nearDists[i]) {
+        std::swap(nearDists[i], nearDists[j]);
+        std::swap(nearNodes[i], nearNodes[j]);
+      }
+  const float dMax = nearDists[k];
+  float w[k], wsum = 0;
+  for (int j = 0; j < k; j++) {
+    const f3 d = v - npos(std::max(nearNodes[j], 0));
+    const float b = 1.0f - (sqrtf(dot(d, d)) / dMax);
+    w[j] = b * b;
+    wsum += w[j];
+  }
+  for (int j = 0; j < k; j++) w[j] /= wsum;
+  f3 newPos = mk3(0, 0, 0), newNorm = mk3(0, 0, 0);
+  const f3 nrm = mk3(s[8], s[9], s[10]);
+  for (int i = 0; i < k; i++) {
+    const float* nd = nodes + (size_t)std::max(nearNodes[i], 0) * 16;
+    const f3 position = mk3(nd[0], nd[1], nd[2]);
+    const f3 c0 = mk3(nd[3], nd[4], nd[5]), c1 = mk3(nd[6], nd[7], nd[8]), c2 = mk3(nd[9], nd[10], nd[11]);  // columns
+    const f3 translation = mk3(nd[12], nd[13], nd[14]);
+    const f3 d = v - position;
+    const f3 rd = mk3(c0.x * d.x + c1.x * d.y + c2.x * d.z, c0.y * d.x + c1.y * d.y + c2.y * d.z, c0.z * d.x + c1.z * d.y + c2.z * d.z);
+    newPos = newPos + ((rd + position) + translation) * w[i];
+    // transpose(inverse(R)) = cofactor(R) / det(R): its columns are the cross products of R's columns
+    const f3 k0 = cross(c1, c2), k1 = cross(c2, c0), k2 = cross(c0, c1);
+    const float det = dot(c0, k0);
+    const f3 tn = mk3((k0.x * nrm.x + k1.x * nrm.y + k2.x * nrm.z) / det, (k0.y * nrm.x + k1.y * nrm.y + k2.y * nrm.z) / det,
+                      (k0.z * nrm.x + k1.z * nrm.y + k2.z * nrm.z) / det);
+    newNorm = newNorm + tn * w[i];
+  }
+  s[0] = newPos.x;
+  s[1] = newPos.y;
+  s[2] = newPos.z;
+  const f3 nn = normalized(newNorm);
+  s[8] = nn.x;
+  s[9] = nn.y;
+  s[10] = nn.z;
+  if (s[3] > conf_threshold && is_fern == 0) {
+    const f3 lp = xform(t_inv, newPos);
+    const float x = ((c.fx * lp.x) / lp.z) + c.cx, y = ((c.fy * lp.y) / lp.z) + c.cy;
+    if (lp.z > 0 && lp.z < max_depth && x > 0 && y > 0 && x < (float)cols && y < (float)rows) {
+      const float currentDepth = depth[(size_t)texel(y / (float)rows, rows) * cols + texel(x / (float)cols, cols)];
+      if (currentDepth > 0.0f && lp.z < currentDepth + 0.1f) s[7] = (float)time;
+    }
+  }
+}
+
+// clean with a deformation graph (GlobalModel.cpp:527-671 with graph.size() > 0). depth = IndexMap::depthTex()
+// (synthesizeDepth, ElasticFusion.cpp:559-569). nodes == nullptr / n_nodes == 0 reduces to efo_clean.
+extern "C" int efo_clean_deform(const float* map, int count, const float* new_unstable, int new_count, const double* T_wc, int time,
+                                const uint32_t* index, const float* vert_conf4, const float* color_time4, float conf_threshold,
+                                int time_delta, float max_depth, int rows, int cols, const float* cam4, const float* nodes, int n_nodes,
+                                const float* depth, int is_fern, float* out) {
+  Cam c{cam4[0], cam4[1], cam4[2], cam4[3]};
+  const Pose t_inv = to_inv_pose_f(T_wc);
+  const int total = count + new_count;
+  std::vector<uint8_t> keep(total, 0);
+  std::vector<float> tmp((size_t)total * 12);
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k < total; ++k) {
+    float* s = tmp.data() + (size_t)k * 12;
+    memcpy(s, (k < count) ? map + (size_t)k * 12 : new_unstable + (size_t)(k - count) * 12, 48);
+    const bool t = clean_test(s, t_inv, c, time, index, vert_conf4, color_time4, conf_threshold, time_delta, rows, cols);
+    keep[k] = t ? 1 : 0;
+    if (t && n_nodes > 0 && s[6] != (float)time) deform_surfel(s, nodes, n_nodes, t_inv, c, time, conf_threshold, max_depth, is_fern, depth, rows, cols);
+  }
+  int n = 0;
+  for (int k = 0; k < total; ++k)
+    if (keep[k]) {
+      memcpy(out + (size_t)n * 12, tmp.data() + (size_t)k * 12, 48);
+      ++n;
+    }
+  return n;
+}
+
 extern "C" int efo_clean(const float* map, int count, const float* new_unstable, int new_count, const double* T_wc,
                          int time, const uint32_t* index, const float* vert_conf4, const float* color_time4,
                          const float* norm_rad4, float conf_threshold, int time_delta, float max_depth, int rows,

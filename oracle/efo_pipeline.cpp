@@ -39,6 +39,18 @@ struct EfoFusion {
   std::vector<float> vertexTex, normalTex, fillVertex, fillNormal;
   std::vector<uint16_t> timeTex;
 
+  // local loop closure front half (ElasticFusion.cpp:447-505)
+  EfoOdometry* modelToModel;
+  bool closeLoops;
+  int icpCountThresh;
+  float icpErrThresh, covThresh;
+  std::vector<uint8_t> oldImage;
+  std::vector<float> oldVertex, oldNormal, synthDepth;
+  std::vector<uint16_t> oldTime;
+  EfoLoopResult loop;
+  std::vector<double> consSrc, consDst;
+  std::vector<int32_t> consTime;
+
   double timers[4];
   float lastWeighting;
   EfoTrackerBackend ext;
@@ -57,6 +69,12 @@ extern "C" EfoFusion* efo_fusion_create(const EfoConfig* cfg) {
   // RGBDOdometry defaults: distThresh 0.10, angleThresh sin(20*3.14159254/180) (RGBDOdometry.h:41-42)
   f->frameToModel = efo_odom_create(cfg->width, cfg->height, cfg->cx, cfg->cy, cfg->fx, cfg->fy, 0.10f,
                                     sinf(20.f * 3.14159254f / 180.f));
+  f->modelToModel = efo_odom_create(cfg->width, cfg->height, cfg->cx, cfg->cy, cfg->fx, cfg->fy, 0.10f, sinf(20.f * 3.14159254f / 180.f));
+  f->closeLoops = false;
+  f->icpCountThresh = 35000;
+  f->icpErrThresh = 5e-05f;
+  f->covThresh = 1e-05f;
+  memset(&f->loop, 0, sizeof(f->loop));
   f->tick = 1;
   for (int i = 0; i < 16; ++i) f->T_wc[i] = (i % 5 == 0) ? 1.0 : 0.0;
   f->maxDepthProcessed = 20.0f;
@@ -84,6 +102,11 @@ extern "C" EfoFusion* efo_fusion_create(const EfoConfig* cfg) {
   f->fillVertex.assign(n * 4, 0.f);
   f->fillNormal.assign(n * 4, 0.f);
   f->timeTex.assign(n, 0);
+  f->oldImage.assign(n * 4, 0);
+  f->oldVertex.assign(n * 4, 0.f);
+  f->oldNormal.assign(n * 4, 0.f);
+  f->oldTime.assign(n, 0);
+  f->synthDepth.assign(n, 0.f);
   for (int i = 0; i < 4; ++i) f->timers[i] = 0;
   f->lastWeighting = 0;
   f->has_ext = false;
@@ -92,6 +115,7 @@ extern "C" EfoFusion* efo_fusion_create(const EfoConfig* cfg) {
 
 extern "C" void efo_fusion_destroy(EfoFusion* f) {
   efo_odom_destroy(f->frameToModel);
+  efo_odom_destroy(f->modelToModel);
   delete f;
 }
 
@@ -106,8 +130,82 @@ static void predict(EfoFusion* f) {
                  f->fillImage.data());
 }
 
+// ElasticFusion.cpp:447-505 (the branch taken when no fern matched: always, here). Resize::vertex / Resize::time sample
+// the W/20 x H/20 grid at texel centres with nearest filtering (Resize.cpp:81-159, resize.frag); the time texture is an integer
+// texture read through a float sampler in the reference (formally undefined) — restated as the integer value.
+static void local_loop_front_half(EfoFusion* f) {
+  EfoLoopResult& L = f->loop;
+  memset(&L, 0, sizeof(L));
+  f->consSrc.clear();
+  f->consDst.clear();
+  f->consTime.clear();
+  L.ran = 1;
+  const int td = f->cfg.time_delta;
+  efo_combined_predict(f->map.data(), f->count, f->T_wc, f->maxDepthProcessed, f->cfg.confidence, 0, f->tick - td, td, f->rows,
+                       f->cols, f->cam4, f->oldImage.data(), f->oldVertex.data(), f->oldNormal.data(), f->oldTime.data(), nullptr, 0);
+  // WARNING initICP* must be called before initRGB* (ElasticFusion.cpp:461-467)
+  efo_odom_init_icp_model(f->modelToModel, f->oldVertex.data(), f->oldNormal.data(), f->T_wc);
+  efo_odom_init_rgb_model(f->modelToModel, f->oldImage.data());
+  efo_odom_init_icp_pred(f->modelToModel, f->vertexTex.data(), f->normalTex.data());
+  efo_odom_init_rgb(f->modelToModel, f->imageTex.data());
+  memcpy(L.T_wc_est, f->T_wc, sizeof(L.T_wc_est));
+  efo_odom_track(f->modelToModel, L.T_wc_est, 0, 10.f, f->cfg.pyramid, f->cfg.fast_odom, 0, nullptr, 0);
+  double cov[36];
+  efo_odom_covariance(f->modelToModel, cov);
+  bool covOk = true;
+  for (int i = 0; i < 6; i++) {
+    L.cov_diag[i] = cov[i * 6 + i];
+    if (cov[i * 6 + i] > f->covThresh) covOk = false;
+  }
+  float st[8];
+  efo_odom_stats(f->modelToModel, st);
+  L.lastICPError = st[0];
+  L.lastICPCount = st[1];
+  if (covOk && st[1] > (float)f->icpCountThresh && st[0] < f->icpErrThresh) {
+    L.accepted = 1;
+    const int dcols = f->cols / 20, drows = f->rows / 20;
+    for (int i = 0; i < dcols; i++)
+      for (int j = 0; j < drows; j++) {
+        const int sx = std::min(f->cols - 1, (int)floorf((((float)i + 0.5f) / (float)dcols) * (float)f->cols));
+        const int sy = std::min(f->rows - 1, (int)floorf((((float)j + 0.5f) / (float)drows) * (float)f->rows));
+        const float* v = f->vertexTex.data() + ((size_t)sy * f->cols + sx) * 4;
+        const uint16_t t = f->oldTime[(size_t)sy * f->cols + sx];
+        if (v[2] > 0 && v[2] < f->maxDepthProcessed && t > 0) {
+          for (int pass = 0; pass < 2; ++pass) {
+            const double* T = pass == 0 ? f->T_wc : L.T_wc_est;
+            std::vector<double>& dst = pass == 0 ? f->consSrc : f->consDst;
+            for (int r = 0; r < 3; ++r) dst.push_back(T[r * 4 + 0] * (double)v[0] + T[r * 4 + 1] * (double)v[1] + T[r * 4 + 2] * (double)v[2] + T[r * 4 + 3]);
+          }
+          f->consTime.push_back((int32_t)t);
+        }
+      }
+    L.n_constraints = (int)f->consTime.size();
+  }
+}
+
+extern "C" void efo_fusion_set_loop_closure(EfoFusion* f, int enabled, int count_thresh, float err_thresh, float cov_thresh) {
+  f->closeLoops = enabled != 0;
+  f->icpCountThresh = count_thresh;
+  f->icpErrThresh = err_thresh;
+  f->covThresh = cov_thresh;
+}
+extern "C" int efo_fusion_loop_result(const EfoFusion* f, EfoLoopResult* out, double* src3, double* dst3, int32_t* times, int max_constraints) {
+  if (out) *out = f->loop;
+  const int n = std::min((int)f->consTime.size(), max_constraints);
+  if (src3) memcpy(src3, f->consSrc.data(), sizeof(double) * 3 * n);
+  if (dst3) memcpy(dst3, f->consDst.data(), sizeof(double) * 3 * n);
+  if (times) memcpy(times, f->consTime.data(), sizeof(int32_t) * n);
+  return n;
+}
+
 extern "C" void efo_fusion_process_frame(EfoFusion* f, const uint8_t* rgb, const uint16_t* depth, int64_t timestamp,
                                          float weightMultiplier, const double* in_T_wc) {
+  efo_fusion_process_frame_deform(f, rgb, depth, timestamp, weightMultiplier, in_T_wc, nullptr, nullptr, 0, 0);
+}
+
+extern "C" void efo_fusion_process_frame_deform(EfoFusion* f, const uint8_t* rgb, const uint16_t* depth, int64_t timestamp,
+                                                float weightMultiplier, const double* in_T_wc, const double* T_override,
+                                                const float* nodes, int n_nodes, int fern_accepted) {
   (void)timestamp;
   const size_t n = (size_t)f->rows * f->cols;
   double t0 = now_s();
@@ -184,6 +282,9 @@ extern "C" void efo_fusion_process_frame(EfoFusion* f, const uint8_t* rgb, const
     // ElasticFusion.cpp:387 — the mid-frame predict(): its outputs are only consumed by loop closure and are
     // overwritten by the predict() at :599, but the reference pays for it, so the timed baseline does too.
     predict(f);
+    f->loop.ran = 0;
+    if (f->closeLoops) local_loop_front_half(f);
+    if (T_override) memcpy(f->T_wc, T_override, sizeof(f->T_wc));  // T_wc_curr = T_wc_est (ElasticFusion.cpp:524)
     double t3 = now_s();
     f->timers[3] += t3 - t2;
 
@@ -201,9 +302,12 @@ extern "C" void efo_fusion_process_frame(EfoFusion* f, const uint8_t* rgb, const
                           f->normRad.data());
       // Transform feedback into a full buffer stops recording primitives (GL 4.x spec, "Transform Feedback": primitives that
       // do not fit are not written and not counted): the map keeps the first `capacity` surfels clean emits, in order.
-      f->count = efo_clean(f->map.data(), f->count, f->newUnstable.data(), newN, f->T_wc, f->tick, f->indexTex.data(),
-                           f->vertConf.data(), f->colorTime.data(), f->normRad.data(), f->cfg.confidence,
-                           f->cfg.time_delta, f->maxDepthProcessed, f->rows, f->cols, f->cam4, f->mapTmp.data());
+      if (n_nodes > 0 && !fern_accepted)  // ElasticFusion.cpp:559-569
+        efo_combined_predict(f->map.data(), f->count, f->T_wc, f->maxDepthProcessed, f->cfg.confidence, f->tick, f->tick - f->cfg.time_delta,
+                             65535, f->rows, f->cols, f->cam4, nullptr, nullptr, nullptr, nullptr, f->synthDepth.data(), 1);
+      f->count = efo_clean_deform(f->map.data(), f->count, f->newUnstable.data(), newN, f->T_wc, f->tick, f->indexTex.data(),
+                                  f->vertConf.data(), f->colorTime.data(), f->cfg.confidence, f->cfg.time_delta, f->maxDepthProcessed,
+                                  f->rows, f->cols, f->cam4, nodes, n_nodes, f->synthDepth.data(), fern_accepted, f->mapTmp.data());
       if (f->count > f->cfg.capacity) f->count = f->cfg.capacity;
       f->map.swap(f->mapTmp);
     }

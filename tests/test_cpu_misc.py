@@ -40,8 +40,11 @@ def test_abi_argument_validation_without_gpu():
     out = ctypes.c_void_p()
     lib = capi.lib()
     assert lib.ef_create(None, None, ctypes.byref(out)) == -1  # EF_EINVAL
-    cfg.close_loops = 1
-    assert lib.ef_create(ctypes.byref(cfg), None, ctypes.byref(out)) == -1  # loop closure is out of scope
+    cfg.reloc = 1
+    assert lib.ef_create(ctypes.byref(cfg), None, ctypes.byref(out)) == -1  # Ferns relocalisation is out of scope
+    assert lib.ef_process_frame_begin(None, None, None, 0, ctypes.c_float(1), None) == -1
+    assert lib.ef_process_frame_end(None, None, None, 0, 0) == -1 and lib.ef_local_loop_result(None, None, None, None, None, 0, None) == -1
+    assert lib.ef_map_clean_deform(None, None, 0, ctypes.c_float(10), 0, ctypes.c_float(20), None, 0, 0) == -1
     assert lib.ef_error_string(-1).decode() == "invalid argument"
     assert lib.ef_sync(None) == -1 and lib.ef_process_frame(None, None, None, 0, ctypes.c_float(1), None) == -1
     # look-ahead entry points validate their arguments before touching the device as well

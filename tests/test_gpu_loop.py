@@ -1,0 +1,240 @@
+"""GPU parity tests of the SURVEY §8(f) rows built this round: f2 -- the local loop closure front half (INACTIVE prediction,
+model-to-model registration, acceptance test, constraint sampling; Core/ElasticFusion.cpp:447-505) -- and f3 -- the deformation
+graph applied inside clean (Core/Shaders/copy_unstable.vert:132-322). Product through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from util import assert_same, rel_err, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+MAXD = 20.0
+BIG = 2147483647 // 2
+
+
+def make_ctx(K, **kw):
+    from elasticfusion_b200 import capi
+
+    kw.setdefault("capacity", 500000)
+    kw.setdefault("time_delta", BIG)
+    return capi.Context(capi.default_config(K.width, K.height, K.fx, K.fy, K.cx, K.cy, **kw))
+
+
+def split_map(frames, K):
+    """Oracle map after 4 frames, made stable and split into an ACTIVE half and a displaced INACTIVE half (see test_gpu_configs)."""
+    f = run_oracle(frames, K, 4)
+    m = f.map()
+    m[:, 3] += 10.0
+    inactive = (np.arange(len(m)) % 2) == 0
+    m[:, 7] = np.where(inactive, 40.0, 295.0)
+    m[:, 6] = np.where(inactive, 10.0, 250.0)
+    ang = 0.004
+    Rd = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], np.float32)
+    m[inactive, 0:3] = (m[inactive, 0:3] @ Rd.T + np.array([0.004, -0.003, 0.002], np.float32)).astype(np.float32)
+    m[inactive, 8:11] = (m[inactive, 8:11] @ Rd.T).astype(np.float32)
+    return np.ascontiguousarray(m), f.pose
+
+
+def test_local_loop_front_half_on_a_given_map(frames, K):
+    """One frame of the front half on a known map: the product's ef_process_frame_begin (in_T_wc, so the pose is given) against the
+    same steps taken with the oracle's stage functions -- INACTIVE / ACTIVE predictions, modelToModel in the reference's order,
+    lastA.lu().inverse() diagonal, thresholds, Resize::vertex / Resize::time sampling in the reference's loop order."""
+    from oracle import ef_oracle as eo
+
+    m, T = split_map(frames, K)
+    tick, td = 300, 200
+    old = eo.combined_predict(m, T, MAXD, 10.0, 0, tick - td, td, K)
+    act = eo.combined_predict(m, T, MAXD, 10.0, tick, tick, td, K)
+    od = eo.Odometry(K.width, K.height, K.cx, K.cy, K.fx, K.fy)
+    od.init_icp_model(old[1], old[2], T)
+    od.init_rgb_model(old[0])
+    od.init_icp_pred(act[1], act[2])
+    od.init_rgb(act[0])
+    T_est, _ = od.track(T, rgb_only=False, icp_weight=10.0, pyramid=True, fast_odom=False, so3=False)
+    A, _ = od.last_system()
+    cov = np.linalg.inv(A)
+    st = od.stats()
+    cov_thresh = float(max(np.diag(cov).max() * 2.0, 1e-5))
+    accepted = bool((np.diag(cov) <= cov_thresh).all() and st["lastICPCount"] > 35000 and st["lastICPError"] < 5e-5)
+    assert accepted, (np.diag(cov), st)
+    src, dst, tms = [], [], []
+    dc, dr = K.width // 20, K.height // 20
+    for i in range(dc):
+        for j in range(dr):
+            sx, sy = int(np.floor((i + 0.5) / dc * K.width)), int(np.floor((j + 0.5) / dr * K.height))
+            v = act[1][sy, sx]
+            t = int(old[3][sy, sx])
+            if v[2] > 0 and v[2] < MAXD and t > 0:
+                p = np.array([v[0], v[1], v[2], 1.0], np.float64)
+                src.append((T @ p)[:3])
+                dst.append((T_est @ p)[:3])
+                tms.append(t)
+    src, dst, tms = np.array(src), np.array(dst), np.array(tms)
+    assert len(src) > 300
+
+    ctx = make_ctx(K, time_delta=td, close_loops=1, cov_thresh=cov_thresh)
+    try:
+        ctx.process_frame(frames[0][0], frames[0][1], 0)  # tick 1: the map is then replaced
+        info0, *_ = ctx.local_loop_result()
+        assert info0["ran"] == 0
+        ctx.map_upload(m)
+        ctx.set_tick(tick)
+        ctx.process_frame_begin(frames[4][0], frames[4][1], 0, T_wc=T)
+        info, s_p, d_p, t_p = ctx.local_loop_result()
+        for name, r in zip(("OLD_IMAGE", "OLD_VERTEX", "OLD_NORMAL", "OLD_TIME"), old):
+            assert_same(ctx.download(name), r, name)
+        for name, r in zip(("IMAGE", "VERTEX", "NORMAL", "TIME"), act):
+            assert_same(ctx.download(name), r, name)
+        assert info["ran"] == 1 and info["accepted"] == 1
+        assert abs(info["lastICPCount"] - st["lastICPCount"]) <= 1e-3 * st["lastICPCount"]
+        assert abs(info["lastICPError"] - st["lastICPError"]) <= 2e-3 * st["lastICPError"]
+        assert rel_err(info["cov_diag"], np.diag(cov)) < 2e-3
+        assert np.abs(info["T_wc_est"] - T_est).max() < 2e-5
+        assert info["n_constraints"] == len(src) == len(s_p)
+        assert np.array_equal(t_p, tms)
+        assert np.abs(s_p - src).max() < 1e-9
+        assert np.abs(d_p - dst).max() < 1e-4
+        # the second half still runs (nothing of the front half is applied), and calls must be paired
+        from elasticfusion_b200 import capi
+
+        with pytest.raises(capi.EfError):
+            ctx.process_frame_begin(frames[4][0], frames[4][1], 0)
+        ctx.process_frame_end()
+        with pytest.raises(capi.EfError):
+            ctx.process_frame_end()
+        assert ctx.get_tick() == tick + 1
+    finally:
+        ctx.close()
+
+
+def test_local_loop_front_half_over_a_sequence():
+    """close_loops = 1 over 130 frames (320x240, timeDelta 12): the front half runs every frame next to the normal pipeline on
+    both sides. The open-loop results are untouched (nothing is applied), the INACTIVE view fills as surfels age and
+    stabilise, and the model-to-model estimates agree."""
+    from elasticfusion_b200 import synth
+    from oracle import ef_oracle as eo
+
+    K2 = synth.Intrinsics(320, 240, 264.0, 264.0, 160.0, 120.0)
+    frames = list(synth.sequence(130, K2, seed=21, noise=True, speed=2.5))
+    thr = dict(count_thresh=3000, err_thresh=5e-5, cov_thresh=1e-4)
+    f = eo.Fusion(K2, time_delta=12, capacity=400000)
+    f.set_loop_closure(True, **thr)
+    ctx = make_ctx(K2, time_delta=12, capacity=400000, close_loops=1, **thr)
+    agree = flips = compared = 0
+    try:
+        for i, (rgb, depth, _) in enumerate(frames):
+            f.process_frame(rgb, depth, i)
+            ctx.process_frame(rgb, depth, i)
+            io, so, do, to = f.loop_result()
+            ip, sp, dp, tp = ctx.local_loop_result()
+            assert ip["ran"] == io["ran"] == (1 if i > 0 else 0), i
+            assert np.abs(ctx.get_pose() - f.pose).max() < 3e-4, i
+            if io["lastICPCount"] > 3000:
+                compared += 1
+                assert abs(ip["lastICPCount"] - io["lastICPCount"]) <= 0.03 * io["lastICPCount"], (i, ip["lastICPCount"], io["lastICPCount"])
+                assert np.abs(ip["T_wc_est"] - io["T_wc_est"]).max() < 1e-3, (i, np.abs(ip["T_wc_est"] - io["T_wc_est"]).max())
+                if ip["accepted"] == io["accepted"]:
+                    agree += 1
+                    if io["accepted"] and len(so) == len(sp):
+                        assert np.array_equal(to, tp) or np.mean(to != tp) < 0.02
+                        assert np.abs(sp - so).max() < 2e-3 and np.abs(dp - do).max() < 2e-3
+                else:
+                    flips += 1
+        assert compared > 40 and agree >= 0.9 * compared, (compared, agree, flips)
+        assert abs(ctx.map_count() - f.count) <= 1e-2 * f.count
+    finally:
+        ctx.close()
+
+
+def make_graph(m, n_nodes=40, seed=4):
+    """A synthetic deformation graph in the reference's raw layout (Deformation.cpp:175-189): nodes sampled from the map in init-
+    time order (the graph is sampled that way, Deformation.cpp:280-330), each with a small rotation (column-major) + translation."""
+    rng = np.random.RandomState(seed)
+    idx = np.sort(rng.choice(len(m), n_nodes, replace=False))
+    nodes = np.zeros((n_nodes, 16), np.float32)
+    for k, i in enumerate(idx):
+        w = rng.standard_normal(3) * 0.01
+        th = np.linalg.norm(w)
+        kx = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]) / max(th, 1e-12)
+        R = np.eye(3) + np.sin(th) * kx + (1 - np.cos(th)) * (kx @ kx)
+        nodes[k, 0:3] = m[i, 0:3]
+        nodes[k, 3:12] = R.T.reshape(-1)  # column-major storage of R
+        nodes[k, 12:15] = rng.standard_normal(3) * 0.01
+        nodes[k, 15] = m[i, 6]
+    order = np.argsort(nodes[:, 15], kind="stable")
+    return np.ascontiguousarray(nodes[order])
+
+
+def test_clean_with_deformation_graph(frames, K):
+    """copy_unstable.vert:132-322 on a map with spread init times: every kept surfel not created this frame is moved by its 4
+    nearest temporally-neighbouring nodes; stable ones in front of the synthesised depth get lastTime = time."""
+    from oracle import ef_oracle as eo
+
+    f = run_oracle(frames, K, 6)
+    m = f.map()
+    n = len(m)
+    m[:, 3] += np.where(np.arange(n) % 3 == 0, 10.0, 0.0).astype(np.float32)  # a third of the surfels stable
+    m[:, 6] = 1 + np.floor(np.arange(n) * 50.0 / n)                            # init times as of a map built over 50 frames
+    m[:, 7] = np.maximum(np.where(np.arange(n) % 2 == 0, 20.0, 58.0), m[:, 6])  # half of it not seen for a while
+    T, tick, td = f.pose, 60, 8
+    nodes = make_graph(m)
+    assert len(np.unique(nodes[:, 15])) >= 10
+    idx = eo.predict_indices(m, T, tick, MAXD, td, K)
+    depth = eo.combined_predict(m, T, MAXD, 10.0, tick, tick - td, 65535, K, depth_only=True)
+    assert (depth > 0).mean() > 0.3
+    new = np.zeros((0, 12), np.float32)
+    ref = eo.clean_deform(m, new, T, tick, idx[0], idx[1], idx[2], 10.0, td, MAXD, K, nodes, depth)
+    plain = eo.clean(m, new, T, tick, *idx, 10.0, td, MAXD, K)
+    assert len(ref) == len(plain) and np.nanmax(np.abs(ref[:, 0:3] - plain[:, 0:3])) > 1e-3
+    assert (ref[:, 7] != plain[:, 7]).sum() > 1000, "the time-stamp refresh never fired"
+    ctx = make_ctx(K, time_delta=td)
+    try:
+        ctx.map_upload(m)
+        ctx.map_predict_indices(T, tick, MAXD, td)
+        ctx.map_raycast(T, MAXD, 10.0, tick, tick - td, 65535, 2)
+        assert_same(ctx.download("SYNTH_DEPTH"), depth, "synthesizeDepth")
+        ctx.map_clean_deform(T, tick, 10.0, td, MAXD, nodes)
+        out = ctx.map_download()
+        assert len(out) == len(ref)
+        assert np.array_equal(out[:, 4:8], ref[:, 4:8]), "colour / times differ"
+        assert np.array_equal(np.isnan(out), np.isnan(ref))
+        ok = ~np.isnan(ref).any(axis=1)
+        assert np.abs(out[ok, 0:3] - ref[ok, 0:3]).max() < 1e-6 and np.abs(out[ok, 8:11] - ref[ok, 8:11]).max() < 1e-6
+        exact = (out[ok] == ref[ok]).all(axis=1).mean()
+        assert exact > 0.99, exact
+        # no graph: identical to the plain clean
+        ctx.map_upload(m)
+        ctx.map_predict_indices(T, tick, MAXD, td)
+        ctx.map_clean_deform(T, tick, 10.0, td, MAXD, np.zeros((0, 16), np.float32))
+        assert_same(ctx.map_download()[:, [0, 1, 2, 4, 5, 6, 7, 8, 9, 10, 11]], plain[:, [0, 1, 2, 4, 5, 6, 7, 8, 9, 10, 11]], "clean without nodes")
+    finally:
+        ctx.close()
+
+
+def test_process_frame_end_with_graph_and_pose_override(frames, K):
+    """The closed-loop hand-over: frame k runs begin -> (host solver) -> end(T_wc_est, graph); both sides then continue tracking
+    against the deformed map for two more frames."""
+    f = run_oracle(frames, K, 0)
+    ctx = make_ctx(K, skip_mid_predict=0)
+    try:
+        for i in range(5):
+            f.process_frame(frames[i][0], frames[i][1], i)
+            ctx.process_frame(frames[i][0], frames[i][1], i)
+        nodes = make_graph(f.map(), n_nodes=24, seed=9)
+        nodes[:, 12:15] *= 0.2
+        T_over = f.pose.copy()
+        T_over[:3, 3] += np.array([0.002, -0.001, 0.0015])
+        f.process_frame_deform(frames[5][0], frames[5][1], 5, T_override=T_over, nodes=nodes)
+        ctx.process_frame_begin(frames[5][0], frames[5][1], 5)
+        ctx.process_frame_end(T_override=T_over, nodes=nodes)
+        assert np.abs(ctx.get_pose() - f.pose).max() < 1e-12
+        assert abs(ctx.map_count() - f.count) <= max(2, 1e-3 * f.count)
+        m_p, m_o = ctx.map_download(), f.map()
+        if len(m_p) == len(m_o):
+            assert np.isclose(m_p, m_o, rtol=1e-4, atol=2e-5, equal_nan=True).all(axis=1).mean() > 0.99
+        for i in (6, 7):
+            f.process_frame(frames[i][0], frames[i][1], i)
+            ctx.process_frame(frames[i][0], frames[i][1], i)
+            assert np.abs(ctx.get_pose() - f.pose).max() < 5e-5, i
+    finally:
+        ctx.close()
