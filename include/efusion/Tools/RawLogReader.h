@@ -6,7 +6,7 @@
 // File layout (Tools/RawLogReader.cpp:22-109): int32 numFrames; per frame int64 timestamp, int32 depthSize,
 // int32 imageSize, depth payload, image payload. depthSize == 2*W*H / imageSize == 3*W*H mark raw payloads; a smaller
 // depth payload is zlib-compressed (supported when <zlib.h> is available, link with -lz); a smaller non-empty image
-// payload is JPEG, which this header does not decode (no JPEG library in scope): it throws std::runtime_error.
+// payload is JPEG, decoded by Tools/JPEGLoader.h (own baseline decoder, bit-identical to libjpeg's default output).
 // hasMore() keeps the reference's "currentFrame + 1 < numFrames" (the last frame of a log is never delivered,
 // RawLogReader.cpp:139-141).
 //
@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "../Utils/Resolution.h"
+#include "JPEGLoader.h"
 
 #if defined(__has_include)
 #if __has_include(<zlib.h>) && !defined(EFUSION_NO_ZLIB)
@@ -187,7 +188,16 @@ class RawLogReader : public LogReader {
     if (isz == numPixels_ * 3) {
       if (std::fread(c, 1, (size_t)isz, fp_) != (size_t)isz) throw std::runtime_error("RawLogReader: truncated image payload");
     } else if (isz > 0) {
-      throw std::runtime_error("RawLogReader: JPEG image payload is not supported (raw .klg only)");
+      jpegBuf_.resize((size_t)isz);
+      if (std::fread(jpegBuf_.data(), 1, (size_t)isz, fp_) != (size_t)isz) throw std::runtime_error("RawLogReader: truncated image payload");
+      int jw = 0, jh = 0;
+      JPEGLoader::decode(jpegBuf_.data(), (size_t)isz, jpegRgb_, jw, jh);
+      if (jw != width_ || jh != height_) throw std::runtime_error("RawLogReader: JPEG payload size differs from the log resolution");
+      for (int i = 0; i < numPixels_; ++i) {  // JPEGLoader::readData's channel swap (reference Tools/JPEGLoader.h:73-82)
+        c[i * 3 + 0] = jpegRgb_[(size_t)i * 3 + 2];
+        c[i * 3 + 1] = jpegRgb_[(size_t)i * 3 + 1];
+        c[i * 3 + 2] = jpegRgb_[(size_t)i * 3 + 0];
+      }
     } else {
       std::memset(c, 0, (size_t)numPixels_ * 3);
     }
@@ -204,7 +214,7 @@ class RawLogReader : public LogReader {
   long frameStart_ = 0;  // file offset of the frame the next getNext() delivers
   std::vector<uint16_t> depthBuf_[2];
   std::vector<uint8_t> rgbBuf_[2];
-  std::vector<uint8_t> scratch_;
+  std::vector<uint8_t> scratch_, jpegBuf_, jpegRgb_;
   int cur_ = 0;
   bool peeked_ = false;
   int64_t peekTimestamp_ = 0;

@@ -49,5 +49,8 @@ int main(int argc, char** argv) {
   for (int r = 0; r < 4; ++r)
     for (int c = 0; c < 4; ++c) std::printf(" %.9f", (double)T(r, c));
   std::printf("\nCOUNT %u TICK %d\n", eFusion.getGlobalModel().lastCount(), eFusion.getTick());
+  // ElasticFusion::savePly (Core/ElasticFusion.cpp:684-781) with a threshold the few frames of a test log can pass
+  eFusion.setConfidenceThreshold(0.9f);
+  eFusion.savePly();
   return 0;
 }

@@ -53,8 +53,28 @@ def test_core_api_example_runs_and_matches_c_abi(tmp_path, small_K, small_frames
             ctx.process_frame(rgb, d, i * 33333)
         assert np.abs(ctx.get_pose() - pose).max() < 1e-8
         assert ctx.map_count() == count and ctx.get_tick() == tick == len(small_frames) + 1
+        surfels = ctx.map_download()
     finally:
         ctx.close()
     assert os.path.exists("/tmp/ef_b200_example.freiburg")
     lines = open("/tmp/ef_b200_example.freiburg").read().strip().split("\n")
     assert len(lines) == len(small_frames) and len(lines[0].split()) == 8
+
+    # savePly (Core/ElasticFusion.cpp:684-781): ASCII header, then per surfel with confidence > threshold: xyz float32 LE,
+    # r g b bytes of the 24-bit colour, NEGATED normal and the radius as float32
+    raw = open("/tmp/ef_b200_example.ply", "rb").read()
+    head, _, body = raw.partition(b"end_header\n")
+    lines = head.decode().split("\n")
+    assert lines[0] == "ply" and lines[1] == "format binary_little_endian 1.0"
+    props = [l for l in lines if l.startswith("property")]
+    assert props == ["property float x", "property float y", "property float z", "property uchar red", "property uchar green", "property uchar blue",
+                     "property float nx", "property float ny", "property float nz", "property float radius"]
+    keep = surfels[surfels[:, 3] > np.float32(0.9)]
+    n = int([l for l in lines if l.startswith("element vertex")][0].split()[-1])
+    assert n == len(keep) and 0 < n < len(surfels) and len(body) == n * 31
+    rec = np.frombuffer(body, np.dtype([("p", "<f4", 3), ("c", "u1", 3), ("n", "<f4", 4)]))
+    assert np.array_equal(rec["p"], keep[:, 0:3])
+    col = keep[:, 4].astype(np.int64)
+    assert np.array_equal(rec["c"], np.stack([(col >> 16) & 255, (col >> 8) & 255, col & 255], 1).astype(np.uint8))
+    nz = ~np.isnan(keep[:, 8:11]).any(axis=1)
+    assert np.array_equal(rec["n"][nz, :3], -keep[nz, 8:11]) and np.array_equal(rec["n"][:, 3], keep[:, 11])
