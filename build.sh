@@ -17,3 +17,7 @@ wait
 OUT=${EF_OUT:-elasticfusion_b200/libefusion.so}
 $NVCC -shared -o $OUT $B/ef_api.o $B/ef_track.o $B/ef_map.o $B/ef_preprocess.o $B/ef_reduce.o -lcudart
 echo "built $OUT"
+# headless driver with the reference application's command line (MainController.cpp), on top of the library
+/usr/bin/g++ -std=c++17 -O2 -Wall -Iinclude/efusion -Iinclude tools/ElasticFusionHeadless.cpp -o tools/ElasticFusionHeadless \
+  -Lelasticfusion_b200 -lefusion -Wl,-rpath,'$ORIGIN/../elasticfusion_b200' -L/usr/local/cuda/lib64 -lcudart -lz
+echo "built tools/ElasticFusionHeadless"

@@ -293,12 +293,17 @@ class ElasticFusion {
                 const float fernThresh = 0.3095, const bool so3 = true, const bool frameToFrameRGB = false, const std::string fileName = "",
                 const int surfelCapacity = 3072 * 3072, const int device = 0)
       : saveFilename(fileName), iclnuim_(iclnuim), confidenceThreshold_(confidence), maxDepthProcessed_(20.0f), timeDelta_(timeDelta) {
-    if (closeLoops || reloc) {
+    if (reloc) {
       std::fprintf(stderr,
-                   "ElasticFusion(b200): loop closure / relocalisation (Ferns, Deformation) are outside this library's scope; "
-                   "construct with closeLoops=false, reloc=false (the reference's -o open-loop mode).\n");
+                   "ElasticFusion(b200): relocalisation (Ferns) is outside this library's scope; construct with reloc=false.\n");
       std::exit(1);
     }
+    if (closeLoops)
+      std::fprintf(stderr,
+                   "ElasticFusion(b200): closeLoops=true runs the LOCAL loop closure front half on the device every frame (registration of "
+                   "the active against the inactive model view, acceptance test, constraint sampling: getLocalLoopClosure()); the "
+                   "deformation solve (Deformation::constrain) and Ferns are not part of this library, so the map stays open-loop unless "
+                   "the caller feeds processFrameEnd() a graph.\n");
     EfConfig cfg;
     ef_default_config(&cfg, Resolution::getInstance().width(), Resolution::getInstance().height(), Intrinsics::getInstance().fx(),
                       Intrinsics::getInstance().fy(), Intrinsics::getInstance().cx(), Intrinsics::getInstance().cy());
@@ -306,6 +311,7 @@ class ElasticFusion {
     cfg.count_thresh = countThresh;
     cfg.err_thresh = errThresh;
     cfg.cov_thresh = covThresh;
+    cfg.close_loops = closeLoops ? 1 : 0;
     cfg.iclnuim = iclnuim;
     cfg.photo_thresh = photoThresh;
     cfg.confidence = confidence;
@@ -377,6 +383,55 @@ class ElasticFusion {
     frameToModel_->refresh();
   }
   void predict() { ef::check(ef_predict(ctx_), "predict"); }
+
+  // B200 additions for closed-loop hosts. The reference runs its CPU deformation solver in the middle of processFrame
+  // (Core/ElasticFusion.cpp:505-526); a host that owns that solver splits the frame instead:
+  //   processFrameBegin(...); c = getLocalLoopClosure(); <Deformation::constrain on c> ; processFrameEnd(&T_wc_est, graph, n)
+  struct LocalLoopClosure {
+    bool ran = false, accepted = false;
+    float lastICPError = 0, lastICPCount = 0;
+    double covDiag[6] = {0, 0, 0, 0, 0, 0};
+    ef::SE3d T_wc_est;
+    std::vector<double> src, dst;  // 3 per constraint: vert_w_curr, vert_w_est (ElasticFusion.cpp:493-503)
+    std::vector<int> times;        // the INACTIVE view's time stamp of each constraint
+  };
+  void processFrameBegin(const uint8_t* rgb, const uint16_t* depth, const int64_t& timestamp, const float weightMultiplier,
+                         const ef::SE3d* in_T_wc = 0) {
+    double T[16];
+    if (in_T_wc) ef::toRowMajor(*in_T_wc, T);
+    ef::check(ef_process_frame_begin(ctx_, rgb, depth, timestamp, weightMultiplier, in_T_wc ? T : nullptr), "processFrameBegin");
+    pendingTimestamp_ = timestamp;
+  }
+  void processFrameEnd(const ef::SE3d* T_wc_override = 0, const float* graphNodes16 = 0, int numNodes = 0, bool fernAccepted = false) {
+    double T[16];
+    if (T_wc_override) ef::toRowMajor(*T_wc_override, T);
+    ef::check(ef_process_frame_end(ctx_, T_wc_override ? T : nullptr, graphNodes16, numNodes, fernAccepted ? 1 : 0), "processFrameEnd");
+    ef::check(ef_get_pose(ctx_, T), "get_T_wc");
+    T_wc_curr_ = ef::fromRowMajor(T);
+    poseLog_.emplace_back(T, T + 16);
+    poseLogTimes_.push_back((uint64_t)pendingTimestamp_);
+    frameToModel_->refresh();
+  }
+  LocalLoopClosure getLocalLoopClosure() {
+    LocalLoopClosure c;
+    EfLoopResult r;
+    const int cap = (Resolution::getInstance().width() / 20) * (Resolution::getInstance().height() / 20);
+    c.src.resize((size_t)cap * 3);
+    c.dst.resize((size_t)cap * 3);
+    c.times.resize((size_t)cap);
+    int32_t n = 0;
+    ef::check(ef_local_loop_result(ctx_, &r, c.src.data(), c.dst.data(), c.times.data(), cap, &n), "getLocalLoopClosure");
+    c.ran = r.ran != 0;
+    c.accepted = r.accepted != 0;
+    c.lastICPError = r.lastICPError;
+    c.lastICPCount = r.lastICPCount;
+    for (int i = 0; i < 6; ++i) c.covDiag[i] = r.cov_diag[i];
+    c.T_wc_est = ef::fromRowMajor(r.T_wc_est);
+    c.src.resize((size_t)n * 3);
+    c.dst.resize((size_t)n * 3);
+    c.times.resize((size_t)n);
+    return c;
+  }
 
   IndexMap& getIndexMap() { return *indexMap_; }
   GlobalModel& getGlobalModel() { return *globalModel_; }
@@ -495,6 +550,7 @@ class ElasticFusion {
   int zero_ = 0;
   bool lost_ = false;
   bool staged_ = false;  // a look-ahead frame is waiting in the library (ef_prefetch_frame)
+  int64_t pendingTimestamp_ = 0;
 };
 
 #endif  // EFUSION_B200_ELASTICFUSION_H_

@@ -78,3 +78,47 @@ def test_core_api_example_runs_and_matches_c_abi(tmp_path, small_K, small_frames
     assert np.array_equal(rec["c"], np.stack([(col >> 16) & 255, (col >> 8) & 255, col & 255], 1).astype(np.uint8))
     nz = ~np.isnan(keep[:, 8:11]).any(axis=1)
     assert np.array_equal(rec["n"][nz, :3], -keep[nz, 8:11]) and np.array_equal(rec["n"][:, 3], keep[:, 11])
+
+
+@pytest.mark.gpu
+def test_headless_cli_matches_c_abi(tmp_path, small_K, small_frames):
+    """tools/ElasticFusionHeadless (the reference application's flags, MainController.cpp:32-104, without GUI): `-l log -cal file -o`
+    over a zlib + raw .klg must leave a .freiburg whose last pose equals the C ABI run's. hasMore() drops the last frame of a log
+    (RawLogReader.cpp:139-141), so N-1 frames are processed."""
+    import zlib, struct
+    from elasticfusion_b200 import capi
+
+    exe = os.path.join(ROOT, "tools", "ElasticFusionHeadless")
+    if not os.path.exists(exe):
+        subprocess.check_call(["bash", os.path.join(ROOT, "build.sh")])
+    K = small_K
+    klg = str(tmp_path / "cli.klg")
+    with open(klg, "wb") as f:
+        f.write(struct.pack("<i", len(small_frames)))
+        for i, (rgb, depth, _) in enumerate(small_frames):
+            db = zlib.compress(depth.astype("<u2").tobytes()) if i % 2 else depth.astype("<u2").tobytes()
+            ib = rgb.tobytes()
+            f.write(struct.pack("<qii", i * 33333, len(db), len(ib)))
+            f.write(db)
+            f.write(ib)
+    cal = str(tmp_path / "cal.txt")
+    open(cal, "w").write(f"{K.fx} {K.fy} {K.cx} {K.cy}\n")
+    outs = []
+    for extra in ([], ["-nola"]):
+        out = subprocess.check_output([exe, "-l", klg, "-cal", cal, "-w", str(K.width), "-h", str(K.height), "-o", "-cap", "500000", "-ply", "-v"] + extra, text=True)
+        outs.append([l for l in out.split("\n") if l.startswith("frame ")])
+        assert f"{len(small_frames) - 1} frames" in out
+    assert [l.rsplit(" ", 2)[0] for l in outs[0]] == [l.rsplit(" ", 2)[0] for l in outs[1]]  # look-ahead changes nothing but the time
+    lines = open(klg + ".freiburg").read().strip().split("\n")
+    assert len(lines) == len(small_frames) - 1
+    ctx = capi.Context(capi.default_config(K.width, K.height, K.fx, K.fy, K.cx, K.cy, capacity=500000, time_delta=2147483647 // 2))
+    try:
+        for i, (rgb, d, _) in enumerate(small_frames[:-1]):
+            ctx.process_frame(rgb, d, i * 33333)
+        T = ctx.get_pose()
+    finally:
+        ctx.close()
+    last = [float(x) for x in lines[-1].split()]
+    assert abs(last[0] - (len(small_frames) - 2) * 33333 / 1e6) < 1e-6
+    assert np.abs(np.array(last[1:4]) - T[:3, 3]).max() < 1e-5
+    assert os.path.getsize(klg + ".ply") > 100
