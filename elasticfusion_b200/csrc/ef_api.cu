@@ -295,6 +295,13 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
   {
     const char* e = getenv("EF_NO_PDL");
     ctx->pdl = !(e && e[0] == '1');
+    e = getenv("EF_IT1_PREFETCH");
+    ctx->it1_prefetch = !(e && e[0] == '0');
+    e = getenv("EF_IT2_MAXBLOCKS");
+    ctx->it2_max_blocks = (e && atoi(e) > 0) ? atoi(e) : MAX_RGB_BLOCKS;
+    if (ctx->it2_max_blocks > MAX_RGB_BLOCKS) ctx->it2_max_blocks = MAX_RGB_BLOCKS;
+    ctx->plain_next = false;
+    ctx->maps_dirty[0] = ctx->maps_dirty[1] = true;
     e = getenv("EF_STAGE_TIMING");
     ctx->stage_timing = (e && e[0] == '1');
     ctx->stage_n = 0;

@@ -107,6 +107,11 @@ __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// The two halves separately, for the few kernels that do pose-independent work (loads of data no kernel in flight can be
+// writing) between them: pdl_launch() first, that work, then pdl_wait() before anything the predecessor may have written.
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // "last block done" ticket: returns true in every thread of the block that arrives last.
 __device__ __forceinline__ bool last_block_done(unsigned int* counter) {
   __shared__ bool is_last;

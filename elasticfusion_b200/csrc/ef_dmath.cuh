@@ -224,7 +224,14 @@ EFM_HD void rodrigues(const double* src, double* dst) {
   double rx = src[0], ry = src[1], rz = src[2];
   double theta = sqrt(rx * rx + ry * ry + rz * rz);
   if (theta >= DBL_EPSILON) {
-    double c = cos(theta), s = sin(theta), c1 = 1. - c;
+    double c, s;
+#ifdef __CUDA_ARCH__
+    sincos(theta, &s, &c);  // one range reduction for both
+#else
+    c = cos(theta);
+    s = sin(theta);
+#endif
+    const double c1 = 1. - c;
     double itheta = theta ? 1. / theta : 0.;
     rx *= itheta;
     ry *= itheta;

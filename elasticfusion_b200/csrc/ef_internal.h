@@ -207,6 +207,10 @@ struct EfContext {
   cudaEvent_t stage_ev[16];
   int stage_n;
   bool pdl;  // programmatic dependent launch on every kernel (default on; EF_NO_PDL=1 disables)
+  bool it1_prefetch;   // k_iter1 loads its first round of live-map pixels before griddepcontrol.wait (EF_IT1_PREFETCH=0 disables)
+  int it2_max_blocks;  // cap on k_iter2's grid (EF_IT2_MAXBLOCKS; default MAX_RGB_BLOCKS)
+  bool plain_next;     // the next ef_launch omits the programmatic-serialisation attribute (EF_PLAIN_NEXT)
+  bool maps_dirty[2];  // a kernel that writes tracker w's pyramids may still be in flight ahead of the next stage launch
 
   ef::OdomDev odom[2];
   ef::MapDev map;
@@ -253,8 +257,12 @@ inline void ef_launch(EfContext* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = ctx->pdl ? 1 : 0;
+  cfg.numAttrs = (ctx->pdl && !ctx->plain_next) ? 1 : 0;
+  ctx->plain_next = false;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
   ctx->launches++;
 }
 #define EF_LAUNCH(ctx, kernel, grid, block, smem, ...) ef_launch((ctx), kernel, dim3(grid), dim3(block), (smem), __VA_ARGS__)
+// the next launch is a plain stream-ordered one: it starts only after everything enqueued before it has completed, so no
+// kernel launched after it can become resident while earlier work is still running (a full barrier in the PDL chain)
+#define EF_PLAIN_NEXT(ctx) ((ctx)->plain_next = true)

@@ -493,8 +493,15 @@ __device__ __forceinline__ void icp_accumulate(const IcpFrame& F, const f3& s, c
 //  (b) the dense geometric rows (ICPReduction, reduce.cu:224-331) reduced to one 29-float partial per CTA.
 // vb / nvb: index and number of the (virtual) CTAs sharing the pass -- the launch grid for the stand-alone kernel, the
 // persistent grid for k_gn_loop. sred: 32 * THREADS/32 floats of shared memory.
+// First grid-stride round of the live maps of one thread (six 16-byte pieces), copied global -> shared asynchronously
+// (cp.async / LDGSTS: no registers are held while the copy is in flight) before griddepcontrol.wait. pre == nullptr: not staged.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int THREADS>
-__device__ __forceinline__ void iter1_body(const OdomDev& od, int level, int do_res, int do_icp, int vb, int nvb, float* sred) {
+__device__ __forceinline__ void iter1_body(const OdomDev& od, int level, int do_res, int do_icp, int vb, int nvb, float* sred, const float4* pre /* [6][THREADS] in shared memory, or nullptr */) {
   GNState* gn = od.gn;
   const int rows = od.rows[level], cols = od.cols[level];
   const int N = rows * cols;
@@ -567,12 +574,23 @@ __device__ __forceinline__ void iter1_body(const OdomDev& od, int level, int do_
       const int ngroups = N >> 2;
       for (int g = gid; g < ngroups; g += gstride) {
         const int i0 = g << 2;
-        const float4 vx4 = *reinterpret_cast<const float4*>(vc + i0);
-        const float4 vy4 = *reinterpret_cast<const float4*>(vc + plane + i0);
-        const float4 vz4 = *reinterpret_cast<const float4*>(vc + 2 * plane + i0);
-        const float4 nx4 = *reinterpret_cast<const float4*>(nc + i0);
-        const float4 ny4 = *reinterpret_cast<const float4*>(nc + plane + i0);
-        const float4 nz4 = *reinterpret_cast<const float4*>(nc + 2 * plane + i0);
+        float4 vx4, vy4, vz4, nx4, ny4, nz4;
+        if (pre && g == gid) {  // this thread's first round was staged in shared memory ahead of the dependency wait
+          cp_async_wait_all();
+          vx4 = pre[0 * THREADS + threadIdx.x];
+          vy4 = pre[1 * THREADS + threadIdx.x];
+          vz4 = pre[2 * THREADS + threadIdx.x];
+          nx4 = pre[3 * THREADS + threadIdx.x];
+          ny4 = pre[4 * THREADS + threadIdx.x];
+          nz4 = pre[5 * THREADS + threadIdx.x];
+        } else {
+          vx4 = *reinterpret_cast<const float4*>(vc + i0);
+          vy4 = *reinterpret_cast<const float4*>(vc + plane + i0);
+          vz4 = *reinterpret_cast<const float4*>(vc + 2 * plane + i0);
+          nx4 = *reinterpret_cast<const float4*>(nc + i0);
+          ny4 = *reinterpret_cast<const float4*>(nc + plane + i0);
+          nz4 = *reinterpret_cast<const float4*>(nc + 2 * plane + i0);
+        }
         const float vxs[4] = {vx4.x, vx4.y, vx4.z, vx4.w}, vys[4] = {vy4.x, vy4.y, vy4.z, vy4.w}, vzs[4] = {vz4.x, vz4.y, vz4.z, vz4.w};
         const float nxs[4] = {nx4.x, nx4.y, nx4.z, nx4.w}, nys[4] = {ny4.x, ny4.y, ny4.z, ny4.w}, nzs[4] = {nz4.x, nz4.y, nz4.z, nz4.w};
         // all four projections first, then all 24 gathers in flight together (the pass is bound by memory round trips, not
@@ -649,11 +667,36 @@ __device__ __forceinline__ void iter1_body(const OdomDev& od, int level, int do_
   }
 }
 
-__global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev od, int level, int do_res, int do_icp, int solve) {
-  pdl_enter();
+// prefetch != 0: the live vertex / normal maps of the thread's first grid-stride round are loaded BEFORE griddepcontrol.wait,
+// i.e. while the predecessor (the previous iteration's k_iter2, whose tail is a single CTA summing and solving) is still
+// running. Nothing in flight can be writing them: they were produced by the frame's input side, and the host puts one plain
+// (non-programmatic) launch between that and the first k_iter1 (odom_track_async: k_gn_begin), so every kernel that wrote
+// them had completed before any kernel of the Gauss-Newton loop could become resident.
+__global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev od, int level, int do_res, int do_icp, int solve, int prefetch) {
+  pdl_launch();
+  __shared__ __align__(16) float4 s_pre[6 * IT1_THREADS];
+  const float4* pre = nullptr;
+  if (prefetch && do_icp && (od.cols[level] & 3) == 0) {
+    const int N = od.rows[level] * od.cols[level];
+    const int gid = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
+    pre = s_pre;  // (uniform across the CTA; threads beyond the last pixel group never take the first round)
+    if (gid < (N >> 2)) {
+      const float* __restrict__ vc = od.vmap_curr[level];
+      const float* __restrict__ nc = od.nmap_curr[level];
+      const size_t plane = (size_t)N;
+      const int i0 = gid << 2;
+      cp_async16(&s_pre[0 * IT1_THREADS + threadIdx.x], vc + i0);
+      cp_async16(&s_pre[1 * IT1_THREADS + threadIdx.x], vc + plane + i0);
+      cp_async16(&s_pre[2 * IT1_THREADS + threadIdx.x], vc + 2 * plane + i0);
+      cp_async16(&s_pre[3 * IT1_THREADS + threadIdx.x], nc + i0);
+      cp_async16(&s_pre[4 * IT1_THREADS + threadIdx.x], nc + plane + i0);
+      cp_async16(&s_pre[5 * IT1_THREADS + threadIdx.x], nc + 2 * plane + i0);
+    }
+  }
+  pdl_wait();
   if (solve && od.gn->break_level == level) return;  // rgbOnly `break`: rest of the level is skipped
   __shared__ float sred[32 * (IT1_THREADS / 32)];
-  iter1_body<IT1_THREADS>(od, level, do_res, do_icp, blockIdx.x, gridDim.x, sred);
+  iter1_body<IT1_THREADS>(od, level, do_res, do_icp, blockIdx.x, gridDim.x, sred, pre);
 }
 
 // ---- photometric row: RGBReduction::getProducts (reduce.cu:419-480); the cloud point is recomputed from the gathered
@@ -1072,11 +1115,11 @@ inline int red_blocks(const EfContext* ctx, int n_items, int per_thread, int thr
   return b;
 }
 
-inline int iter2_blocks(int npx, bool rgb, int nb1) {
+inline int iter2_blocks(const EfContext* ctx, int npx, bool rgb, int nb1) {
   int b = rgb ? (npx / 8 + IT2_THREADS - 1) / IT2_THREADS : 1;  // candidates are typically <= 1/8 of the pixels; the loop strides anyway
   const int b_icp = (nb1 + 7) / 8;                              // <= 8 dense-pass partials pre-summed per CTA
   if (b_icp > b) b = b_icp;
-  return b < 1 ? 1 : (b > MAX_RGB_BLOCKS ? MAX_RGB_BLOCKS : b);
+  return b < 1 ? 1 : (b > ctx->it2_max_blocks ? ctx->it2_max_blocks : b);
 }
 
 #define EF_CHECK_LAST()                          \
@@ -1126,7 +1169,12 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
     }
   }
   if (which == 0) ctx->so3_ready = false;
+  // One plain launch between the frame's input side and the Gauss-Newton loop: k_gn_begin starts only when everything before it
+  // has completed, so k_iter1 may read the live maps ahead of its dependency wait (see k_iter1).
+  const int prefetch = ctx->it1_prefetch ? 1 : 0;
+  if (prefetch) EF_PLAIN_NEXT(ctx);
   EF_LAUNCH(ctx, k_gn_begin, 1, GN_BEGIN_THREADS, 0, od.gn, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0, (const So3State*)od.so3s, od.trace);
+  ctx->maps_dirty[which] = false;
   ef_stage(ctx, 4);
   EF_LAUNCH(ctx, k_gn_seed, 1, 32, 0, od.gn, ns ? sched_level[0] : 0, (const So3State*)od.so3s);
   for (int s = 0; s < ns; ++s) {
@@ -1134,8 +1182,8 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
     const int npx = od.rows[lv] * od.cols[lv];
     const int next_lv = (s + 1 < ns) ? sched_level[s + 1] : -1;
     const int nb1 = red_blocks(ctx, npx, 4, IT1_THREADS, IT1_CTAS_PER_SM);
-    EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, lv, rgb ? 1 : 0, icp ? 1 : 0, 1);
-    const int nb2 = iter2_blocks(npx, rgb, icp ? nb1 : 0);
+    EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, lv, rgb ? 1 : 0, icp ? 1 : 0, 1, prefetch);
+    const int nb2 = iter2_blocks(ctx, npx, rgb, icp ? nb1 : 0);
     EF_LAUNCH(ctx, k_iter2, nb2, IT2_THREADS, 0, od, lv, sched_iter[s], next_lv, nb1, (rgb ? 1 | 8 : 0) | (icp ? 2 : 0) | 4, 0.f);
   }
   ef_stage(ctx, 5);
@@ -1163,20 +1211,36 @@ int odom_set_pose_async(EfContext* ctx, int which, const double* T_dev) {
   return 0;
 }
 
+// Stage-API launches of k_iter1: the live maps may have been written by a kernel that is still in flight (an init stage
+// called just before). The first such launch is a plain stream-ordered one (a full barrier); until an init stage runs again
+// the maps are static and later launches may read them ahead of their dependency wait.
+static int stage_prefetch(EfContext* ctx, int which) {
+  if (!ctx->it1_prefetch) return 0;
+  if (ctx->maps_dirty[which]) {
+    EF_PLAIN_NEXT(ctx);
+    ctx->maps_dirty[which] = false;
+  }
+  return 1;
+}
+
 // stand-alone reduction launches for the stage API
 int launch_se3_step_raw(EfContext* ctx, int which, int level, bool do_icp, bool do_rgb, float sigma) {
   OdomDev& od = ctx->odom[which];
   const int npx = od.rows[level] * od.cols[level];
   const int nb1 = red_blocks(ctx, npx, 4, IT1_THREADS, IT1_CTAS_PER_SM);
-  if (do_icp) EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, level, 0, 1, 0);
-  EF_LAUNCH(ctx, k_iter2, iter2_blocks(npx, do_rgb, do_icp ? nb1 : 0), IT2_THREADS, 0, od, level, 0, -1, nb1, (do_rgb ? 1 | 16 : 0) | (do_icp ? 2 : 0), sigma);
+  if (do_icp) {
+    const int prefetch = stage_prefetch(ctx, which);
+    EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, level, 0, 1, 0, prefetch);
+  }
+  EF_LAUNCH(ctx, k_iter2, iter2_blocks(ctx, npx, do_rgb, do_icp ? nb1 : 0), IT2_THREADS, 0, od, level, 0, -1, nb1, (do_rgb ? 1 | 16 : 0) | (do_icp ? 2 : 0), sigma);
   EF_CHECK_LAST();
   return 0;
 }
 int launch_icp_dense_only(EfContext* ctx, int which, int level) {
   OdomDev& od = ctx->odom[which];
   const int nb1 = red_blocks(ctx, od.rows[level] * od.cols[level], 4, IT1_THREADS, IT1_CTAS_PER_SM);
-  EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, level, 0, 1, 0);
+  const int prefetch = stage_prefetch(ctx, which);
+  EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, level, 0, 1, 0, prefetch);
   EF_CHECK_LAST();
   return 0;
 }
@@ -1184,7 +1248,7 @@ int launch_rgb_residual_raw(EfContext* ctx, int which, int level) {
   OdomDev& od = ctx->odom[which];
   const int npx = od.rows[level] * od.cols[level];
   const int nb1 = red_blocks(ctx, npx, 4, IT1_THREADS, IT1_CTAS_PER_SM);
-  EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, level, 1, 0, 0);
+  EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, level, 1, 0, 0, 0);
   EF_LAUNCH(ctx, k_iter2, 1, IT2_THREADS, 0, od, level, 0, -1, nb1, 8, 0.f);
   cudaError_t e = cudaMemsetAsync(od.corres[level], 0, (size_t)npx * sizeof(DataTerm), ctx->stream);
   if (e != cudaSuccess) return (int)e;

@@ -413,6 +413,7 @@ void scan_scratch(EfContext* ctx, uint8_t** flags, int** offsets);
 
 int odom_init_icp_depth(EfContext* ctx, int which, const uint16_t* depth_dev, float cutoff) {
   OdomDev& od = ctx->odom[which];
+  ctx->maps_dirty[which] = true;
   cudaError_t e = cudaMemcpyAsync(od.depth_tmp[0], depth_dev, sizeof(uint16_t) * od.width * od.height, cudaMemcpyDeviceToDevice, ctx->stream);
   if (e != cudaSuccess) return (int)e;
   for (int i = 1; i < NUM_PYRS; ++i)
@@ -453,6 +454,7 @@ static int copy_and_resize(EfContext* ctx, OdomDev& od, const float* vtx4, const
 
 int odom_init_icp_pred(EfContext* ctx, int which, const float* vtx4, const float* nrm4) {
   OdomDev& od = ctx->odom[which];
+  ctx->maps_dirty[which] = true;
   return copy_and_resize(ctx, od, vtx4, nrm4, od.vmap_curr, od.nmap_curr);
 }
 

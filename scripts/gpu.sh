@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: scripts/gpu.sh <timeout_s> <command...>   -- retries gpurun while the pod answers "busy" (exit 3), up to ~40 min
 T=$1; shift
-for i in $(seq 1 20); do
+for i in $(seq 1 100); do
   /usr/local/graft/bin/gpurun --timeout "$T" -- "$@"
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
