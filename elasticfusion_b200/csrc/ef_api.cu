@@ -43,6 +43,7 @@ int map_set_graph(EfContext* ctx, const float* nodes16, int n_nodes);
 int map_loop_constraints_async(EfContext* ctx, int count_thresh, float err_thresh, float cov_thresh);
 int map_loop_reset_async(EfContext* ctx);
 int odom_copy_pose_async(EfContext* ctx, int dst, int src);
+int map_resize_to_host(EfContext* ctx, const void* src_dev, int elem, int factor, void* host_out);
 int map_raycast_async(EfContext* ctx, float max_depth, float conf_threshold, int time, int max_time, int time_delta, int mode,
                       bool use_device_tick);
 int map_fill_in_async(EfContext* ctx, bool passthrough_geometry, bool passthrough_image);
@@ -516,6 +517,18 @@ extern "C" int ef_buffer(EfContext* ctx, int32_t id, int32_t level, void** dev_p
   return 0;
 }
 
+extern "C" int ef_resize(EfContext* ctx, int32_t id, int32_t factor, void* host_out, size_t bytes) {
+  if (!ctx || !host_out || factor < 1) return EF_EINVAL;
+  void* p;
+  size_t b;
+  RC(ef_buffer(ctx, id, 0, &p, &b));
+  if (id >= 40) return EF_EINVAL;  // full-resolution image attachments only
+  const size_t n = (size_t)ctx->cfg.width * ctx->cfg.height;
+  const int elem = (int)(b / n);
+  if (elem != 2 && elem != 4 && elem != 16) return EF_EINVAL;
+  if (bytes < (size_t)(ctx->cfg.width / factor) * (ctx->cfg.height / factor) * elem) return EF_EINVAL;
+  return map_resize_to_host(ctx, p, elem, factor, host_out);
+}
 extern "C" int ef_upload(EfContext* ctx, int32_t id, int32_t level, const void* host, size_t bytes) {
   void* p;
   size_t b;
@@ -1010,7 +1023,7 @@ static int local_loop_async(EfContext* ctx) {
   OdomDev& od = ctx->odom[1];
   RC(map_raycast_async(ctx, ctx->max_depth_processed, ctx->confidence, 0, ctx->tick - ctx->cfg.time_delta, ctx->cfg.time_delta, 1, false));
   RC(odom_copy_pose_async(ctx, 1, 0));
-  RC(odom_init_icp_model(ctx, 1, (const float*)t.old_vertex, (const float*)t.old_normal));
+  RC(odom_init_icp_model(ctx, 1, (const float*)t.old_vertex, (const float*)t.old_normal, nullptr, nullptr, nullptr, false));
   RC(odom_populate(ctx, 1, (const uint8_t*)t.old_image, od.lastDepth, od.lastImage, true));
   RC(odom_init_icp_pred(ctx, 1, (const float*)t.vertex, (const float*)t.normal));
   RC(odom_populate(ctx, 1, (const uint8_t*)t.image, od.nextDepth, od.nextImage, true));

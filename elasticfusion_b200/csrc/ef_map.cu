@@ -1521,6 +1521,41 @@ int map_upload_range(EfContext* ctx, const float* in, int first, int n) {
   return 0;
 }
 
+// Resize::image / vertex / time (Resize.cpp:50-159, resize.frag): the source sampled at the centres of a (cols/factor) x
+// (rows/factor) grid with nearest filtering. elem: bytes per texel (4 RGBA8, 16 RGBA32F, 2 R16UI); out: device, tightly packed.
+__global__ void k_resize_nearest(const uint8_t* __restrict__ src, int rows, int cols, int factor, int elem, uint8_t* __restrict__ out) {
+  pdl_enter();
+  const int drows = rows / factor, dcols = cols / factor, n = drows * dcols;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+    const int j = q / dcols, i = q - j * dcols;
+    const int sx = texel(((float)i + 0.5f) / (float)dcols, cols), sy = texel(((float)j + 0.5f) / (float)drows, rows);
+    const uint8_t* s = src + ((size_t)sy * cols + sx) * elem;
+    uint8_t* d = out + (size_t)q * elem;
+    if (elem == 16)
+      *reinterpret_cast<float4*>(d) = *reinterpret_cast<const float4*>(s);
+    else if (elem == 4)
+      *reinterpret_cast<uint32_t*>(d) = *reinterpret_cast<const uint32_t*>(s);
+    else
+      *reinterpret_cast<uint16_t*>(d) = *reinterpret_cast<const uint16_t*>(s);
+  }
+}
+int map_resize_to_host(EfContext* ctx, const void* src_dev, int elem, int factor, void* host_out) {
+  MapDev& m = ctx->map;
+  MapBuffers& B = mb(ctx);
+  if (factor < 1 || m.rows / factor < 1 || m.cols / factor < 1) return EF_EINVAL;
+  const size_t n = (size_t)(m.rows / factor) * (m.cols / factor);
+  if (n * elem > B.aos_cap * 48) {
+    if (B.aos) cudaFree(B.aos);
+    B.aos = nullptr;
+    CU(cudaMalloc((void**)&B.aos, n * elem + 48));
+    B.aos_cap = (n * elem + 47) / 48;
+  }
+  EF_LAUNCH(ctx, k_resize_nearest, sblocks(ctx, n), 256, 0, (const uint8_t*)src_dev, m.rows, m.cols, factor, elem, (uint8_t*)B.aos);
+  CU(cudaMemcpyAsync(host_out, B.aos, n * elem, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 // deformation graph for the next clean (GlobalModel.cpp:542-546: glTexSubImage2D of the node texture); nodes: HOST, 16 floats each
 int map_set_graph(EfContext* ctx, const float* nodes16, int n_nodes) {
   MapDev& m = ctx->map;

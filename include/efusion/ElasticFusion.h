@@ -142,6 +142,7 @@ class GPUTexture {
   }
   void download(void* host) const { ef::check(ef_download(ctx_, id_, 0, host, bytes()), "ef_download"); }
   int id() const { return id_; }
+  EfContext* context() const { return ctx_; }
 
  private:
   EfContext* ctx_;
@@ -259,11 +260,14 @@ class GlobalModel {
     ef::check(ef_map_fuse(ctx_, T, time, depthCutoff, weighting), "fuse");
   }
   void clean(const ef::SE3d& T_wc, const int& time, GPUTexture*, GPUTexture*, GPUTexture*, GPUTexture*, GPUTexture*, const float confThreshold,
-             std::vector<float>& graph, const int timeDelta, const float maxDepth, const bool) {
-    if (!graph.empty()) ef::check(EF_EINVAL, "clean: deformation graphs are outside the scope of libefusion_b200");
+             std::vector<float>& graph, const int timeDelta, const float maxDepth, const bool isFern) {
     double T[16];
     ef::toRowMajor(T_wc, T);
-    ef::check(ef_map_clean(ctx_, T, time, confThreshold, timeDelta, maxDepth), "clean");
+    // graph: 16 floats per node as Deformation::constrain writes them (Core/Deformation.cpp:175-189); the time-stamp refresh of
+    // deformed surfels reads IndexMap::depthTex(), i.e. the last synthesizeDepth
+    ef::check(ef_map_clean_deform(ctx_, T, time, confThreshold, timeDelta, maxDepth, graph.empty() ? nullptr : graph.data(), (int32_t)(graph.size() / 16),
+                                  isFern ? 1 : 0),
+              "clean");
   }
   uint32_t lastCount() {
     int32_t n = 0;

@@ -274,6 +274,9 @@ enum {
 int ef_buffer(EfContext* ctx, int32_t id, int32_t level, void** dev_ptr, size_t* bytes);
 int ef_upload(EfContext* ctx, int32_t id, int32_t level, const void* host, size_t bytes);
 int ef_download(EfContext* ctx, int32_t id, int32_t level, void* host, size_t bytes);
+/* Resize::image / vertex / time (Core/Shaders/Resize.cpp:50-159): the named full-resolution attachment (RGBA8, RGBA32F or
+ * R16UI) sampled on the (W/factor) x (H/factor) grid of texel centres with nearest filtering, into HOST memory, tightly packed. */
+int ef_resize(EfContext* ctx, int32_t id, int32_t factor, void* host_out, size_t bytes);
 /* number of kernels launched by this context since creation (bench.py's gpu_launches) */
 int ef_launch_count(EfContext* ctx, int64_t* n);
 /* EF_STAGE_TIMING=1 in the environment at ef_create: milliseconds between the stage events of the last frame, out[16]:

@@ -122,3 +122,25 @@ def test_headless_cli_matches_c_abi(tmp_path, small_K, small_frames):
     assert abs(last[0] - (len(small_frames) - 2) * 33333 / 1e6) < 1e-6
     assert np.abs(np.array(last[1:4]) - T[:3, 3]).max() < 1e-5
     assert os.path.getsize(klg + ".ply") > 100
+
+
+@pytest.mark.gpu
+def test_ferns_keyframes_and_relocalisation_candidate(tmp_path, K):
+    """include/efusion/Ferns.h (Core/Ferns.h:36-166, Ferns.cpp:22-420): frames are encoded at W/8 x H/8 and stored when dissimilar
+    enough; findFrame on a revisited view proposes a stored frame and its 80x60 ICP-only registration (third RGBDOdometry
+    instance of the reference) recovers the camera pose; 50-sample surface constraints come back."""
+    from elasticfusion_b200 import synth
+
+    exe = str(tmp_path / "ferns_check")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", f"-I{ROOT}/include/efusion", f"-I{ROOT}/include",
+                           os.path.join(ROOT, "tests", "cpp", "ferns_check.cpp"), "-o", exe, f"-L{ROOT}/elasticfusion_b200", "-lefusion",
+                           f"-Wl,-rpath,{ROOT}/elasticfusion_b200", f"-L{CUDA_LIB}", "-lcudart", "-lz"])
+    frames = list(synth.sequence(31, K, seed=17, noise=True, speed=3.0))
+    klg = str(tmp_path / "ferns.klg")
+    synth.write_klg(klg, [(f[0], f[1]) for f in frames])
+    out = subprocess.check_output([exe, klg, str(K.width), str(K.height), str(K.fx), str(K.fy), str(K.cx), str(K.cy), "400"], text=True)
+    kv = dict(zip(out.split()[0::2], out.split()[1::2]))
+    assert int(kv["FRAMES"]) == 30 and int(kv["STORED"]) >= 1 and int(kv["STORED"]) == int(kv["ADDED"])
+    assert int(kv["CLOSEST"]) >= 0, out
+    assert float(kv["ICPERR"]) < 3e-4 and float(kv["ICPCOUNT"]) > 2400 and float(kv["PHOTO"]) < 115, out
+    assert float(kv["TDIFF"]) < 0.03 and int(kv["CONSTRAINTS"]) > 10, out
