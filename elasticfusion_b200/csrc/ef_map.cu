@@ -5,9 +5,11 @@
 // driven by a single-pass decoupled look-back scan; the per-surfel "update map" render target (3 x 3072^2 RGBA32F,
 // cleared every frame, GlobalModel.cpp:375-378) becomes a 4-byte-per-surfel winner slot touched only by matches.
 //
-// GL semantics encoded: nearest sampling texel = clamp(floor(coord*size)); 1-px points at
-// floor(window xy), clipped by centre; point sprites cover pixel centres in [xw - s/2, xw + s/2), size clamped to
-// [1, 2047]; window depth round(z * (2^24-1)); fragments at depth 1.0 fail GL_LESS against the clear value.
+// GL semantics encoded, pinned by executing the reference's shader files on Mesa llvmpipe (oracle/gl):
+// nearest sampling texel = clamp(floor(coord*size)); window coordinates snapped to 1/256 px; 1-px points cover the pixel whose
+// centre lies in the half-open unit square around the snapped position, clipped by centre; point sprites cover the pixel centres
+// in the half-open square of their size, size clamped to [1, 2047]; window depth round(z * (2^24-1)); fragments at depth 1.0
+// fail GL_LESS against the clear value.
 #include <float.h>
 #include <stddef.h>
 
@@ -98,6 +100,19 @@ __device__ __forceinline__ f3 vertex_u(const uint16_t* depth, int rows, int cols
   iy = iy < 0 ? 0 : (iy >= rows ? rows - 1 : iy);
   const float z = (float)depth[(size_t)iy * cols + ix] / 1000.0f;
   return mk3(((float)x - c.cx) * z * ifx, ((float)y - c.cy) * z * ify, z);
+}
+// GL rasterises in fixed point: window coordinates are snapped to 1/256 pixel (GL_SUBPIXEL_BITS = 8 on Mesa llvmpipe and on NVIDIA
+// GPUs), the pixel-centre offset removed first. A size-1 point then covers the pixel whose centre lies in the half-open unit
+// square around the snapped coordinate, a sprite the pixels whose centres lie in the half-open square of its (snapped) size.
+// Pinned by running the reference's index_map / splat shaders on Mesa (oracle/gl, tests/golden/ref_mapping_*.npz).
+__device__ __forceinline__ int snap256(float w) { return __float2int_rn((w - 0.5f) * 256.0f); }
+__device__ __forceinline__ int point_pixel(float w) { return (snap256(w) + 127) >> 8; }
+__device__ __forceinline__ void sprite_range(float w, float size, int& p0, int& p1) {
+  int fw = __float2int_rn(size * 256.0f);
+  if (fw < 256) fw = 256;
+  const int x0 = snap256(w) - fw / 2;
+  p0 = (x0 + 255) >> 8;
+  p1 = ((x0 + fw + 255) >> 8) - 1;
 }
 __device__ __forceinline__ unsigned int depth24(float zw) {
   if (!(zw > 0.f)) zw = 0.f;
@@ -314,7 +329,7 @@ __global__ void k_index_scatter(const float4* __restrict__ pos_conf, const float
     if (!(xn >= -1.f && xn <= 1.f && yn >= -1.f && yn <= 1.f && zn >= -1.f && zn <= 1.f)) continue;
     const float xw = (xn + 1.0f) * (fcols * 0.5f);
     const float yw = (yn + 1.0f) * (frows * 0.5f);
-    const int px = (int)floorf(xw), py = (int)floorf(yw);
+    const int px = point_pixel(xw), py = point_pixel(yw);
     if (px < 0 || py < 0 || px >= cols || py >= rows) continue;
     const unsigned int d24 = depth24(0.5f * zn + 0.5f);
     if (d24 >= 16777215u) continue;
@@ -1002,10 +1017,9 @@ __global__ void __launch_bounds__(SPLAT_THREADS) k_splat_scatter(RayArgs a, cons
     Splat sp;
     int x0 = 0, y0 = 0, bw = 0, nfrag = 0;
     if (id < n && splat_vertex(a, mp, pos_conf[id], color_time[id], norm_rad, id, sp)) {
-      const float half = sp.size * 0.5f;
-      x0 = (int)ceilf((sp.xw - half) - 0.5f);
-      y0 = (int)ceilf((sp.yw - half) - 0.5f);
-      int x1 = (int)ceilf((sp.xw + half) - 0.5f) - 1, y1 = (int)ceilf((sp.yw + half) - 0.5f) - 1;
+      int x1, y1;
+      sprite_range(sp.xw, sp.size, x0, x1);
+      sprite_range(sp.yw, sp.size, y0, y1);
       x0 = max(x0, 0);
       y0 = max(y0, 0);
       x1 = min(x1, a.cols - 1);

@@ -127,6 +127,18 @@ inline f3 vertex_u(const uint16_t* depth, int rows, int cols, int ix, int iy, in
   return mk3(((float)x - c.cx) * z * ifx, ((float)y - c.cy) * z * ify, z);
 }
 
+// fixed-point window coordinate of a point / sprite centre: round((w - 0.5) * 256), the pixel-centre offset removed
+inline int snap256(float w) { return (int)lrintf((w - 0.5f) * 256.0f); }
+// the pixel whose centre lies in the half-open unit square around the snapped coordinate
+inline int point_pixel(float w) { return (snap256(w) + 127) >> 8; }
+// pixel range [p0, p1] whose centres lie in the half-open square of side `size` around the snapped centre
+inline void sprite_range(float w, float size, int& p0, int& p1) {
+  int fw = (int)lrintf(size * 256.0f);
+  if (fw < 256) fw = 256;
+  const int x0 = snap256(w) - fw / 2;
+  p0 = (x0 + 255) >> 8;
+  p1 = ((x0 + fw + 255) >> 8) - 1;
+}
 inline uint32_t depth24(float zw) {
   if (!(zw > 0.f)) zw = 0.f;
   if (zw > 1.f) zw = 1.f;
@@ -270,7 +282,10 @@ extern "C" void efo_predict_indices(const float* map, int count, const double* T
     if (!(xn >= -1.f && xn <= 1.f && yn >= -1.f && yn <= 1.f && zn >= -1.f && zn <= 1.f)) continue;
     float xw = (xn + 1.0f) * (fcols * 0.5f);
     float yw = (yn + 1.0f) * (frows * 0.5f);
-    int px = (int)floorf(xw), py = (int)floorf(yw);
+    // Window coordinates are snapped to 1/256 pixel before rasterisation (GL_SUBPIXEL_BITS = 8 on Mesa llvmpipe and on NVIDIA
+    // hardware), and a size-1 point is the half-open square [xs - 0.5, xs + 0.5): pinned against the reference's shaders
+    // run on Mesa (tests/golden/ref_mapping_*.npz).
+    const int px = point_pixel(xw), py = point_pixel(yw);
     if (px < 0 || py < 0 || px >= cols || py >= rows) continue;
     uint32_t d24 = depth24(0.5f * zn + 0.5f);
     if (d24 >= 16777215u) continue;  // GL_LESS against the cleared depth 1.0
@@ -733,10 +748,9 @@ inline bool splat_fragment(const Splat& sp, const Cam& c, int px, int py, f3& co
 
 inline void splat_bounds(const Splat& sp, int rows, int cols, int& x0, int& x1, int& y0, int& y1) {
   float half = sp.size * 0.5f;
-  x0 = (int)ceilf((sp.xw - half) - 0.5f);
-  x1 = (int)ceilf((sp.xw + half) - 0.5f) - 1;
-  y0 = (int)ceilf((sp.yw - half) - 0.5f);
-  y1 = (int)ceilf((sp.yw + half) - 0.5f) - 1;
+  (void)half;
+  sprite_range(sp.xw, sp.size, x0, x1);
+  sprite_range(sp.yw, sp.size, y0, y1);
   if (x0 < 0) x0 = 0;
   if (y0 < 0) y0 = 0;
   if (x1 >= cols) x1 = cols - 1;

@@ -246,10 +246,27 @@ void (*_XLockMutex_fn)(void*) = NULL;
 void (*_XUnlockMutex_fn)(void*) = NULL;
 void* _Xglobal_lock = NULL;
 
+/* Mesa's GLX registers itself by walking / prepending to Display::ext_procs, a PRIVATE member of struct _XDisplay (Xlibint.h:
+ * at byte 0x140 on LP64, after xdefaults, scratch_buffer, scratch_length, ext_number); struct _XExten = { next, XExtCodes codes,
+ * nine hook pointers (close_display at 0x48), char* name at 0x60, ... }. */
+typedef struct _XExten {
+  struct _XExten* next;
+  XExtCodes codes;
+  void* hooks[9];
+  char* name;
+  void* more[16];
+} XExten;
 XExtCodes* XAddExtension(Display* d) {
-  (void)d;
-  static XExtCodes codes = {1, 128, 64, 128};
-  return &codes;
+  XExten* e = (XExten*)calloc(1, sizeof(XExten));
+  XExten** head = (XExten**)((char*)d + 0x140);
+  static int next_ext = 1;
+  e->codes.extension = next_ext++;
+  e->codes.major_opcode = 128 + e->codes.extension;
+  e->codes.first_event = 64;
+  e->codes.first_error = 128;
+  e->next = *head;
+  *head = e;
+  return &e->codes;
 }
 Bool XQueryExtension(Display* d, const char* name, int* major, int* ev, int* err) {
   (void)d;

@@ -170,9 +170,14 @@ def test_index_map_depth_test_and_id_zero_quirk(small_K):
 
     s = np.array([surfel(0, 0, 2.0), surfel(0, 0, 1.0), surfel(0.3, 0, 1.5), surfel(0.3, 0, 1.5)], np.float32)
     idx, vc, ct, nr = eo.predict_indices(s, np.eye(4), 2, 20.0, 1 << 30, K)
-    cy, cx = int(K.cy), int(K.cx)
+    # window coordinates are snapped to 1/256 px and a 1-px point covers the half-open unit square around them: a point that
+    # projects exactly onto the integer coordinate (cx, cy) lands in pixel (cx - 1, cy - 1) -- the behaviour of the reference's
+    # index_map shaders on Mesa llvmpipe (tests/golden/ref_mapping_160x120.npz pins it on real data)
+    pix = lambda w: (int(round((w - 0.5) * 256)) + 127) >> 8
+    cy, cx = pix(K.cy), pix(K.cx)
+    assert (cy, cx) == (int(K.cy) - 1, int(K.cx) - 1)
     assert idx[cy, cx] == 1 and vc[cy, cx, 2] == 1.0
-    px = int(np.floor(K.fx * 0.3 / 1.5 + K.cx))
+    px = pix(K.fx * 0.3 / 1.5 + K.cx)
     assert idx[cy, px] == 2  # equal depth: earlier primitive
     assert (idx > 0).sum() == 2
     s0 = np.array([surfel(0, 0, 1.0)], np.float32)
