@@ -123,22 +123,31 @@ __device__ __forceinline__ unsigned int depth24(float zw) {
 
 // The reference walks a 4x4 sample window with float loop counters (data.vert:132-160, copy_unstable.vert:75-111):
 //   for (float i = c - 2*step; i < c + 2*step; i += step)   with step = half a texel, nearest sampling.
-// The samples land on <= 3 distinct texels per axis, some of them twice. This evaluates the float loop literally once per axis
-// and returns the distinct texel indices (ascending, first-occurrence order) with how many samples hit each.
-__device__ __forceinline__ int window_axis(float centre, float step, int n, int (&tex)[3], int (&mult)[3]) {
-  int cnt = 0;
+// The samples are monotone and half a texel apart, so they land on at most three consecutive texels t0, t0+1, t0+2, some of
+// them twice. This evaluates the float loop literally once per axis (it runs 4 times, 5 when rounding leaves the accumulated
+// counter just short of the bound) and returns the first texel with how many samples hit each of the three. No array is
+// indexed dynamically (registers only).
+struct WinAxis {
+  int t0;
+  int m[3];
+};
+__device__ __forceinline__ WinAxis window_axis(float centre, float step, int n) {
+  WinAxis A;
   const float lo = centre - (1.0f * step * 2.0f), hi = centre + (1.0f * step * 2.0f);
-  for (float i = lo; i < hi; i += step) {
-    const int t = texel(i, n);
-    if (cnt > 0 && tex[cnt - 1] == t) {
-      mult[cnt - 1]++;
-    } else if (cnt < 3) {
-      tex[cnt] = t;
-      mult[cnt] = 1;
-      cnt++;
+  A.t0 = texel(lo, n);
+  A.m[0] = A.m[1] = A.m[2] = 0;
+  float i = lo;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    if (i < hi) {
+      const int d = texel(i, n) - A.t0;
+      A.m[0] += (d == 0);
+      A.m[1] += (d == 1);
+      A.m[2] += (d >= 2);
     }
+    i += step;
   }
-  return cnt;
+  return A;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -442,22 +451,34 @@ __global__ void k_fuse_associate(FuseArgs a, const int* __restrict__ count, uint
       const float lambda = sqrtf(xl * xl + yl * yl + 1);
       const f3 ray = mk3(xl, yl, 1);
       // duplicates of a texel cannot change the outcome (strict `dist < bestDist`), so each distinct texel is visited once,
-      // in the reference's order (x outer, y inner, ascending)
-      int tx[3], mx[3], ty[3], my[3];
-      const int nx = window_axis(tcx, indexXStep, a.cols, tx, mx);
-      const int ny = window_axis(tcy, indexYStep, a.rows, ty, my);
-      for (int ia = 0; ia < nx; ++ia)
-        for (int jb = 0; jb < ny; ++jb) {
-          const int p = ty[jb] * a.cols + tx[ia];
-          const uint32_t current = a.index[p];
+      // in the reference's order (x outer, y inner, ascending). All nine index texels are fetched first, then the attributes
+      // of the occupied ones column by column: four dependent memory round trips instead of one or two per texel.
+      const WinAxis ax = window_axis(tcx, indexXStep, a.cols), ay = window_axis(tcy, indexYStep, a.rows);
+      uint32_t cur[9];
+#pragma unroll
+      for (int ia = 0; ia < 3; ++ia)
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb)
+          cur[ia * 3 + jb] = (ax.m[ia] > 0 && ay.m[jb] > 0) ? a.index[(ay.t0 + jb) * a.cols + (ax.t0 + ia)] : 0u;
+#pragma unroll
+      for (int ia = 0; ia < 3; ++ia) {
+        float4 vc[3], nr[3];
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb)
+          if (cur[ia * 3 + jb] > 0U) {
+            const int p = (ay.t0 + jb) * a.cols + (ax.t0 + ia);
+            vc[jb] = a.vert_conf[p];
+            nr[jb] = a.norm_rad[p];
+          }
+#pragma unroll
+        for (int jb = 0; jb < 3; ++jb) {
+          const uint32_t current = cur[ia * 3 + jb];
           if (current > 0U) {
-            const float4 vc = a.vert_conf[p];
-            if (fabsf((vc.z * lambda) - (vPosLocal.z * lambda)) < 0.05f) {
-              const float dist = norm(cross(ray, mk3(vc.x, vc.y, vc.z))) / norm(ray);
-              const float4 nr = a.norm_rad[p];
-              const f3 nrm = mk3(nr.x, nr.y, nr.z);
+            if (fabsf((vc[jb].z * lambda) - (vPosLocal.z * lambda)) < 0.05f) {
+              const float dist = norm(cross(ray, mk3(vc[jb].x, vc[jb].y, vc[jb].z))) / norm(ray);
+              const f3 nrm = mk3(nr[jb].x, nr[jb].y, nr[jb].z);
               const float ang = acosf(dot(nrm, vNormLocal) / (norm(nrm) * norm(vNormLocal)));
-              if (dist < bestDist && (fabsf(nr.z) < 0.75f || fabsf(ang) < 0.5f)) {
+              if (dist < bestDist && (fabsf(nr[jb].z) < 0.75f || fabsf(ang) < 0.5f)) {
                 counter++;
                 bestDist = dist;
                 best = current;
@@ -465,6 +486,7 @@ __global__ void k_fuse_associate(FuseArgs a, const int* __restrict__ count, uint
             }
           }
         }
+      }
       if (counter > 0) {
         res = best;
         if ((int)best < cnt) atomicMin(&pending[best], d);  // lowest draw index wins the update-map texel
@@ -686,18 +708,29 @@ __device__ __forceinline__ bool clean_test(const CleanArgs& a, const MapPose* mp
   if ((float)a.time - col.w < (float)a.time_delta && localPos.z > 0 && x > 0 && y > 0 && x < fcols && y < frows) {
     const f3 localNorm = normalized(rot(mp->t_inv, mk3(nr.x, nr.y, nr.z)));
     // duplicate samples COUNT here (copy_unstable.vert:94,106): each distinct texel is read once and
-    // weighted by the number of float-loop samples that land on it
-    int tx[3], mx[3], ty[3], my[3];
-    const int nx = window_axis(x / fcols, indexXStep, a.cols, tx, mx);
-    const int ny = window_axis(y / frows, indexYStep, a.rows, ty, my);
-    for (int ia = 0; ia < nx; ++ia)
-      for (int jb = 0; jb < ny; ++jb) {
-        const int p = ty[jb] * a.cols + tx[ia];
-        const uint32_t current = a.index[p];
-        if (current > 0U) {
-          const int m = mx[ia] * my[jb];
-          const float4 vc = a.vert_conf[p];
-          const float4 ct = a.col_time[p];
+    // weighted by the number of float-loop samples that land on it. Index texels first, attributes of the occupied ones after.
+    const WinAxis ax = window_axis(x / fcols, indexXStep, a.cols), ay = window_axis(y / frows, indexYStep, a.rows);
+    uint32_t cur[9];
+#pragma unroll
+    for (int ia = 0; ia < 3; ++ia)
+#pragma unroll
+      for (int jb = 0; jb < 3; ++jb)
+        cur[ia * 3 + jb] = (ax.m[ia] > 0 && ay.m[jb] > 0) ? a.index[(ay.t0 + jb) * a.cols + (ax.t0 + ia)] : 0u;
+#pragma unroll
+    for (int ia = 0; ia < 3; ++ia) {
+      float4 vcs[3], cts[3];
+#pragma unroll
+      for (int jb = 0; jb < 3; ++jb)
+        if (cur[ia * 3 + jb] > 0U) {
+          const int p = (ay.t0 + jb) * a.cols + (ax.t0 + ia);
+          vcs[jb] = a.vert_conf[p];
+          cts[jb] = a.col_time[p];
+        }
+#pragma unroll
+      for (int jb = 0; jb < 3; ++jb)
+        if (cur[ia * 3 + jb] > 0U) {
+          const int m = ax.m[ia] * ay.m[jb];
+          const float4 vc = vcs[jb], ct = cts[jb];
           const float dx = vc.x - localPos.x, dy = vc.y - localPos.y;
           if (ct.z < col.z && vc.w > a.conf_threshold && vc.z > localPos.z && vc.z - localPos.z < 0.01f &&
               sqrtf(dx * dx + dy * dy) < nr.w * 1.4f)
@@ -706,7 +739,7 @@ __device__ __forceinline__ bool clean_test(const CleanArgs& a, const MapPose* mp
               fabsf(localNorm.z) > 0.85f)
             zCount += m;
         }
-      }
+    }
   }
   if (count > 8 || zCount > 4) test = 0;
   if (col.w == -2) col.w = (float)a.time;
@@ -751,7 +784,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 //    culled before them: the common case for the old, stable bulk of a map sorted by init time) are not written at all:
 //    48 B read per surfel and no write, against 48 + 48 for the reference's VBO-to-VBO pass (GlobalModel.cpp:527-671);
 //  * the last CTA to leave publishes the new count and clears the new-surfel count (GlobalModel.cpp:667-670).
-constexpr int CC_THREADS = 256, CC_ITEMS = 4, CC_TILE = CC_THREADS * CC_ITEMS;
+// 512-surfel tiles: two 24 KB stages per CTA, four CTAs (1024 threads) per SM -- the window test of in-view surfels is a chain of
+// L2 gathers that only thread-level parallelism hides
+constexpr int CC_THREADS = 256, CC_ITEMS = 2, CC_TILE = CC_THREADS * CC_ITEMS;
 struct CcStage {
   float4 pos[CC_TILE], col[CC_TILE], nr[CC_TILE];
 };
@@ -763,6 +798,7 @@ struct CcShared {
   int next_tile, prefix, aggregate;
 };
 
+template <bool DEFORM>
 __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const MapPose* __restrict__ mp, float4* pos_conf, float4* color_time,
                                                               float4* norm_rad, int* count, const float4* __restrict__ new_pos,
                                                               const float4* __restrict__ new_col, const float4* __restrict__ new_nr,
@@ -840,7 +876,7 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
       if (idx < n_in) {
         float4 col = st.col[idx];
         keep[k] = clean_test(a, mp, st.pos[idx], col, st.nr[idx]);
-        if (keep[k] && a.n_nodes > 0 && col.z != (float)a.time) {
+        if (DEFORM && keep[k] && a.n_nodes > 0 && col.z != (float)a.time) {
           // (col.w was refreshed by the test for new surfels: the shader works on the updated vColor as well)
           float4 pos = st.pos[idx], nr = st.nr[idx];
           deform_surfel(a, mp, pos, col, nr);
@@ -855,16 +891,16 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
     }
     __syncthreads();
     if (wid == 0) {
-      // exclusive scan of the CC_ITEMS x 8 warp counts (32 values, one per lane), then the decoupled look-back
-      static_assert(CC_ITEMS * (CC_THREADS / 32) == 32, "one warp scans the slab x warp counts");
-      const int c = S.warp_cnt[lane];
+      // exclusive scan of the CC_ITEMS x 8 warp counts (one per lane), then the decoupled look-back
+      static_assert(CC_ITEMS * (CC_THREADS / 32) <= 32, "one warp scans the slab x warp counts");
+      const int c = (lane < CC_ITEMS * (CC_THREADS / 32)) ? S.warp_cnt[lane] : 0;
       int incl = c;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, off);
         if (lane >= off) incl += t;
       }
-      S.warp_excl[lane] = incl - c;
+      if (lane < CC_ITEMS * (CC_THREADS / 32)) S.warp_excl[lane] = incl - c;
       const int aggregate = __shfl_sync(0xffffffffu, incl, 31);
       volatile unsigned long long* vstate = state;
       int prefix = 0;
@@ -898,7 +934,7 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
     __syncthreads();
     const int prefix = S.prefix;
     // scatter: kept surfels go to prefix + rank. Old surfels that stay where they are are not written.
-    if (!(prefix == g0 && S.aggregate == n_in && g0 + n_in <= n_old) || a.n_nodes > 0) {
+    if (!(prefix == g0 && S.aggregate == n_in && g0 + n_in <= n_old) || (DEFORM && a.n_nodes > 0)) {
 #pragma unroll
       for (int k = 0; k < CC_ITEMS; ++k) {
         if (!keep[k]) continue;
@@ -1248,7 +1284,8 @@ int alloc_map(EfContext* ctx) {
   CU(ctx_alloc(ctx, &m.pos_conf, cap));
   CU(ctx_alloc(ctx, &m.color_time, cap));
   CU(ctx_alloc(ctx, &m.norm_rad, cap));
-  CU(cudaFuncSetAttribute(k_clean_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CcShared)));
+  CU(cudaFuncSetAttribute(k_clean_compact<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CcShared)));
+  CU(cudaFuncSetAttribute(k_clean_compact<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CcShared)));
   CU(ctx_alloc(ctx, &m.count, 4));
   CU(ctx_alloc(ctx, &m.new_pos, n));
   CU(ctx_alloc(ctx, &m.new_col, n));
@@ -1423,15 +1460,17 @@ int map_clean_async(EfContext* ctx, int time, float conf_threshold, int time_del
     CU(cudaMemsetAsync(m.scan_tile_state, 0, B.scan_state_bytes, ctx->stream));
     B.scan_epoch = 1;
   }
-  // grid from the surfel count the host last saw (any value is correct: the kernel reads the device-resident counts and its
-  // CTAs draw tiles until none are left); two 97 KB CTAs fit per SM
-  const size_t guess = (size_t)(ctx->host_count > 0 ? ctx->host_count : 0) + (size_t)m.rows * m.cols / 4;
-  size_t nb = (guess + CC_TILE - 1) / CC_TILE;
+  // one resident wave (four 49 KB CTAs per SM); CTAs draw tiles until none are left, so the grid never depends on a surfel
+  // count the host would have to read back
+  size_t nb = (size_t)ctx->num_sms * 4;
   if (nb > tiles) nb = tiles;
-  if (nb > (size_t)ctx->num_sms * 2) nb = (size_t)ctx->num_sms * 2;
   if (nb < 1) nb = 1;
-  EF_LAUNCH(ctx, k_clean_compact, (int)nb, CC_THREADS, sizeof(CcShared), a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos, m.new_col,
-            m.new_nr, m.new_count, m.capacity, (unsigned long long*)m.scan_tile_state, m.scan_counter, B.totals + 3, B.scan_epoch);
+  if (n_nodes > 0)
+    EF_LAUNCH(ctx, k_clean_compact<true>, (int)nb, CC_THREADS, sizeof(CcShared), a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos,
+              m.new_col, m.new_nr, m.new_count, m.capacity, (unsigned long long*)m.scan_tile_state, m.scan_counter, B.totals + 3, B.scan_epoch);
+  else
+    EF_LAUNCH(ctx, k_clean_compact<false>, (int)nb, CC_THREADS, sizeof(CcShared), a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos,
+              m.new_col, m.new_nr, m.new_count, m.capacity, (unsigned long long*)m.scan_tile_state, m.scan_counter, B.totals + 3, B.scan_epoch);
   LAST();
   return 0;
 }
