@@ -329,9 +329,10 @@ __global__ void k_index_scatter(const float4* __restrict__ pos_conf, const float
   const float fcols = (float)cols, frows = (float)rows;
   for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
     const float4 pc = pos_conf[id];
+    const float last_time = color_time[id].w;  // fetched with the position: one memory round trip per surfel, not two
     const f3 h = xform(mp->t_inv, mk3(pc.x, pc.y, pc.z));
     if (h.z > max_depth || h.z < 0) continue;
-    if ((float)time - color_time[id].w > (float)time_delta) continue;
+    if ((float)time - last_time > (float)time_delta) continue;
     const float xn = ((((c.fx * h.x) / h.z) + c.cx) - (fcols * 0.5f)) / (fcols * 0.5f);
     const float yn = ((((c.fy * h.y) / h.z) + c.cy) - (frows * 0.5f)) / (frows * 0.5f);
     const float zn = h.z / max_depth;

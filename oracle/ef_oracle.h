@@ -8,9 +8,11 @@
  * PARITY PIN STATUS: the reference ships no tests, golden vectors or fixtures.
  *  - tracking half: pinned against the reference's own CUDA kernels compiled unmodified
  *    from /root/reference into oracle/_ref/ (run on the GPU box; tests/test_ref_pin.py).
- *  - mapping half (GLSL): the reference cannot be built or run here (no GL) —
- *    "parity unpinned": this restatement follows the shader sources line by line and encodes
- *    GL rasterisation rules from the spec.
+ *  - mapping half (GLSL): pinned against the reference's own shader files, executed unmodified
+ *    on Mesa 18 llvmpipe (the software libGL bundled with Nsight Compute in this image) by
+ *    oracle/gl/ref_gl_harness.cpp; the outputs are committed as tests/golden/ref_mapping_160x120.npz
+ *    (generator tests/golden/make_gl_golden.py) and tests/test_gl_golden.py compares every pass.
+ *    The reference's application (Pangolin window, NVIDIA GL) itself cannot be built here.
  *
  * Conventions: all images row-major, no pitch. SoA vertex/normal maps are 3 planes stacked
  * vertically ((3*rows) x cols) exactly as the reference's DeviceArray2D<float> maps.

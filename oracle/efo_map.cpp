@@ -1,19 +1,22 @@
 // TEST INFRASTRUCTURE ONLY — CPU oracle, mapping half + depth preprocess.
 // Restates the reference's GLSL passes (Core/Shaders/*.{vert,geom,frag,glsl}) with the host sequencing of
 // Core/GlobalModel.cpp, Core/IndexMap.cpp, Core/Shaders/{FillIn,Resize,FeedbackBuffer,ComputePack}.cpp.
-// PARITY UNPINNED: the GL path cannot be built or run in this environment (no GL). GL semantics encoded here
-// (SURVEY.md App. B):
+// PARITY PINNED against the reference's own shader files executed on Mesa 18 llvmpipe (oracle/gl/ref_gl_harness.cpp ->
+// tests/golden/ref_mapping_160x120.npz, compared pass by pass in tests/test_gl_golden.py). GL semantics encoded here
+// (the fixed-point snapping was learnt from that comparison):
 //   * nearest sampling + clamp-to-edge: texel = clamp(floor(coord * size), 0, size-1) in fp32
 //   * full-screen pass: fragment (i,j) <-> texel (i,j)
-//   * 1-px points: pixel = floor(window xy); clipped when the centre leaves the clip volume
-//   * point sprites: size clamped to [1, 2047]; covered pixels are those whose centre c satisfies
-//     xw - s/2 <= c < xw + s/2
+//   * window coordinates are snapped to 1/256 px (GL_SUBPIXEL_BITS = 8) before rasterisation
+//   * 1-px points: the pixel whose centre lies in the half-open unit square around the snapped position (an integer window
+//     coordinate x belongs to pixel x - 1); clipped when the centre leaves the clip volume
+//   * point sprites: size clamped to [1, 2047] (NVIDIA; Mesa's limit is 255, not reached by the fixtures); covered pixels are
+//     those whose centre lies in the half-open square of the snapped size around the snapped centre
 //   * depth: window z quantised to 24 bits, round(z * (2^24-1)); GL_LESS; equal depth -> earlier primitive wins
 //   * transform feedback = order-preserving compaction in draw order
 //   * all shader arithmetic is IEEE fp32, no contraction (real GPUs use approximate rcp/rsqrt/exp — ulp-level)
 //   * mat4*vec4 / mat3*vec3 accumulate left to right: ((m0*x + m1*y) + m2*z) + m3*w
-//   * poses reach the shaders as float(double matrix) (the reference casts the Sophus quaternion to float first,
-//     GlobalModel.cpp:405 — a ~1e-7 deviation that cannot be pinned without the GL build)
+//   * poses reach the shaders as float(double matrix) (the reference builds the matrix from the Sophus quaternion first,
+//     GlobalModel.cpp:405 — a ~1e-16 relative difference before the float cast)
 #include "ef_oracle.h"
 #include "efo_common.h"
 #include "efo_linalg.h"

@@ -737,6 +737,34 @@ void efg_fill_image(const uint8_t* existing4, const uint8_t* rgb, int passthroug
   del({te, tr});
 }
 
+// ---- Resize::image / vertex / time (Resize.cpp:50-159): empty.vert + quad.geom + resize.frag into a (W/factor) x (H/factor)
+// target. which: 0 = RGBA8 image (read back as RGB, 3 bytes per texel), 1 = RGBA32F, 2 = R16UI through the float sampler
+// (formally undefined, see the note in DESIGN.md; reported as read back) ----
+static GLuint g_pResize = 0;
+void efg_resize(const void* src, int which, int factor, void* out) {
+  if (!g_pResize) g_pResize = program("empty.vert", "resize.frag", "quad.geom", false);
+  const int dw = G.W / factor, dh = G.H / factor;
+  GLuint ts = which == 0 ? tex_rgba8((const uint8_t*)src) : which == 1 ? tex_f4((const float*)src) : tex_u16((const uint16_t*)src);
+  GLuint dst = which == 0 ? tex(dw, dh, GL_RGBA, GL_RGB, GL_UNSIGNED_BYTE, nullptr)
+                          : which == 1 ? tex(dw, dh, GL_RGBA32F, GL_RGBA, GL_FLOAT, nullptr) : tex(dw, dh, GL_R16UI, GL_RED_INTEGER, GL_UNSIGNED_SHORT, nullptr);
+  Fbo f = make_fbo(dw, dh, {dst});
+  bind_clear(f);
+  glUseProgram(g_pResize);
+  u1i(g_pResize, "eSampler", 0);
+  glActiveTexture(GL_TEXTURE0);
+  glBindTexture(GL_TEXTURE_2D, ts);
+  glDrawArrays(GL_POINTS, 0, 1);
+  glFinish();
+  if (which == 0)
+    glReadPixels(0, 0, dw, dh, GL_RGB, GL_UNSIGNED_BYTE, out);
+  else if (which == 1)
+    glReadPixels(0, 0, dw, dh, GL_RGBA, GL_FLOAT, out);
+  else
+    glReadPixels(0, 0, dw, dh, GL_RED_INTEGER, GL_UNSIGNED_SHORT, out);
+  free_fbo(f);
+  del({ts});
+}
+
 unsigned efg_gl_error() { return glGetError(); }
 
 }  // extern "C"
