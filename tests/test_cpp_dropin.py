@@ -135,7 +135,10 @@ def test_ferns_keyframes_and_relocalisation_candidate(tmp_path, K):
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", f"-I{ROOT}/include/efusion", f"-I{ROOT}/include",
                            os.path.join(ROOT, "tests", "cpp", "ferns_check.cpp"), "-o", exe, f"-L{ROOT}/elasticfusion_b200", "-lefusion",
                            f"-Wl,-rpath,{ROOT}/elasticfusion_b200", f"-L{CUDA_LIB}", "-lcudart", "-lz"])
-    frames = list(synth.sequence(31, K, seed=17, noise=True, speed=3.0))
+    # out and back: the last processed frame looks at the scene from (almost) where frame 0, the first key frame, did
+    out_leg = list(synth.sequence(16, K, seed=17, noise=True, speed=3.0))
+    frames = out_leg + out_leg[-2::-1]
+    assert len(frames) == 31
     klg = str(tmp_path / "ferns.klg")
     synth.write_klg(klg, [(f[0], f[1]) for f in frames])
     out = subprocess.check_output([exe, klg, str(K.width), str(K.height), str(K.fx), str(K.fy), str(K.cx), str(K.cy), "400"], text=True)

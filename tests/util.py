@@ -55,3 +55,24 @@ def run_oracle(frames, K, n, **kw):
     for i in range(n):
         f.process_frame(frames[i][0], frames[i][1], i * 33333)
     return f
+
+
+def oracle_sensitivity(frames, K, **cfg):
+    """How far the ORACLE moves from itself when one depth pixel of frame 1 is 1 mm deeper: the scale below which a
+    trajectory difference says nothing about an implementation (tracking amplifies any rounding difference the same way).
+    Returns (oracle poses of the unperturbed run, ATE RMSE between the two runs, largest per-frame |dT| element)."""
+    from elasticfusion_b200 import synth
+
+    runs = []
+    for perturb in (False, True):
+        f = run_oracle(frames, K, 0, **cfg)
+        est = []
+        for i, fr in enumerate(frames):
+            d = fr[1]
+            if perturb and i == 1:
+                d = d.copy()
+                d[K.height // 2, K.width // 2] += 1
+            f.process_frame(fr[0], d, i * 33333)
+            est.append(f.pose.copy())
+        runs.append(np.array(est))
+    return runs[0], float(synth.ate_rmse(runs[0], runs[1])), float(np.abs(runs[0] - runs[1]).max())
