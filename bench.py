@@ -452,8 +452,8 @@ def map_stage_rooflines(ctx, torch, stream, flush, K):
     ctx.map_predict_indices(None, tick, MAXD, BIG)
     ctx.map_clean(None, tick, 10.0, BIG, MAXD)  # settle: whatever this view culls is gone after one pass
     t = timed(lambda: ctx.map_clean(None, tick, 10.0, BIG, MAXD))
-    b = 48 * ctx.map_count()
-    out["clean_static"] = {"kernels": "k_update_pose + k_clean_compact (nothing moves: read only)", "algorithmic_bytes": b, "duration_us": t, "achieved": b / t / 1e3,
+    b = 32 * ctx.map_count()  # (+16 B normal/radius for the surfels in view: not counted)
+    out["clean_static"] = {"kernels": "k_update_pose + k_clean_flags + k_clean_move (nothing moves: position + colour/time read, one bit written)", "algorithmic_bytes": b, "duration_us": t, "achieved": b / t / 1e3,
                            "unit": "GB/s"}
     # whole-map shift: cull surfel 1 (lastTime = -1 -> `w == -1` rule, copy_unstable.vert:119), every later surfel moves down by one
     if n > 4096:
@@ -468,8 +468,8 @@ def map_stage_rooflines(ctx, torch, stream, flush, K):
             ts.append(timed(lambda: ctx.map_clean(None, tick, 10.0, BIG, MAXD), reps=1))
             assert ctx.map_count() == cnt - 1
         t = statistics.median(ts)
-        b = 96 * ctx.map_count()
-        out["clean_shift"] = {"kernels": "k_update_pose + k_clean_compact (every surfel moves down by one)", "algorithmic_bytes": b, "duration_us": t,
+        b = 128 * ctx.map_count()
+        out["clean_shift"] = {"kernels": "k_update_pose + k_clean_flags + k_clean_move (every surfel moves down by one: 32 B test read + 48 B read + 48 B written)", "algorithmic_bytes": b, "duration_us": t,
                               "achieved": b / t / 1e3, "unit": "GB/s"}
     return out
 

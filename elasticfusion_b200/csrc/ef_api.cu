@@ -22,6 +22,7 @@ int odom_init_icp_model(EfContext* ctx, int which, const float* vtx4, const floa
                         const float* nrmB = nullptr, const int* flag = nullptr, bool with_global = true);
 int odom_populate(EfContext* ctx, int which, const uint8_t* rgba, float** destDepths, uint8_t** destImages, bool with_depth,
                   const uint8_t* rgbaB = nullptr, const int* flag = nullptr, bool forceB = false, bool with_image = true);
+int odom_cluster_size(int want);
 int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom, bool so3);
 int odom_finish_async(EfContext* ctx, int which, float weightMultiplier, bool have_track);
 int odom_set_pose_async(EfContext* ctx, int which, const double* T_dev);
@@ -196,6 +197,12 @@ static int alloc_odom(EfContext* ctx, OdomDev& od) {
   CU(A->alloc(&od.partials, (size_t)MAX_RED_BLOCKS * PARTIAL_STRIDE));
   CU(A->alloc(&od.partials_rgb, (size_t)MAX_RGB_BLOCKS * 32));
   CU(A->alloc(&od.partials2, (size_t)MAX_RGB_BLOCKS * 32));
+  // (the reductions read whole 32-float rows of these; the kernels write the 29 / 11 terms of a system, so the padding lanes
+  // are defined once here)
+  CU(cudaMemsetAsync(od.so3_partials, 0, (size_t)MAX_RGB_BLOCKS * PARTIAL_STRIDE * sizeof(float), ctx->stream));
+  CU(cudaMemsetAsync(od.partials, 0, (size_t)MAX_RED_BLOCKS * PARTIAL_STRIDE * sizeof(float), ctx->stream));
+  CU(cudaMemsetAsync(od.partials_rgb, 0, (size_t)MAX_RGB_BLOCKS * 32 * sizeof(float), ctx->stream));
+  CU(cudaMemsetAsync(od.partials2, 0, (size_t)MAX_RGB_BLOCKS * 32 * sizeof(double), ctx->stream));
   {
     size_t flat = 0;
     for (int i = 0; i < NUM_PYRS; ++i) {
@@ -303,6 +310,14 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
     if (ctx->it2_max_blocks > MAX_RGB_BLOCKS) ctx->it2_max_blocks = MAX_RGB_BLOCKS;
     ctx->plain_next = false;
     ctx->maps_dirty[0] = ctx->maps_dirty[1] = true;
+    // Gauss-Newton iterations of the coarse pyramid levels inside one thread-block cluster (k_gn_cluster): EF_GN_CLUSTER = wanted
+    // cluster size (16 default, 8, or 0 = off), EF_GN_CLUSTER_LEVELS = how many levels from the top of the pyramid (default 2)
+    e = getenv("EF_GN_CLUSTER");
+    ctx->gn_cluster = odom_cluster_size(e ? atoi(e) : 16);
+    e = getenv("EF_GN_CLUSTER_LEVELS");
+    ctx->gn_cluster_levels = e ? atoi(e) : 2;
+    if (ctx->gn_cluster_levels < 0) ctx->gn_cluster_levels = 0;
+    if (ctx->gn_cluster_levels > NUM_PYRS) ctx->gn_cluster_levels = NUM_PYRS;
     e = getenv("EF_STAGE_TIMING");
     ctx->stage_timing = (e && e[0] == '1');
     ctx->stage_n = 0;
@@ -381,6 +396,7 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
     TA(la.so3s, 1);
     TA(la.so3_partials, (size_t)MAX_RGB_BLOCKS * PARTIAL_STRIDE);
     TA(la.so3_counter, 4);
+    if (!rc) cudaMemsetAsync(la.so3_partials, 0, (size_t)MAX_RGB_BLOCKS * PARTIAL_STRIDE * sizeof(float), ctx->stream);
     if (!rc) {
       cudaError_t e = cudaStreamCreateWithFlags(&la.stream, cudaStreamNonBlocking);
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(&la.ready, cudaEventDisableTiming);

@@ -142,6 +142,8 @@ struct MapDev {
   // scan scratch
   int* scan_tile_state;   // decoupled look-back
   unsigned int* scan_counter;
+  unsigned int* clean_ctl;   // [0] tile dispenser, [1] exit tickets, [2] first tile that moves (k_clean_flags -> k_clean_move)
+  uint32_t* keep_mask;       // one warp ballot per 32 surfels: the clean test's verdicts
   uint8_t* flags;         // capacity + W*H
   // first-frame feedback buffers
   float4 *fb_raw[3], *fb_filt[3];
@@ -209,6 +211,8 @@ struct EfContext {
   bool pdl;  // programmatic dependent launch on every kernel (default on; EF_NO_PDL=1 disables)
   bool it1_prefetch;   // k_iter1 loads its first round of live-map pixels before griddepcontrol.wait (EF_IT1_PREFETCH=0 disables)
   int it2_max_blocks;  // cap on k_iter2's grid (EF_IT2_MAXBLOCKS; default MAX_RGB_BLOCKS)
+  int gn_cluster;         // CTAs of the cluster that runs the coarse-level Gauss-Newton iterations (0: two-kernel path everywhere)
+  int gn_cluster_levels;  // pyramid levels, from the coarsest, whose iterations run in that cluster
   bool plain_next;     // the next ef_launch omits the programmatic-serialisation attribute (EF_PLAIN_NEXT)
   bool maps_dirty[2];  // a kernel that writes tracker w's pyramids may still be in flight ahead of the next stage launch
 

@@ -696,7 +696,7 @@ __device__ __noinline__ void deform_surfel(const CleanArgs& a, const MapPose* mp
   }
 }
 
-__device__ __forceinline__ bool clean_test(const CleanArgs& a, const MapPose* mp, const float4& pos, float4& col, const float4& nr) {
+__device__ __forceinline__ bool clean_test(const CleanArgs& a, const MapPose* mp, const float4& pos, float4& col, const float4* __restrict__ nr_ptr) {
   const float fcols = (float)a.cols, frows = (float)a.rows;
   int test = 1;
   const f3 localPos = xform(mp->t_inv, mk3(pos.x, pos.y, pos.z));
@@ -707,6 +707,7 @@ __device__ __forceinline__ bool clean_test(const CleanArgs& a, const MapPose* mp
   const float indexYStep = (1.0f / (frows * scale)) * 0.5f;
   int count = 0, zCount = 0;
   if ((float)a.time - col.w < (float)a.time_delta && localPos.z > 0 && x > 0 && y > 0 && x < fcols && y < frows) {
+    const float4 nr = *nr_ptr;  // normal + radius: only the surfels in view need them (32 B instead of 48 for the rest)
     const f3 localNorm = normalized(rot(mp->t_inv, mk3(nr.x, nr.y, nr.z)));
     // duplicate samples COUNT here (copy_unstable.vert:94,106): each distinct texel is read once and
     // weighted by the number of float-loop samples that land on it. Index texels first, attributes of the occupied ones after.
@@ -774,19 +775,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
-// clean in ONE launch: copy_unstable.vert's keep/cull test, the order-preserving compaction (transform feedback) and the
-// append of this frame's new surfels, as a single-pass decoupled look-back stream compaction over tiles of CC_TILE surfels.
-//  * persistent CTAs draw tiles from a dispenser; each tile (3 x 16 KB of float4, or its old-map / new-surfel parts) is
-//    staged in shared memory by 1-D bulk copies (cp.async.bulk + mbarrier complete_tx), double buffered: the next tile's
-//    copies are in flight while the current one is tested;
-//  * IN PLACE: tile t publishes its aggregate only after its input is resident in shared memory, and a tile learns its
-//    output offset only from the published states of all its predecessors -- so when it writes [prefix, prefix + kept), which
-//    lies inside the input ranges of tiles <= t, every one of those has already been read. Surfels that do not move (nothing
-//    culled before them: the common case for the old, stable bulk of a map sorted by init time) are not written at all:
-//    48 B read per surfel and no write, against 48 + 48 for the reference's VBO-to-VBO pass (GlobalModel.cpp:527-671);
+// clean in TWO launches (copy_unstable.vert + transform feedback, GlobalModel.cpp:527-671):
+//  k_clean_flags  the keep / cull test of every surfel (old map + this frame's new ones), embarrassingly parallel at full
+//                 occupancy: 32 B read per surfel (48 for those in view) and ONE BIT written (a warp ballot per 32 surfels). It
+//                 also finds the first tile that has to move: the first one that lost a surfel or holds a new one.
+//  k_clean_move   the order-preserving compaction + append, IN PLACE, over the tiles from that first mover on only -- the old,
+//                 stable bulk of a map sorted by init time is neither read nor written again. Single-pass decoupled look-back
+//                 over tiles of CC_TILE surfels:
+//  * persistent CTAs draw tiles from a dispenser; each tile (3 x 8 KB of float4, or its old-map / new-surfel parts) is
+//    staged in shared memory by 1-D bulk copies (cp.async.bulk + mbarrier complete_tx), double buffered;
+//  * tile t publishes its aggregate only after its input is resident in shared memory, and a tile learns its output offset
+//    only from the published states of all its predecessors -- so when it writes [prefix, prefix + kept), which lies inside
+//    the input ranges of tiles <= t, every one of those has already been read. Surfels that do not move are not written;
 //  * the last CTA to leave publishes the new count and clears the new-surfel count (GlobalModel.cpp:667-670).
-// 512-surfel tiles: two 24 KB stages per CTA, four CTAs (1024 threads) per SM -- the window test of in-view surfels is a chain of
-// L2 gathers that only thread-level parallelism hides
+// (One fused launch was measured first: in-view tiles take ~10x longer than the rest and the look-back makes every tile wait
+// for the slowest tile in flight, 267 us at 5 M surfels; split, the test runs unordered and the ordered part touches little.)
 constexpr int CC_THREADS = 256, CC_ITEMS = 2, CC_TILE = CC_THREADS * CC_ITEMS;
 struct CcStage {
   float4 pos[CC_TILE], col[CC_TILE], nr[CC_TILE];
@@ -799,12 +802,50 @@ struct CcShared {
   int next_tile, prefix, aggregate;
 };
 
+constexpr int CC_WORDS = CC_ITEMS * (CC_THREADS / 32);  // keep-mask words per tile, in (item slab k, warp) order
+
+// ctl[0] tile dispenser, ctl[1] exit tickets, ctl[2] first tile that moves (0xffffffff: none)
+__global__ void __launch_bounds__(CC_THREADS, 4) k_clean_flags(CleanArgs a, const MapPose* __restrict__ mp, const float4* __restrict__ pos_conf,
+                                                               const float4* __restrict__ color_time, const float4* __restrict__ norm_rad,
+                                                               const int* __restrict__ count, const float4* __restrict__ new_pos,
+                                                               const float4* __restrict__ new_col, const float4* __restrict__ new_nr,
+                                                               const int* __restrict__ new_count, uint32_t* __restrict__ keep_mask,
+                                                               unsigned int* ctl) {
+  pdl_enter();
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n_old = *count, total = n_old + *new_count;
+  const int num_tiles = (total + CC_TILE - 1) / CC_TILE;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const int g0 = t * CC_TILE;
+    const int n_in = min(CC_TILE, total - g0);
+    // a tile moves when it holds new surfels (they have to be appended), lost one of its own, or a graph deforms the map
+    bool moves = (g0 + n_in > n_old) || a.n_nodes > 0;
+    // item index k * CC_THREADS + tid: coalesced, and (k, warp, lane) = map order for the ballots
+#pragma unroll
+    for (int k = 0; k < CC_ITEMS; ++k) {
+      const int idx = k * CC_THREADS + tid, g = g0 + idx;
+      bool keep = false;
+      if (idx < n_in) {
+        const bool is_old = g < n_old;
+        const float4 pos = is_old ? pos_conf[g] : new_pos[g - n_old];
+        float4 col = is_old ? color_time[g] : new_col[g - n_old];
+        keep = clean_test(a, mp, pos, col, is_old ? norm_rad + g : new_nr + (g - n_old));
+      }
+      const unsigned int ballot = __ballot_sync(0xffffffffu, keep);
+      const unsigned int valid = __ballot_sync(0xffffffffu, idx < n_in);
+      if (lane == 0) keep_mask[(size_t)t * CC_WORDS + k * (CC_THREADS / 32) + wid] = ballot;
+      moves = moves || ballot != valid;
+    }
+    if (moves && lane == 0) atomicMin(ctl + 2, (unsigned int)t);
+  }
+}
+
 template <bool DEFORM>
-__global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const MapPose* __restrict__ mp, float4* pos_conf, float4* color_time,
-                                                              float4* norm_rad, int* count, const float4* __restrict__ new_pos,
-                                                              const float4* __restrict__ new_col, const float4* __restrict__ new_nr,
-                                                              int* new_count, int capacity, unsigned long long* state, unsigned int* counter,
-                                                              int* total_out, unsigned int epoch) {
+__global__ void __launch_bounds__(CC_THREADS) k_clean_move(CleanArgs a, const MapPose* __restrict__ mp, float4* pos_conf, float4* color_time,
+                                                           float4* norm_rad, int* count, const float4* __restrict__ new_pos,
+                                                           const float4* __restrict__ new_col, const float4* __restrict__ new_nr,
+                                                           int* new_count, int capacity, const uint32_t* __restrict__ keep_mask,
+                                                           unsigned long long* state, unsigned int* ctl, int* total_out, unsigned int epoch) {
   pdl_enter();
   extern __shared__ __align__(128) unsigned char cc_smem_raw[];
   CcShared& S = *reinterpret_cast<CcShared*>(cc_smem_raw);
@@ -812,6 +853,10 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
   const int n_old = *count, total = n_old + *new_count;
   const int num_tiles = (total + CC_TILE - 1) / CC_TILE;
   const unsigned long long tag = (unsigned long long)epoch << 34;
+  unsigned int* counter = ctl;
+  // tiles below `first` are full and stay where they are: the compaction starts there with prefix first * CC_TILE
+  const unsigned int first_u = *(volatile unsigned int*)(ctl + 2);
+  const int first = first_u > (unsigned int)num_tiles ? num_tiles : (int)first_u;
   if (tid == 0) {
     mbar_init(&S.bar[0], 1);
     mbar_init(&S.bar[1], 1);
@@ -843,7 +888,7 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
 
   int cur = 0;
   if (tid == 0) {
-    cur = (int)atomicAdd(counter, 1u);
+    cur = first + (int)atomicAdd(counter, 1u);
     S.next_tile = cur;
     if (cur < num_tiles) issue(cur, 0);
   }
@@ -854,7 +899,7 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
   while (cur < num_tiles) {
     __syncthreads();  // S.next_tile has been read by everyone; the other stage's readers (previous iteration) are done
     if (tid == 0) {
-      const int nx = (int)atomicAdd(counter, 1u);
+      const int nx = first + (int)atomicAdd(counter, 1u);
       S.next_tile = nx;
       if (nx < num_tiles) issue(nx, stage ^ 1);
     }
@@ -865,20 +910,20 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
     const int g0 = cur * CC_TILE;
     const int n_in = min(CC_TILE, total - g0);
 
-    // keep / cull test (copy_unstable.vert:60-130) for this thread's CC_ITEMS surfels; item index k * CC_THREADS + tid keeps
-    // the shared-memory reads conflict-free and the order (k, warp, lane) = map order
+    // the keep masks k_clean_flags left for this tile; item index k * CC_THREADS + tid keeps the shared-memory reads
+    // conflict-free and the order (k, warp, lane) = map order
     unsigned int ballots[CC_ITEMS];
     bool keep[CC_ITEMS];
     unsigned int deformed = 0;  // bit k: item k was moved by the deformation graph (always rewritten)
 #pragma unroll
     for (int k = 0; k < CC_ITEMS; ++k) {
       const int idx = k * CC_THREADS + tid;
-      keep[k] = false;
-      if (idx < n_in) {
+      ballots[k] = keep_mask[(size_t)cur * CC_WORDS + k * (CC_THREADS / 32) + wid];
+      keep[k] = (ballots[k] >> lane) & 1u;
+      if (DEFORM && keep[k] && a.n_nodes > 0) {
         float4 col = st.col[idx];
-        keep[k] = clean_test(a, mp, st.pos[idx], col, st.nr[idx]);
-        if (DEFORM && keep[k] && a.n_nodes > 0 && col.z != (float)a.time) {
-          // (col.w was refreshed by the test for new surfels: the shader works on the updated vColor as well)
+        if (col.w == -2) col.w = (float)a.time;  // copy_unstable.vert:114-117 -- the shader deforms with the refreshed vColor
+        if (col.z != (float)a.time) {
           float4 pos = st.pos[idx], nr = st.nr[idx];
           deform_surfel(a, mp, pos, col, nr);
           st.pos[idx] = pos;
@@ -887,7 +932,6 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
           deformed |= 1u << k;
         }
       }
-      ballots[k] = __ballot_sync(0xffffffffu, keep[k]);
       if (lane == 0) S.warp_cnt[k * (CC_THREADS / 32) + wid] = __popc(ballots[k]);
     }
     __syncthreads();
@@ -904,15 +948,16 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
       if (lane < CC_ITEMS * (CC_THREADS / 32)) S.warp_excl[lane] = incl - c;
       const int aggregate = __shfl_sync(0xffffffffu, incl, 31);
       volatile unsigned long long* vstate = state;
-      int prefix = 0;
-      if (cur == 0) {
-        if (lane == 0) vstate[0] = tag | (2ull << 32) | (unsigned int)aggregate;
+      int prefix = first * CC_TILE;
+      if (cur == first) {
+        if (lane == 0) vstate[cur] = tag | (2ull << 32) | (unsigned int)(prefix + aggregate);
       } else {
+        prefix = 0;
         if (lane == 0) vstate[cur] = tag | (1ull << 32) | (unsigned int)aggregate;
         int look = cur - 1;
         while (true) {
           const int idx = look - lane;
-          const unsigned long long w = (idx >= 0) ? vstate[idx] : (tag | (2ull << 32));
+          const unsigned long long w = (idx >= first) ? vstate[idx] : (tag | (2ull << 32));
           const unsigned int stt = ((w >> 34) == (unsigned long long)epoch) ? ((unsigned int)(w >> 32) & 3u) : 0u;
           if (__any_sync(0xffffffffu, stt == 0)) continue;
           const unsigned int m2 = __ballot_sync(0xffffffffu, stt == 2);
@@ -944,7 +989,7 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
         const int o = prefix + S.warp_excl[k * (CC_THREADS / 32) + wid] + __popc(ballots[k] & ((1u << lane) - 1u));
         if (o >= capacity || (o == g && g < n_old && !(deformed >> k & 1u))) continue;
         float4 col = st.col[idx];
-        if (g >= n_old && col.w == -2) col.w = (float)a.time;  // copy_unstable.vert:114-117
+        if (col.w == -2) col.w = (float)a.time;  // copy_unstable.vert:114-117 (only new surfels carry -2)
         pos_conf[o] = st.pos[idx];
         color_time[o] = col;
         norm_rad[o] = st.nr[idx];
@@ -960,8 +1005,11 @@ __global__ void __launch_bounds__(CC_THREADS) k_clean_compact(CleanArgs a, const
       __threadfence();
       counter[0] = 0u;
       counter[1] = 0u;
-      const int kept = (num_tiles > 0) ? *(volatile int*)total_out : 0;
-      *count = kept < capacity ? kept : capacity;
+      counter[2] = 0xffffffffu;
+      if (first < num_tiles) {  // (otherwise nothing was culled and nothing is new: the count stands)
+        const int kept = *(volatile int*)total_out;
+        *count = kept < capacity ? kept : capacity;
+      }
       *new_count = 0;
     }
   }
@@ -1285,8 +1333,8 @@ int alloc_map(EfContext* ctx) {
   CU(ctx_alloc(ctx, &m.pos_conf, cap));
   CU(ctx_alloc(ctx, &m.color_time, cap));
   CU(ctx_alloc(ctx, &m.norm_rad, cap));
-  CU(cudaFuncSetAttribute(k_clean_compact<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CcShared)));
-  CU(cudaFuncSetAttribute(k_clean_compact<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CcShared)));
+  CU(cudaFuncSetAttribute(k_clean_move<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CcShared)));
+  CU(cudaFuncSetAttribute(k_clean_move<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CcShared)));
   CU(ctx_alloc(ctx, &m.count, 4));
   CU(ctx_alloc(ctx, &m.new_pos, n));
   CU(ctx_alloc(ctx, &m.new_col, n));
@@ -1303,6 +1351,8 @@ int alloc_map(EfContext* ctx) {
   CU(ctx_alloc(ctx, &st, tiles));
   m.scan_tile_state = reinterpret_cast<int*>(st);
   CU(ctx_alloc(ctx, &m.scan_counter, 4));
+  CU(ctx_alloc(ctx, &m.clean_ctl, 4));
+  CU(ctx_alloc(ctx, &m.keep_mask, ((max_items + CC_TILE - 1) / CC_TILE) * CC_WORDS));
   CU(ctx_alloc(ctx, &m.flags, 2 * n));
   CU(ctx_alloc(ctx, &B->offsets, 2 * n));
   CU(ctx_alloc(ctx, &B->totals, 4));
@@ -1320,6 +1370,8 @@ int alloc_map(EfContext* ctx) {
   B->scan_state_bytes = tiles * 8;
   CU(cudaMemsetAsync(m.scan_tile_state, 0, tiles * 8, ctx->stream));
   CU(cudaMemsetAsync(m.scan_counter, 0, 16, ctx->stream));
+  CU(cudaMemsetAsync(m.clean_ctl, 0, 8, ctx->stream));
+  CU(cudaMemsetAsync(m.clean_ctl + 2, 0xff, 8, ctx->stream));
   CU(cudaMemsetAsync(m.zbuf, 0xff, n * 8, ctx->stream));  // kept cleared by the resolve passes from here on
   CU(cudaMemsetAsync(m.count, 0, 16, ctx->stream));
   CU(cudaMemsetAsync(m.new_count, 0, 16, ctx->stream));
@@ -1454,24 +1506,28 @@ int map_clean_async(EfContext* ctx, int time, float conf_threshold, int time_del
   a.depth = ctx->tex.synth_depth;
   a.max_depth = max_depth;
   a.is_fern = is_fern ? 1 : 0;
-  // one launch: test + order-preserving in-place compaction + append of the new surfels + count publication
+  // test (parallel) -> order-preserving in-place compaction + append of the new surfels + count publication (movers only)
   const size_t max_items = (size_t)m.capacity + (size_t)m.rows * m.cols;
   const size_t tiles = (max_items + CC_TILE - 1) / CC_TILE;
   if (++B.scan_epoch >= (1u << 30)) {
     CU(cudaMemsetAsync(m.scan_tile_state, 0, B.scan_state_bytes, ctx->stream));
     B.scan_epoch = 1;
   }
-  // one resident wave (four 49 KB CTAs per SM); CTAs draw tiles until none are left, so the grid never depends on a surfel
-  // count the host would have to read back
+  // grids never depend on a surfel count the host would have to read back: the test strides over the tiles, the movers draw
+  // tiles from a dispenser (one resident wave: four 49 KB CTAs per SM)
   size_t nb = (size_t)ctx->num_sms * 4;
   if (nb > tiles) nb = tiles;
   if (nb < 1) nb = 1;
+  EF_LAUNCH(ctx, k_clean_flags, (int)nb, CC_THREADS, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos, m.new_col, m.new_nr,
+            m.new_count, m.keep_mask, m.clean_ctl);
   if (n_nodes > 0)
-    EF_LAUNCH(ctx, k_clean_compact<true>, (int)nb, CC_THREADS, sizeof(CcShared), a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos,
-              m.new_col, m.new_nr, m.new_count, m.capacity, (unsigned long long*)m.scan_tile_state, m.scan_counter, B.totals + 3, B.scan_epoch);
+    EF_LAUNCH(ctx, k_clean_move<true>, (int)nb, CC_THREADS, sizeof(CcShared), a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos,
+              m.new_col, m.new_nr, m.new_count, m.capacity, m.keep_mask, (unsigned long long*)m.scan_tile_state, m.clean_ctl, B.totals + 3,
+              B.scan_epoch);
   else
-    EF_LAUNCH(ctx, k_clean_compact<false>, (int)nb, CC_THREADS, sizeof(CcShared), a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos,
-              m.new_col, m.new_nr, m.new_count, m.capacity, (unsigned long long*)m.scan_tile_state, m.scan_counter, B.totals + 3, B.scan_epoch);
+    EF_LAUNCH(ctx, k_clean_move<false>, (int)nb, CC_THREADS, sizeof(CcShared), a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos,
+              m.new_col, m.new_nr, m.new_count, m.capacity, m.keep_mask, (unsigned long long*)m.scan_tile_state, m.clean_ctl, B.totals + 3,
+              B.scan_epoch);
   LAST();
   return 0;
 }

@@ -926,6 +926,334 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
 }
 
 
+// =============================================================================================
+// Gauss-Newton iterations inside ONE thread-block cluster
+// =============================================================================================
+// The coarse pyramid levels are latency chains, not throughput problems: 19 k / 77 k pixels per pass, yet every iteration of
+// the two-kernel path above pays two kernel boundaries, a gpu-scope ticket and an L2 round trip for the partials (~16 us per
+// iteration for ~3 us of work). Here a whole run of iterations executes in one launch of a single cluster of up to 16 CTAs:
+//  * the per-iteration hand-offs are hardware cluster barriers (barrier.cluster.arrive/wait) instead of kernel boundaries;
+//  * the correspondence statistics and the per-CTA 29-term partial systems travel through DISTRIBUTED SHARED MEMORY
+//    (remote atomics / stores into the leader CTA's shared memory), not through L2;
+//  * the statistics barrier is split: CTAs arrive after the photometric correspondence pass, run the dense geometric pass, and
+//    only then wait -- the photometric rows need sigma, the geometric rows do not;
+//  * the leader sums the <= 16 partials in rank order in double, its first warp solves (gn_update_warp, unchanged) and
+//    publishes the 25 floats the next iteration needs through its shared memory.
+// Same per-pixel arithmetic as k_iter1 / k_iter2 (icp_project, icp_accumulate, rgb_accumulate); only the grouping of the float
+// partial sums differs (<= 16 CTA partials instead of 600), which moves A and b by float rounding.
+struct GnSched {
+  int n;
+  signed char level[24], iter[24];
+};
+constexpr int GC_THREADS = 512;
+constexpr int GC_MAX_CL = 16;
+
+struct GcParams {  // what one iteration needs from the solver
+  float Mcp[9], tcp[3], krkinv[9], kt[3];
+  int break_level;
+};
+constexpr int GC_PARAM_WORDS = 25;
+struct GcShared {
+  GnScratch S;                 // leader: operands of the solve
+  float slots[GC_MAX_CL][64];  // leader: per-CTA partial systems, [0,29) geometric and [32,61) photometric
+  unsigned int stat[2];        // leader: {count, sum int(diff^2)} of the correspondence pass
+  GcParams P;                  // leader: published parameters
+  GcParams Pl;                 // every CTA: its copy for the running iteration
+  float sred_a[32 * (GC_THREADS / 32)], sred_b[32 * (GC_THREADS / 32)];
+  unsigned int s_stat[2];
+  float sigma;
+  int brk;
+};
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+  cluster_arrive();
+  cluster_wait();
+}
+__device__ __forceinline__ unsigned int cluster_rank() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned int cluster_size() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// generic address of `p` (a shared-memory object of this CTA) in the shared memory of CTA `rank` of the cluster
+template <typename T>
+__device__ __forceinline__ T* cluster_map(T* p, unsigned int rank) {
+  unsigned long long in = (unsigned long long)p, out;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(in), "r"(rank));
+  return (T*)out;
+}
+
+__global__ void __launch_bounds__(GC_THREADS, 1) k_gn_cluster(OdomDev od, GnSched sched, int s_begin, int s_end, int do_rgb, int do_icp) {
+  pdl_enter();
+  __shared__ GcShared sh;
+  GNState* gn = od.gn;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int rank = (int)cluster_rank(), C = (int)cluster_size();
+  GcShared* lead = cluster_map(&sh, 0u);
+
+  // parameters of the first iteration (k_gn_begin / k_gn_seed or the previous launch left them in the global state)
+  if (tid < 9) {
+    sh.Pl.Mcp[tid] = gn->Mcp[tid];
+    sh.Pl.krkinv[tid] = gn->krkinv[tid];
+  } else if (tid < 12) {
+    sh.Pl.tcp[tid - 9] = gn->tcp[tid - 9];
+    sh.Pl.kt[tid - 9] = gn->kt[tid - 9];
+  } else if (tid == 12) {
+    sh.Pl.break_level = gn->break_level;
+    sh.s_stat[0] = sh.s_stat[1] = 0u;
+    sh.stat[0] = sh.stat[1] = 0u;
+  }
+  if (rank == 0 && wid == 1) {
+    GnScratch& S = sh.S;
+    if (lane < 16) S.rRt[lane] = gn->resultRt[lane];
+    if (lane < 9) S.Rprev[lane] = gn->Rprev[lane];
+    if (lane < 3) S.tprev[lane] = gn->tprev[lane];
+    if (lane == 0) {
+      S.flags[0] = gn->icp;
+      S.flags[1] = gn->rgb;
+      S.w = gn->icpWeight;
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();  // every CTA's shared memory is initialised before anyone touches it remotely
+
+  for (int s = s_begin; s < s_end; ++s) {
+    const int level = sched.level[s], iter = sched.iter[s];
+    const int next_level = (s + 1 < sched.n) ? sched.level[s + 1] : -1;
+    if (sh.Pl.break_level == level) {
+      // rgbOnly `break` (RGBDOdometry.cpp:452-455): the rest of the level is skipped; the first iteration of the next level
+      // still needs its warp matrices
+      if (next_level >= 0 && next_level != level) {
+        if (rank == 0 && tid == 0) {
+          gn_prepare_warp(gn, next_level);
+          for (int k = 0; k < 9; ++k) sh.P.krkinv[k] = gn->krkinv[k];
+          for (int k = 0; k < 3; ++k) sh.P.kt[k] = gn->kt[k];
+        }
+        cluster_sync_all();
+        if (tid < 9)
+          sh.Pl.krkinv[tid] = lead->P.krkinv[tid];
+        else if (tid < 12)
+          sh.Pl.kt[tid - 9] = lead->P.kt[tid - 9];
+        __syncthreads();
+      }
+      continue;
+    }
+    const int rows = od.rows[level], cols = od.cols[level];
+    const int N = rows * cols;
+    const size_t plane = (size_t)N;
+    // work items are dealt to warps round-robin across the CTAs of the cluster
+    const int gid = (wid * C + rank) * 32 + lane, gstride = C * GC_THREADS;
+    const int base = gn->cand_base[level], ncand = do_rgb ? gn->cand_base[level + 1] - base : 0;
+    int4* terms = od.terms + base;
+
+    // ---- (a) photometric correspondences for this pose (RGBResidual::getProducts, reduce.cu:661-697)
+    if (do_rgb) {
+      unsigned int cnt = 0, sig = 0;
+      const m33 krkinv = load_m33(sh.Pl.krkinv);
+      const f3 kt = mk3(sh.Pl.kt[0], sh.Pl.kt[1], sh.Pl.kt[2]);
+      const float* __restrict__ lastDepth = od.lastDepth[level];
+      const uint8_t* __restrict__ lastImage = od.lastImage[level];
+      const int4* __restrict__ cand = od.cand + base;
+      for (int c = gid; c < ncand; c += gstride) {
+        const int4 cr = cand[c];
+        const int k = cr.x;
+        const int y = k / cols, x = k - y * cols;
+        const float d1 = __int_as_float(cr.y);
+        const float transformed_d1 = (float)(d1 * (krkinv.r[2].x * x + krkinv.r[2].y * y + krkinv.r[2].z) + kt.z);
+        const int u0 = __float2int_rn((d1 * (krkinv.r[0].x * x + krkinv.r[0].y * y + krkinv.r[0].z) + kt.x) / transformed_d1);
+        const int v0 = __float2int_rn((d1 * (krkinv.r[1].x * x + krkinv.r[1].y * y + krkinv.r[1].z) + kt.y) / transformed_d1);
+        int4 out = make_int4(-1, 0, cr.z, 0);
+        if (u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows) {
+          const float d0 = lastDepth[(size_t)v0 * cols + u0];
+          const int li = lastImage[(size_t)v0 * cols + u0];
+          if (d0 > 0 && fabsf(transformed_d1 - d0) <= od.maxDepthDeltaRGB && li != 0) {
+            const float diff = (float)cr.w - (float)li;
+            out.x = (u0 & 0xffff) | (v0 << 16);
+            out.y = __float_as_int(diff);
+            out.w = __float_as_int(d0);
+            cnt += 1;
+            sig += (unsigned int)__float2int_rz(diff * diff);
+          }
+        }
+        terms[c] = out;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+        sig += __shfl_down_sync(0xffffffffu, sig, off);
+      }
+      if (lane == 0 && (cnt | sig)) {
+        atomicAdd(&sh.s_stat[0], cnt);
+        atomicAdd(&sh.s_stat[1], sig);
+      }
+      __syncthreads();
+      if (tid == 0) {  // one pair of remote integer atomics per CTA (wrapping adds: order independent, deterministic)
+        atomicAdd(&lead->stat[0], sh.s_stat[0]);
+        atomicAdd(&lead->stat[1], sh.s_stat[1]);
+        sh.s_stat[0] = sh.s_stat[1] = 0u;
+      }
+    }
+    cluster_arrive();
+
+    // ---- (b) dense geometric rows (ICPReduction, reduce.cu:224-331) while the statistics settle
+    float acc[29];
+#pragma unroll
+    for (int k = 0; k < 29; ++k) acc[k] = 0.f;
+    if (do_icp) {
+      IcpFrame F;
+      F.M = load_m33(sh.Pl.Mcp);
+      F.t = mk3(sh.Pl.tcp[0], sh.Pl.tcp[1], sh.Pl.tcp[2]);
+      level_intr(gn, level, F.fx, F.fy, F.cx, F.cy);
+      F.distThres2 = od.distThres * od.distThres;
+      F.angleThres2 = od.angleThres * od.angleThres;
+      const float* __restrict__ vc = od.vmap_curr[level];
+      const float* __restrict__ nc = od.nmap_curr[level];
+      const float* __restrict__ vp = od.vmap_c_prev[level];
+      const float* __restrict__ np_ = od.nmap_c_prev[level];
+      if ((cols & 3) == 0) {
+        const int ngroups = N >> 2;
+        for (int g = gid; g < ngroups; g += gstride) {
+          const int i0 = g << 2;
+          const float4 vx4 = *reinterpret_cast<const float4*>(vc + i0);
+          const float4 vy4 = *reinterpret_cast<const float4*>(vc + plane + i0);
+          const float4 vz4 = *reinterpret_cast<const float4*>(vc + 2 * plane + i0);
+          const float4 nx4 = *reinterpret_cast<const float4*>(nc + i0);
+          const float4 ny4 = *reinterpret_cast<const float4*>(nc + plane + i0);
+          const float4 nz4 = *reinterpret_cast<const float4*>(nc + 2 * plane + i0);
+          const float vxs[4] = {vx4.x, vx4.y, vx4.z, vx4.w}, vys[4] = {vy4.x, vy4.y, vy4.z, vy4.w}, vzs[4] = {vz4.x, vz4.y, vz4.z, vz4.w};
+          const float nxs[4] = {nx4.x, nx4.y, nx4.z, nx4.w}, nys[4] = {ny4.x, ny4.y, ny4.z, ny4.w}, nzs[4] = {nz4.x, nz4.y, nz4.z, nz4.w};
+          f3 sv[4];
+          int qv[4];
+          float gm[4][6];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) qv[h] = icp_project(F, mk3(vxs[h], vys[h], vzs[h]), rows, cols, sv[h]);
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int a = qv[h] < 0 ? 0 : qv[h];
+            gm[h][0] = __ldg(vp + a);
+            gm[h][1] = __ldg(vp + plane + a);
+            gm[h][2] = __ldg(vp + 2 * plane + a);
+            gm[h][3] = __ldg(np_ + a);
+            gm[h][4] = __ldg(np_ + plane + a);
+            gm[h][5] = __ldg(np_ + 2 * plane + a);
+          }
+#pragma unroll
+          for (int h = 0; h < 4; ++h)
+            if (qv[h] >= 0) icp_accumulate(F, sv[h], mk3(nxs[h], nys[h], nzs[h]), mk3(gm[h][0], gm[h][1], gm[h][2]), mk3(gm[h][3], gm[h][4], gm[h][5]), acc);
+        }
+      } else {
+        for (int i = gid; i < N; i += gstride) {
+          f3 sp;
+          const int q = icp_project(F, mk3(vc[i], vc[i + plane], vc[i + 2 * plane]), rows, cols, sp);
+          if (q >= 0)
+            icp_accumulate(F, sp, mk3(nc[i], nc[i + plane], nc[i + 2 * plane]), mk3(vp[q], vp[q + plane], vp[q + 2 * plane]),
+                           mk3(np_[q], np_[q + plane], np_[q + 2 * plane]), acc);
+        }
+      }
+    }
+    cluster_wait();
+
+    // ---- (c) photometric rows (RGBReduction::getProducts, reduce.cu:419-480) with this iteration's sigma
+    float acc2[29];
+#pragma unroll
+    for (int k = 0; k < 29; ++k) acc2[k] = 0.f;
+    if (do_rgb) {
+      if (tid == 0) {
+        const int rgbSize = (int)lead->stat[0], sigma = (int)lead->stat[1];
+        // reference: std::sqrt((float)sigma / rgbSize == 0 ? 1 : rgbSize)  (RGBDOdometry.cpp:442, App. A-1)
+        float sigmaVal = (float)sqrt((double)(((float)sigma / rgbSize == 0) ? 1 : rgbSize));
+        if (gn->rgbOnly) sigmaVal = -1;
+        sh.sigma = sigmaVal;
+      }
+      __syncthreads();
+      const float sigma = sh.sigma;
+      float lfx, lfy, lcx, lcy;
+      level_intr(gn, level, lfx, lfy, lcx, lcy);
+      for (int c = gid; c < ncand; c += gstride) {
+        const int4 t = terms[c];
+        if (t.x != -1) rgb_accumulate(t, sigma, lfx, lfy, lcx, lcy, od.sobelScale, acc2);
+      }
+    }
+    block_reduce_sum<29, GC_THREADS>(acc, sh.sred_a);
+    block_reduce_sum<29, GC_THREADS>(acc2, sh.sred_b);
+    if (tid < 29) {
+      lead->slots[rank][tid] = acc[0];
+      lead->slots[rank][32 + tid] = acc2[0];
+    }
+    cluster_sync_all();
+
+    // ---- (d) leader: statistics bookkeeping, sums in rank order, solve, publish
+    if (rank == 0) {
+      GnScratch& S = sh.S;
+      if (tid == 0) {
+        sh.brk = 0;
+        if (do_rgb) {
+          const int rgbSize = (int)sh.stat[0], sigma = (int)sh.stat[1];
+          float sigmaVal = (float)sqrt((double)(((float)sigma / rgbSize == 0) ? 1 : rgbSize));
+          const float rgbError = (float)(sqrt((double)sigma) / (rgbSize == 0 ? 1 : rgbSize));
+          const float prevError = (iter == 0) ? FLT_MAX : gn->rgbErrBuf[(iter + 1) & 1];  // RGBDOdometry.cpp:404
+          const bool brk = gn->rgbOnly && rgbError > prevError;
+          if (gn->rgbOnly) sigmaVal = -1;
+          sh.brk = brk ? 1 : 0;
+          gn->sum_res[0] = rgbSize;
+          gn->sum_res[1] = sigma;
+          gn->rgbSize = rgbSize;
+          gn->sigma = sigma;
+          if (!brk) {
+            gn->rgbErrBuf[iter & 1] = rgbError;
+            gn->lastRGBError = rgbError;
+            gn->lastRGBCount = (float)rgbSize;
+            gn->sigmaVal = sigmaVal;
+          }
+          sh.stat[0] = sh.stat[1] = 0u;
+        }
+      }
+      if (tid >= 64 && tid < 128) {
+        const int v = tid - 64;
+        double t = 0;
+        for (int r = 0; r < C; ++r) t += (double)sh.slots[r][v];
+        const float f = (float)t;
+        S.sums[v] = f;
+        if (v < 32)
+          gn->sum_icp[v] = f;
+        else
+          gn->sum_rgb[v - 32] = f;
+      }
+      __syncthreads();
+      if (sh.brk) {
+        if (tid == 0) {
+          gn->break_level = level;
+          if (next_level >= 0 && next_level != level) gn_prepare_warp(gn, next_level);
+        }
+      } else if (wid == 0) {
+        gn_update_warp(od, S, level, iter, next_level);
+        __syncwarp();
+        if (lane < 16) S.rRt[lane] = S.nrt[lane];
+      }
+      __syncthreads();
+      if (tid < 9) {
+        sh.P.Mcp[tid] = gn->Mcp[tid];
+        sh.P.krkinv[tid] = gn->krkinv[tid];
+      } else if (tid < 12) {
+        sh.P.tcp[tid - 9] = gn->tcp[tid - 9];
+        sh.P.kt[tid - 9] = gn->kt[tid - 9];
+      } else if (tid == 12) {
+        sh.P.break_level = gn->break_level;
+      }
+    }
+    cluster_sync_all();
+    if (tid < GC_PARAM_WORDS) reinterpret_cast<int*>(&sh.Pl)[tid] = reinterpret_cast<const int*>(&lead->P)[tid];
+    __syncthreads();
+  }
+  cluster_sync_all();  // nobody leaves while a peer may still read its shared memory
+}
+
 // expands the compact per-candidate terms into the reference's dense DataTerm image (inspection / stage API only)
 __global__ void k_terms_expand(OdomDev od, int level) {
   pdl_enter();
@@ -1134,6 +1462,50 @@ namespace ef {
 
 // the device-resident Gauss-Newton schedule; T_wc in/out lives in gn->T_wc
 // The SO(3) pre-alignment loop of tracker `which` on ctx->stream (its state block, partials and ticket are its own)
+// one cluster of `cluster` CTAs (grid = cluster), programmatic dependent launch like every other kernel
+template <typename... KArgs, typename... Args>
+static void ef_launch_cluster(EfContext* ctx, void (*kernel)(KArgs...), int cluster, int block, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (ctx->pdl && !ctx->plain_next) ? 2 : 1;
+  ctx->plain_next = false;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  ctx->launches++;
+}
+
+// Largest cluster (16, else 8) of k_gn_cluster the device can co-schedule; 0 when clusters are unavailable. Called once per context.
+int odom_cluster_size(int want) {
+  if (want <= 0) return 0;
+  cudaFuncSetAttribute(k_gn_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  for (int c = want > 8 ? 16 : 8; c >= 8; c >>= 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(c);
+    cfg.blockDim = dim3(GC_THREADS);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = c;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_gn_cluster, &cfg) == cudaSuccess && n >= 1) return c;
+    cudaGetLastError();
+  }
+  return 0;
+}
+
 int odom_so3_async(EfContext* ctx, int which) {
   OdomDev& od = ctx->odom[which];
   EF_LAUNCH(ctx, k_so3_begin, 1, 32, 0, od.so3s, (const GNState*)od.gn);
@@ -1177,7 +1549,19 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
   ctx->maps_dirty[which] = false;
   ef_stage(ctx, 4);
   EF_LAUNCH(ctx, k_gn_seed, 1, 32, 0, od.gn, ns ? sched_level[0] : 0, (const So3State*)od.so3s);
-  for (int s = 0; s < ns; ++s) {
+  // the coarse levels (ctx->gn_cluster_levels of them, from the top of the pyramid) run inside one cluster launch
+  int s0 = 0;
+  if (ctx->gn_cluster > 0 && ns > 0) {
+    GnSched sched;
+    sched.n = ns;
+    for (int s = 0; s < ns; ++s) {
+      sched.level[s] = (signed char)sched_level[s];
+      sched.iter[s] = (signed char)sched_iter[s];
+    }
+    while (s0 < ns && sched_level[s0] > NUM_PYRS - 1 - ctx->gn_cluster_levels) ++s0;
+    if (s0 > 0) ef_launch_cluster(ctx, k_gn_cluster, ctx->gn_cluster, GC_THREADS, od, sched, 0, s0, rgb ? 1 : 0, icp ? 1 : 0);
+  }
+  for (int s = s0; s < ns; ++s) {
     const int lv = sched_level[s];
     const int npx = od.rows[lv] * od.cols[lv];
     const int next_lv = (s + 1 < ns) ? sched_level[s + 1] : -1;

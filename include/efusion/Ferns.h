@@ -131,6 +131,8 @@ class Ferns {
         minId = (int)i;
       }
     }
+    lastCandidate = minId;
+    lastDissimilarity = minimum;
     ef::SE3d T_wc_est;
     if (minId != -1 && blockHDAware(&frame, frames.at(minId)) > 0.3) {
       const Frame& fern = *frames.at(minId);
@@ -179,6 +181,8 @@ class Ferns {
   int lastClosest;
   const uint8_t badCode;
   float lastICPError = 0, lastICPCount = 0, lastPhotoError = 0;  // of the last registration (the reference prints them in a comment)
+  int lastCandidate = -1;                                        // the frame findFrame tried to register against, accepted or not
+  float lastDissimilarity = 0;
 
  private:
   struct Small {

@@ -5,6 +5,7 @@
 #include <Ferns.h>
 #include <Tools/RawLogReader.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -36,6 +37,13 @@ int main(int argc, char** argv) {
   const auto B = T_est.matrix();
   double dmax = 0;
   for (int r = 0; r < 3; ++r) dmax = std::fmax(dmax, std::fabs((double)A(r, 3) - (double)B(r, 3)));
+  for (size_t i = 0; i < ferns.frames.size(); ++i) {
+    const auto F = ferns.frames[i]->T_wc.matrix();
+    double d2 = 0;
+    for (int r = 0; r < 3; ++r) d2 += ((double)A(r, 3) - (double)F(r, 3)) * ((double)A(r, 3) - (double)F(r, 3));
+    std::fprintf(stderr, "stored %zu srcTime %d goodCodes %d dist_to_query %.4f\n", i, ferns.frames[i]->srcTime, ferns.frames[i]->goodCodes, std::sqrt(d2));
+  }
+  std::fprintf(stderr, "candidate %d dissimilarity %.4f\n", ferns.lastCandidate, (double)ferns.lastDissimilarity);
   std::printf("CLOSEST %d ICPERR %.6g ICPCOUNT %.0f PHOTO %.3f CONSTRAINTS %zu TDIFF %.5f\n", ferns.lastClosest, (double)ferns.lastICPError,
               (double)ferns.lastICPCount, (double)ferns.lastPhotoError, constraints.size(), dmax);
   return 0;

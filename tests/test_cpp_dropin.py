@@ -141,9 +141,11 @@ def test_ferns_keyframes_and_relocalisation_candidate(tmp_path, K):
     assert len(frames) == 31
     klg = str(tmp_path / "ferns.klg")
     synth.write_klg(klg, [(f[0], f[1]) for f in frames])
-    out = subprocess.check_output([exe, klg, str(K.width), str(K.height), str(K.fx), str(K.fy), str(K.cx), str(K.cy), "400"], text=True)
+    run = subprocess.run([exe, klg, str(K.width), str(K.height), str(K.fx), str(K.fy), str(K.cx), str(K.cy), "400"], text=True, capture_output=True, check=True)
+    out = run.stdout
+    print(run.stderr)
     kv = dict(zip(out.split()[0::2], out.split()[1::2]))
     assert int(kv["FRAMES"]) == 30 and int(kv["STORED"]) >= 1 and int(kv["STORED"]) == int(kv["ADDED"])
-    assert int(kv["CLOSEST"]) >= 0, out
+    assert int(kv["CLOSEST"]) >= 0, out + run.stderr
     assert float(kv["ICPERR"]) < 3e-4 and float(kv["ICPCOUNT"]) > 2400 and float(kv["PHOTO"]) < 115, out
     assert float(kv["TDIFF"]) < 0.03 and int(kv["CONSTRAINTS"]) > 10, out
