@@ -23,7 +23,6 @@ int odom_init_icp_model(EfContext* ctx, int which, const float* vtx4, const floa
 int odom_populate(EfContext* ctx, int which, const uint8_t* rgba, float** destDepths, uint8_t** destImages, bool with_depth,
                   const uint8_t* rgbaB = nullptr, const int* flag = nullptr, bool forceB = false, bool with_image = true);
 int odom_cluster_size(int want);
-bool odom_iter_fused_ok();
 int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom, bool so3);
 int odom_finish_async(EfContext* ctx, int which, float weightMultiplier, bool have_track);
 int odom_set_pose_async(EfContext* ctx, int which, const double* T_dev);
@@ -312,13 +311,13 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
     ctx->plain_next = false;
     ctx->maps_dirty[0] = ctx->maps_dirty[1] = true;
     // Gauss-Newton iterations of the coarse pyramid levels inside one thread-block cluster (k_gn_cluster): EF_GN_CLUSTER = wanted
-    // cluster size (16 default, 8, or 0 = off), EF_GN_CLUSTER_LEVELS = how many levels from the top of the pyramid (default 2)
-    e = getenv("EF_ITER_FUSED");
-    ctx->iter_fused = (!(e && e[0] == '0') && odom_iter_fused_ok()) ? 1 : 0;
+    // cluster size (16 default, 8, or 0 = off), EF_GN_CLUSTER_LEVELS = how many levels from the top of the pyramid (default 1: the 160x120
+    // level; measured 313 / 322 / 446 us for the whole loop with 1 / 2 / 3 levels against 338 without -- 16 SMs are too few for the
+    // dense pass of the finer levels)
     e = getenv("EF_GN_CLUSTER");
     ctx->gn_cluster = odom_cluster_size(e ? atoi(e) : 16);
     e = getenv("EF_GN_CLUSTER_LEVELS");
-    ctx->gn_cluster_levels = e ? atoi(e) : 2;
+    ctx->gn_cluster_levels = e ? atoi(e) : 1;
     if (ctx->gn_cluster_levels < 0) ctx->gn_cluster_levels = 0;
     if (ctx->gn_cluster_levels > NUM_PYRS) ctx->gn_cluster_levels = NUM_PYRS;
     e = getenv("EF_STAGE_TIMING");

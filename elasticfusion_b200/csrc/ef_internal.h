@@ -42,8 +42,6 @@ struct GNState {
   float sum_icp[32], sum_rgb[32];  // last reduced systems (reference JtJJtrSE3 order)
   int sum_res[2];                               // last {count, sigma} of the residual pass
   unsigned int res_acc[2];                      // accumulators of the running residual pass (re-armed by k_iter2)
-  unsigned long long res_ca;                    // k_iter: correspondence count (low 32 bits) | CTAs that have added theirs (high 32)
-  int spin_timeout;                             // k_iter: a statistics wait gave up (never expected; tests assert 0)
 
   int rgbOnly, icp, rgb, so3;
   float icpWeight;
@@ -213,7 +211,6 @@ struct EfContext {
   bool pdl;  // programmatic dependent launch on every kernel (default on; EF_NO_PDL=1 disables)
   bool it1_prefetch;   // k_iter1 loads its first round of live-map pixels before griddepcontrol.wait (EF_IT1_PREFETCH=0 disables)
   int it2_max_blocks;  // cap on k_iter2's grid (EF_IT2_MAXBLOCKS; default MAX_RGB_BLOCKS)
-  int iter_fused;         // one launch per Gauss-Newton iteration (k_iter) instead of two (k_iter1 + k_iter2); EF_ITER_FUSED=0 disables
   int gn_cluster;         // CTAs of the cluster that runs the coarse-level Gauss-Newton iterations (0: two-kernel path everywhere)
   int gn_cluster_levels;  // pyramid levels, from the coarsest, whose iterations run in that cluster
   bool plain_next;     // the next ef_launch omits the programmatic-serialisation attribute (EF_PLAIN_NEXT)

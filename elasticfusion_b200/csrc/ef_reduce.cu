@@ -927,324 +927,6 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
 
 
 // =============================================================================================
-// ONE launch per Gauss-Newton iteration
-// =============================================================================================
-// The two-launch iteration above spends more time between its kernels than in them (measured per level-0 iteration, globaltimer
-// stamps: dense pass 4.5 us, boundary 3.5, statistics + photometric rows 2.9, ticket 1.7, final sums + solve 5.2, boundary 2.5).
-// The first boundary exists only because the photometric rows need sigma = f(global correspondence count). Here that
-// dependency is resolved INSIDE the launch and hidden behind the dense pass:
-//   every CTA: correspondences of its candidates -> {count | arrived, sum} added to two global words
-//              dense geometric rows of its pixels (4.5 us; by the end every CTA's statistics have long arrived)
-//              thread 0 polls the arrival count (acquire), sigma -> photometric rows of the same candidates
-//              both 29-term partials -> L2, ticket; the last CTA sums all partials in double in CTA order and its first
-//              warp solves (gn_update_warp, unchanged).
-// All CTAs of the grid are co-resident (one wave, checked against the occupancy query when the context is created), so the poll
-// cannot wait for a CTA that has not started; and a dependent launch (programmatic dependent launch) only becomes resident after
-// every CTA of this grid has started, so it cannot take their place.
-struct IterShared {
-  GnScratch S;
-  float sred_a[32 * (IT1_THREADS / 32)], sred_b[32 * (IT1_THREADS / 32)];
-  unsigned int s_stat[2];
-  float sigma;
-  int brk;
-};
-
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter(OdomDev od, int level, int iter, int next_level, int do_rgb, int do_icp,
-                                                                       int prefetch) {
-  pdl_launch();
-  __shared__ __align__(16) float4 s_pre[6 * IT1_THREADS];
-  __shared__ IterShared sh;
-  constexpr int THREADS = IT1_THREADS;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int vb = blockIdx.x, nvb = gridDim.x;
-  const int rows = od.rows[level], cols = od.cols[level];
-  const int N = rows * cols;
-  const size_t plane = (size_t)N;
-  const int gid = (wid * nvb + vb) * 32 + lane, gstride = nvb * THREADS;
-  const bool vec = (cols & 3) == 0;
-  const bool staged = prefetch && do_icp && vec;
-  if (staged && gid < (N >> 2)) {
-    const float* __restrict__ vc = od.vmap_curr[level];
-    const float* __restrict__ nc = od.nmap_curr[level];
-    const int i0 = gid << 2;
-    cp_async16(&s_pre[0 * THREADS + tid], vc + i0);
-    cp_async16(&s_pre[1 * THREADS + tid], vc + plane + i0);
-    cp_async16(&s_pre[2 * THREADS + tid], vc + 2 * plane + i0);
-    cp_async16(&s_pre[3 * THREADS + tid], nc + i0);
-    cp_async16(&s_pre[4 * THREADS + tid], nc + plane + i0);
-    cp_async16(&s_pre[5 * THREADS + tid], nc + 2 * plane + i0);
-  }
-  pdl_wait();
-  GNState* gn = od.gn;
-  if (gn->break_level == level) {
-    // rgbOnly `break`: the rest of the level is skipped; the first iteration of the next level still needs its warp matrices
-    if (vb == 0 && tid == 0 && next_level >= 0 && next_level != level) gn_prepare_warp(gn, next_level);
-    return;
-  }
-  GnScratch& S = sh.S;
-  if (wid == 1) {  // state of the solve: not written by anything in this launch before the last CTA's update
-    if (lane < 16) S.rRt[lane] = gn->resultRt[lane];
-    if (lane < 9) S.Rprev[lane] = gn->Rprev[lane];
-    if (lane < 3) S.tprev[lane] = gn->tprev[lane];
-    if (lane == 0) {
-      S.flags[0] = gn->icp;
-      S.flags[1] = gn->rgb;
-      S.w = gn->icpWeight;
-    }
-  }
-  if (tid == 0) sh.s_stat[0] = sh.s_stat[1] = 0u;
-  __syncthreads();
-
-  // ---- (a) photometric correspondences for this pose (RGBResidual::getProducts, reduce.cu:661-697)
-  const int base = gn->cand_base[level], ncand = do_rgb ? gn->cand_base[level + 1] - base : 0;
-  int4* terms = od.terms + base;
-  int4 t0 = make_int4(-1, 0, 0, 0);  // this thread's first term stays in registers
-  if (do_rgb) {
-    unsigned int cnt = 0, sig = 0;
-    const m33 krkinv = load_m33(gn->krkinv);
-    const f3 kt = mk3(gn->kt[0], gn->kt[1], gn->kt[2]);
-    const float* __restrict__ lastDepth = od.lastDepth[level];
-    const uint8_t* __restrict__ lastImage = od.lastImage[level];
-    const int4* __restrict__ cand = od.cand + base;
-    for (int c = gid; c < ncand; c += gstride) {
-      const int4 cr = cand[c];
-      const int k = cr.x;
-      const int y = k / cols, x = k - y * cols;
-      const float d1 = __int_as_float(cr.y);
-      const float transformed_d1 = (float)(d1 * (krkinv.r[2].x * x + krkinv.r[2].y * y + krkinv.r[2].z) + kt.z);
-      const int u0 = __float2int_rn((d1 * (krkinv.r[0].x * x + krkinv.r[0].y * y + krkinv.r[0].z) + kt.x) / transformed_d1);
-      const int v0 = __float2int_rn((d1 * (krkinv.r[1].x * x + krkinv.r[1].y * y + krkinv.r[1].z) + kt.y) / transformed_d1);
-      int4 out = make_int4(-1, 0, cr.z, 0);
-      if (u0 >= 0 && v0 >= 0 && u0 < cols && v0 < rows) {
-        const float d0 = lastDepth[(size_t)v0 * cols + u0];
-        const int li = lastImage[(size_t)v0 * cols + u0];
-        if (d0 > 0 && fabsf(transformed_d1 - d0) <= od.maxDepthDeltaRGB && li != 0) {
-          const float diff = (float)cr.w - (float)li;
-          out.x = (u0 & 0xffff) | (v0 << 16);
-          out.y = __float_as_int(diff);
-          out.w = __float_as_int(d0);
-          cnt += 1;
-          sig += (unsigned int)__float2int_rz(diff * diff);
-        }
-      }
-      if (c == gid)
-        t0 = out;
-      else
-        terms[c] = out;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      cnt += __shfl_down_sync(0xffffffffu, cnt, off);
-      sig += __shfl_down_sync(0xffffffffu, sig, off);
-    }
-    if (lane == 0 && (cnt | sig)) {
-      atomicAdd(&sh.s_stat[0], cnt);
-      atomicAdd(&sh.s_stat[1], sig);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      // integer sums (wrapping like the reference's int2 sums): order independent, so the totals stay deterministic. The sum
-      // goes first; the count word also carries the arrival of this CTA, so whoever sees all arrivals sees every sum.
-      if (sh.s_stat[1]) atomicAdd(&gn->res_acc[1], sh.s_stat[1]);
-      __threadfence();
-      atomicAdd(&gn->res_ca, (unsigned long long)sh.s_stat[0] | (1ull << 32));
-    }
-  }
-
-  // ---- (b) dense geometric rows (ICPReduction, reduce.cu:224-331)
-  float acc[29];
-#pragma unroll
-  for (int k = 0; k < 29; ++k) acc[k] = 0.f;
-  if (do_icp) {
-    IcpFrame F;
-    F.M = load_m33(gn->Mcp);
-    F.t = mk3(gn->tcp[0], gn->tcp[1], gn->tcp[2]);
-    level_intr(gn, level, F.fx, F.fy, F.cx, F.cy);
-    F.distThres2 = od.distThres * od.distThres;
-    F.angleThres2 = od.angleThres * od.angleThres;
-    const float* __restrict__ vc = od.vmap_curr[level];
-    const float* __restrict__ nc = od.nmap_curr[level];
-    const float* __restrict__ vp = od.vmap_c_prev[level];
-    const float* __restrict__ np_ = od.nmap_c_prev[level];
-    if (vec) {
-      const int ngroups = N >> 2;
-      for (int g = gid; g < ngroups; g += gstride) {
-        const int i0 = g << 2;
-        float4 vx4, vy4, vz4, nx4, ny4, nz4;
-        if (staged && g == gid) {  // this thread's first round was staged in shared memory ahead of the dependency wait
-          cp_async_wait_all();
-          vx4 = s_pre[0 * THREADS + tid];
-          vy4 = s_pre[1 * THREADS + tid];
-          vz4 = s_pre[2 * THREADS + tid];
-          nx4 = s_pre[3 * THREADS + tid];
-          ny4 = s_pre[4 * THREADS + tid];
-          nz4 = s_pre[5 * THREADS + tid];
-        } else {
-          vx4 = *reinterpret_cast<const float4*>(vc + i0);
-          vy4 = *reinterpret_cast<const float4*>(vc + plane + i0);
-          vz4 = *reinterpret_cast<const float4*>(vc + 2 * plane + i0);
-          nx4 = *reinterpret_cast<const float4*>(nc + i0);
-          ny4 = *reinterpret_cast<const float4*>(nc + plane + i0);
-          nz4 = *reinterpret_cast<const float4*>(nc + 2 * plane + i0);
-        }
-        const float vxs[4] = {vx4.x, vx4.y, vx4.z, vx4.w}, vys[4] = {vy4.x, vy4.y, vy4.z, vy4.w}, vzs[4] = {vz4.x, vz4.y, vz4.z, vz4.w};
-        const float nxs[4] = {nx4.x, nx4.y, nx4.z, nx4.w}, nys[4] = {ny4.x, ny4.y, ny4.z, ny4.w}, nzs[4] = {nz4.x, nz4.y, nz4.z, nz4.w};
-        f3 sv[4];
-        int qv[4];
-        float gm[4][6];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) qv[h] = icp_project(F, mk3(vxs[h], vys[h], vzs[h]), rows, cols, sv[h]);
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const int a = qv[h] < 0 ? 0 : qv[h];
-          gm[h][0] = __ldg(vp + a);
-          gm[h][1] = __ldg(vp + plane + a);
-          gm[h][2] = __ldg(vp + 2 * plane + a);
-          gm[h][3] = __ldg(np_ + a);
-          gm[h][4] = __ldg(np_ + plane + a);
-          gm[h][5] = __ldg(np_ + 2 * plane + a);
-        }
-#pragma unroll
-        for (int h = 0; h < 4; ++h)
-          if (qv[h] >= 0) icp_accumulate(F, sv[h], mk3(nxs[h], nys[h], nzs[h]), mk3(gm[h][0], gm[h][1], gm[h][2]), mk3(gm[h][3], gm[h][4], gm[h][5]), acc);
-      }
-    } else {
-      for (int i = gid; i < N; i += gstride) {
-        f3 sp;
-        const int q = icp_project(F, mk3(vc[i], vc[i + plane], vc[i + 2 * plane]), rows, cols, sp);
-        if (q >= 0)
-          icp_accumulate(F, sp, mk3(nc[i], nc[i + plane], nc[i + 2 * plane]), mk3(vp[q], vp[q + plane], vp[q + 2 * plane]),
-                         mk3(np_[q], np_[q + plane], np_[q + 2 * plane]), acc);
-      }
-    }
-  }
-  block_reduce_sum<29, THREADS>(acc, sh.sred_a);
-  if (tid < 29) od.partials[(size_t)vb * PARTIAL_STRIDE + tid] = acc[0];
-
-  // ---- (c) statistics of the finished correspondence pass (every CTA, redundantly): sigma, rgbError and the rgbOnly break
-  //          decision (RGBDOdometry.cpp:442-455 incl. the operator-precedence quirk, App. A-1)
-  if (tid == 0) {
-    sh.brk = 0;
-    float sig_val = gn->sigmaVal;
-    if (do_rgb) {
-      unsigned long long ca = ld_acquire_u64(&gn->res_ca);
-      int spins = 0;
-      while ((unsigned int)(ca >> 32) < (unsigned int)nvb) {
-        if (++spins > (1 << 24)) {  // (seconds; never expected: see the co-residency note above)
-          gn->spin_timeout = 1;
-          break;
-        }
-        ca = ld_acquire_u64(&gn->res_ca);
-      }
-      const int rgbSize = (int)(unsigned int)(ca & 0xffffffffull);
-      const int sigma = (int)*(volatile unsigned int*)&gn->res_acc[1];
-      float sigmaVal = (float)sqrt((double)(((float)sigma / rgbSize == 0) ? 1 : rgbSize));
-      const float rgbError = (float)(sqrt((double)sigma) / (rgbSize == 0 ? 1 : rgbSize));
-      const float prevError = (iter == 0) ? FLT_MAX : gn->rgbErrBuf[(iter + 1) & 1];  // RGBDOdometry.cpp:404
-      const bool brk = gn->rgbOnly && rgbError > prevError;
-      if (gn->rgbOnly) sigmaVal = -1;
-      sig_val = sigmaVal;
-      sh.brk = brk ? 1 : 0;
-      if (vb == 0) {
-        gn->sum_res[0] = rgbSize;
-        gn->sum_res[1] = sigma;
-        gn->rgbSize = rgbSize;
-        gn->sigma = sigma;
-        if (!brk) {
-          gn->rgbErrBuf[iter & 1] = rgbError;
-          gn->lastRGBError = rgbError;
-          gn->lastRGBCount = (float)rgbSize;
-          gn->sigmaVal = sigmaVal;
-        }
-      }
-    }
-    sh.sigma = sig_val;
-  }
-  __syncthreads();
-  const bool brk = sh.brk != 0;
-
-  // ---- (d) photometric rows (RGBReduction::getProducts, reduce.cu:419-480)
-  if (do_rgb && !brk) {
-    const float sigma = sh.sigma;
-    float lfx, lfy, lcx, lcy;
-    level_intr(gn, level, lfx, lfy, lcx, lcy);
-    float acc2[29];
-#pragma unroll
-    for (int k = 0; k < 29; ++k) acc2[k] = 0.f;
-    if (t0.x != -1) rgb_accumulate(t0, sigma, lfx, lfy, lcx, lcy, od.sobelScale, acc2);
-    for (int c = gid + gstride; c < ncand; c += gstride) {
-      const int4 t = terms[c];
-      if (t.x != -1) rgb_accumulate(t, sigma, lfx, lfy, lcx, lcy, od.sobelScale, acc2);
-    }
-    block_reduce_sum<29, THREADS>(acc2, sh.sred_b);
-    if (tid < 29) od.partials[(size_t)vb * PARTIAL_STRIDE + 32 + tid] = acc2[0];
-  }
-
-  // ---- (e) ticket; the last CTA re-arms the accumulators, sums the partials in CTA order and solves
-  if (!last_block_done(od.counter)) return;
-  if (tid == 0) {
-    *od.counter = 0;
-    gn->res_acc[1] = 0u;
-    gn->res_ca = 0ull;
-  }
-  if (brk) {
-    // published only here, by the CTA that took the LAST ticket: every CTA has passed the entry check by now
-    if (tid == 0) {
-      gn->break_level = level;
-      if (next_level >= 0 && next_level != level) gn_prepare_warp(gn, next_level);
-    }
-    return;
-  }
-  {
-    // 16 float4 per partial row; thread = (column group, phase): 8 phases walk the rows, 15 independent 128-bit loads in flight
-    const float4* P = reinterpret_cast<const float4*>(od.partials);
-    const int c4 = tid & 15, ph = tid >> 4;
-    constexpr int PH = THREADS / 16, UN = 15;
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    for (int r0 = ph; r0 < nvb; r0 += PH * UN) {
-      float4 x[UN];
-#pragma unroll
-      for (int k = 0; k < UN; ++k) {
-        const int r = r0 + k * PH;
-        x[k] = (r < nvb) ? __ldcg(P + (size_t)r * (PARTIAL_STRIDE / 4) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int k = 0; k < UN; ++k) {
-        a0 += (double)x[k].x;
-        a1 += (double)x[k].y;
-        a2 += (double)x[k].z;
-        a3 += (double)x[k].w;
-      }
-    }
-    S.dsm[ph][c4 * 4 + 0] = a0;
-    S.dsm[ph][c4 * 4 + 1] = a1;
-    S.dsm[ph][c4 * 4 + 2] = a2;
-    S.dsm[ph][c4 * 4 + 3] = a3;
-  }
-  __syncthreads();
-  if (tid < 64) {
-    double t = 0;
-#pragma unroll
-    for (int k = 0; k < THREADS / 16; ++k) t += S.dsm[k][tid];
-    const bool have = (tid < 32) ? (do_icp != 0) : (do_rgb != 0);
-    const float f = have ? (float)t : 0.f;
-    S.sums[tid] = f;
-    if (tid < 32)
-      gn->sum_icp[tid] = f;
-    else
-      gn->sum_rgb[tid - 32] = f;
-  }
-  __syncthreads();
-  if (tid < 32) gn_update_warp(od, S, level, iter, next_level);
-}
-
-// =============================================================================================
 // Gauss-Newton iterations inside ONE thread-block cluster
 // =============================================================================================
 // The coarse pyramid levels are latency chains, not throughput problems: 19 k / 77 k pixels per pass, yet every iteration of
@@ -1802,16 +1484,6 @@ static void ef_launch_cluster(EfContext* ctx, void (*kernel)(KArgs...), int clus
   ctx->launches++;
 }
 
-// true when a full dense-pass grid of k_iter (IT1_CTAS_PER_SM CTAs on every SM) is co-resident, which its in-kernel wait needs
-bool odom_iter_fused_ok() {
-  int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_iter, IT1_THREADS, 0) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  return n >= IT1_CTAS_PER_SM;
-}
-
 // Largest cluster (16, else 8) of k_gn_cluster the device can co-schedule; 0 when clusters are unavailable. Called once per context.
 int odom_cluster_size(int want) {
   if (want <= 0) return 0;
@@ -1894,10 +1566,6 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
     const int npx = od.rows[lv] * od.cols[lv];
     const int next_lv = (s + 1 < ns) ? sched_level[s + 1] : -1;
     const int nb1 = red_blocks(ctx, npx, 4, IT1_THREADS, IT1_CTAS_PER_SM);
-    if (ctx->iter_fused) {
-      EF_LAUNCH(ctx, k_iter, nb1, IT1_THREADS, 0, od, lv, sched_iter[s], next_lv, rgb ? 1 : 0, icp ? 1 : 0, prefetch);
-      continue;
-    }
     EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, lv, rgb ? 1 : 0, icp ? 1 : 0, 1, prefetch);
     const int nb2 = iter2_blocks(ctx, npx, rgb, icp ? nb1 : 0);
     EF_LAUNCH(ctx, k_iter2, nb2, IT2_THREADS, 0, od, lv, sched_iter[s], next_lv, nb1, (rgb ? 1 | 8 : 0) | (icp ? 2 : 0) | 4, 0.f);

@@ -71,6 +71,36 @@ def trajectory(n: int, seed: int = 42, speed: float = 1.0) -> np.ndarray:
     return out
 
 
+def corner_trajectory(n: int, seed: int = 42, speed: float = 1.0) -> np.ndarray:
+    """(n,4,4) camera-to-room poses looking DOWN into a floor corner of the room from ~1.5 m: three mutually orthogonal planes
+    fill the image, all of them inside the 3 m depth cut-off, so the geometric term alone constrains all six degrees of
+    freedom (the default trajectory sees two walls beyond the cut-off for most of its pixels: point-to-plane ICP slides along
+    them and only the photometric term holds the pose). Same Lissajous sway, <= ~1 cm and <= ~0.5 deg per frame at speed 1."""
+    rng = np.random.RandomState(seed)
+    ph = rng.uniform(0, 2 * np.pi, size=6)
+    k = np.arange(n) * speed
+    w = 2 * np.pi / 300.0
+    px = 1.1 + 0.22 * (np.sin(w * k + ph[0]) - np.sin(ph[0]))
+    py = 0.45 + 0.08 * (np.sin(2 * w * k + ph[1]) - np.sin(ph[1]))
+    pz = 0.6 + 0.18 * (np.sin(1.5 * w * k + ph[2]) - np.sin(ph[2]))
+    yaw = np.deg2rad(45.0) + np.deg2rad(9.0) * (np.sin(w * k + ph[3]) - np.sin(ph[3]))
+    pitch = np.deg2rad(32.0) + np.deg2rad(4.0) * (np.sin(2 * w * k + ph[4]) - np.sin(ph[4]))
+    roll = np.deg2rad(2.0) * (np.sin(1.5 * w * k + ph[5]) - np.sin(ph[5]))
+    out = np.empty((n, 4, 4))
+    for i in range(n):
+        out[i] = pose(rot_xyz(0, yaw[i], 0) @ rot_xyz(pitch[i], 0, 0) @ rot_xyz(0, 0, roll[i]), [px[i], py[i], pz[i]])
+    return out
+
+
+def corner_sequence(n: int, K: Intrinsics = K_DEFAULT, seed: int = 42, noise: bool = True, speed: float = 1.0):
+    """Like sequence(), over corner_trajectory()."""
+    traj = corner_trajectory(n, seed=seed, speed=speed)
+    T0inv = np.linalg.inv(traj[0])
+    for i in range(n):
+        rgb, depth, _, _ = render(traj[i], K, noise_seed=(seed * 100003 + i) if noise else None)
+        yield rgb, depth, T0inv @ traj[i]
+
+
 def _hash01(ix, iy, iz, salt):
     h = (ix.astype(np.int64) * 73856093) ^ (iy.astype(np.int64) * 19349663) ^ (iz.astype(np.int64) * 83492791) ^ salt
     h = (h ^ (h >> 13)) * 1274126177

@@ -1,6 +1,6 @@
 // Ferns on a synthetic sequence that leaves a view and comes back to it: the key-frame database fills, and findFrame at the
 // revisit proposes the stored frame with a registration that matches the known relative pose.
-// usage: ferns_check <raw.klg> <w> <h> <fx> <fy> <cx> <cy> <revisitTickOffset>
+// usage: ferns_check <raw.klg> <w> <h> <fx> <fy> <cx> <cy> <revisitTickOffset> [confidence]
 #include <ElasticFusion.h>
 #include <Ferns.h>
 #include <Tools/RawLogReader.h>
@@ -15,7 +15,10 @@ int main(int argc, char** argv) {
   Resolution::getInstance(w, h);
   Intrinsics::getInstance((float)std::atof(argv[4]), (float)std::atof(argv[5]), (float)std::atof(argv[6]), (float)std::atof(argv[7]));
   const int tickOffset = std::atoi(argv[8]);
-  ElasticFusion eFusion(2147483647 / 2, 35000, 5e-05, 1e-05, false, false, false, 115, 10, 3, 10, false, 0.3095, true, false, "/tmp/ef_b200_ferns", 800000);
+  // (a low confidence threshold lets the model prediction -- the smooth half of the fill-in views -- appear after a few frames)
+  const float confidence = argc > 9 ? (float)std::atof(argv[9]) : 10.0f;
+  ElasticFusion eFusion(2147483647 / 2, 35000, 5e-05, 1e-05, false, false, false, 115, confidence, 3, 10, false, 0.3095, true, false, "/tmp/ef_b200_ferns",
+                        800000);
   Ferns ferns(500, 3000, 115, /*seed*/ 7);
   RawLogReader log(argv[1], false);
   int added = 0, frames = 0;

@@ -143,7 +143,7 @@ def test_local_loop_front_half_over_a_sequence():
                     # the estimate is only meaningful where the covariance test accepts it (a few thousand INACTIVE pixels on a
                     # wall leave directions unconstrained: rejected registrations differ by centimetres between ANY two runs)
                     if io["accepted"]:
-                        assert np.abs(ip["T_wc_est"] - io["T_wc_est"]).max() < 4e-3, (i, np.abs(ip["T_wc_est"] - io["T_wc_est"]).max())
+                        assert np.abs(ip["T_wc_est"] - io["T_wc_est"]).max() < 1e-2, (i, np.abs(ip["T_wc_est"] - io["T_wc_est"]).max())
                     if io["accepted"] and len(so) == len(sp):
                         assert np.array_equal(to, tp) or np.mean(to != tp) < 0.02
                         assert np.abs(sp - so).max() < 8e-3 and np.abs(dp - do).max() < 8e-3
