@@ -189,6 +189,7 @@ static int alloc_odom(EfContext* ctx, OdomDev& od) {
   CU(A->alloc(&od.vmaps_tmp, 4 * n0));
   CU(cudaMemsetAsync(od.vmaps_tmp, 0, 4 * n0 * sizeof(float), ctx->stream));
   CU(A->alloc(&od.gn, 1));
+  od.cand_base = reinterpret_cast<const int*>(reinterpret_cast<const char*>(od.gn) + offsetof(GNState, cand_base));
   CU(A->alloc(&od.so3s, 1));
   CU(A->alloc(&od.so3_partials, (size_t)MAX_RGB_BLOCKS * PARTIAL_STRIDE));
   CU(A->alloc(&od.so3_counter, 4));

@@ -96,6 +96,7 @@ struct OdomDev {
   // photometric candidates: pixels that pass every pose-independent gate of computeRgbResidual (reference reduce.cu:641-660),
   // compacted once per frame; {pixel index, nextDepth bits, dIdx | dIdy << 16, nextImage}
   int4* cand;
+  const int* cand_base;   // = gn->cand_base (device address): bounds of each level's candidates; like `cand`, final before the loop starts
   int4* terms;            // per candidate and iteration: {zero_x | zero_y << 16 (or -1), diff bits, dIdx | dIdy << 16, lastDepth[zero] bits}
   int level_start[NUM_PYRS + 1];  // flat pixel offset of each level
 

@@ -501,7 +501,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int THREADS>
-__device__ __forceinline__ void iter1_body(const OdomDev& od, int level, int do_res, int do_icp, int vb, int nvb, float* sred, const float4* pre /* [6][THREADS] in shared memory, or nullptr */) {
+__device__ __forceinline__ void iter1_body(const OdomDev& od, int level, int do_res, int do_icp, int vb, int nvb, float* sred, const float4* pre /* [6][THREADS] in shared memory, or nullptr */,
+                                           int pre_cand_have = 0, int pre_base = 0, int pre_ncand = 0, int4 pre_cand = make_int4(0, 0, 0, 0)) {
   GNState* gn = od.gn;
   const int rows = od.rows[level], cols = od.cols[level];
   const int N = rows * cols;
@@ -516,7 +517,9 @@ __device__ __forceinline__ void iter1_body(const OdomDev& od, int level, int do_
   unsigned int cnt = 0, sig = 0;
   const bool vec = (cols & 3) == 0;
   if (do_res) {
-    const int base = gn->cand_base[level], ncand = gn->cand_base[level + 1] - base;
+    // (bounds and this thread's first candidate may have been read ahead of the dependency wait: see k_iter1)
+    const int base = pre_cand_have ? pre_base : gn->cand_base[level];
+    const int ncand = pre_cand_have ? pre_ncand : gn->cand_base[level + 1] - base;
     const m33 krkinv = load_m33(gn->krkinv);
     const f3 kt = mk3(gn->kt[0], gn->kt[1], gn->kt[2]);
     const float* __restrict__ lastDepth = od.lastDepth[level];
@@ -524,7 +527,7 @@ __device__ __forceinline__ void iter1_body(const OdomDev& od, int level, int do_
     const int4* __restrict__ cand = od.cand + base;
     int4* terms = od.terms + base;
     for (int c = gid; c < ncand; c += gstride) {
-      const int4 cr = cand[c];
+      const int4 cr = (pre_cand_have && c == gid) ? pre_cand : cand[c];
       const int k = cr.x;
       const int y = k / cols, x = k - y * cols;
       const float d1 = __int_as_float(cr.y);
@@ -693,10 +696,22 @@ __global__ void __launch_bounds__(IT1_THREADS, IT1_CTAS_PER_SM) k_iter1(OdomDev 
       cp_async16(&s_pre[5 * IT1_THREADS + threadIdx.x], nc + 2 * plane + i0);
     }
   }
+  // ... and so were the photometric candidate list and its per-level bounds (launch_sobel runs before that fence): the bounds and
+  // this thread's first candidate are loaded here as well, which takes two dependent round trips out of the chain after the wait
+  int pre_base = 0, pre_ncand = 0;
+  int4 pre_cand = make_int4(0, 0, 0, 0);
+  const int pre_cand_have = (prefetch && do_res) ? 1 : 0;
+  if (pre_cand_have) {
+    const int* __restrict__ cb = od.cand_base;
+    pre_base = cb[level];
+    pre_ncand = cb[level + 1] - pre_base;
+    const int c0 = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
+    if (c0 < pre_ncand) pre_cand = od.cand[pre_base + c0];
+  }
   pdl_wait();
   if (solve && od.gn->break_level == level) return;  // rgbOnly `break`: rest of the level is skipped
   __shared__ float sred[32 * (IT1_THREADS / 32)];
-  iter1_body<IT1_THREADS>(od, level, do_res, do_icp, blockIdx.x, gridDim.x, sred, pre);
+  iter1_body<IT1_THREADS>(od, level, do_res, do_icp, blockIdx.x, gridDim.x, sred, pre, pre_cand_have, pre_base, pre_ncand, pre_cand);
 }
 
 // ---- photometric row: RGBReduction::getProducts (reduce.cu:419-480); the cloud point is recomputed from the gathered
@@ -745,7 +760,7 @@ struct Iter2Shared {
 // the dense-pass partials and the photometric rows over its candidates. Returns the rgbOnly `break` decision.
 template <int THREADS>
 __device__ __forceinline__ bool iter2_rows(const OdomDev& od, Iter2Shared& sh, int level, int iter, int next_level, int nblocks1, int mode,
-                                           float sigma_override, int vb, int nvb) {
+                                           float sigma_override, int vb, int nvb, int pre_have = 0, int pre_base = 0, int pre_ncand = 0) {
   GnScratch& S = sh.S;
   GNState* gn = od.gn;
   const bool do_rgb = mode & 1, do_icp = mode & 2, solve = mode & 4, have_res = mode & 8;
@@ -754,8 +769,9 @@ __device__ __forceinline__ bool iter2_rows(const OdomDev& od, Iter2Shared& sh, i
   EF_STAMP(gn, 8, stamp && vb == 0);
 
   // issue the loads that do not depend on sigma first: this CTA's candidate terms and its share of the dense partials
-  const int base = gn->cand_base[level], ncand = do_rgb ? gn->cand_base[level + 1] - base : 0;
-  const int4* terms = od.terms + base;  // (not __restrict__: k_gn_loop writes them in its first phase)
+  const int base = pre_have ? pre_base : gn->cand_base[level];
+  const int ncand = do_rgb ? (pre_have ? pre_ncand : gn->cand_base[level + 1] - base) : 0;
+  const int4* terms = od.terms + base;
   const int c0 = (wid * nvb + vb) * 32 + lane, cstride = nvb * THREADS;
   int4 t0 = make_int4(-1, 0, 0, 0);
   if (c0 < ncand) t0 = terms[c0];
@@ -867,18 +883,21 @@ __device__ __forceinline__ void iter2_final(const OdomDev& od, Iter2Shared& sh, 
     const int v = lane, sl = wid;
     double a0 = 0, a1 = 0;
     constexpr int SL = THREADS / 32;
-    for (int bb = sl; bb < nvb; bb += 8 * SL) {  // 16 independent loads in flight per thread
-      double x[8];
-      float y[8];
+    // every row of this thread's slice in ONE batch of independent loads (<= 160 CTA rows / 8 slices = 20 x 2 loads): the sums
+    // wait for one L2 round trip instead of three (2.7 -> ~1 us of the serial tail of every iteration)
+    constexpr int UN = (MAX_RGB_BLOCKS + SL - 1) / SL;
+    for (int bb = sl; bb < nvb; bb += UN * SL) {
+      double x[UN];
+      float y[UN];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < UN; ++k) {
         const int b = bb + k * SL;
         const bool in = b < nvb;
         x[k] = (in && do_icp) ? od.partials2[b * 32 + v] : 0.0;
         y[k] = (in && do_rgb) ? od.partials_rgb[b * 32 + v] : 0.f;
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < UN; ++k) {
         a0 += x[k];
         a1 += (double)y[k];
       }
@@ -910,8 +929,17 @@ __device__ __forceinline__ void iter2_final(const OdomDev& od, Iter2Shared& sh, 
 // photometric rows over the candidate terms are reduced; the CTA that takes the last ticket sums all partials in double
 // and its first warp solves and updates the pose. mode bits: 1 = rgb rows, 2 = icp partials present, 4 = solve,
 // 8 = correspondence statistics present, 16 = use sigma_override.
+// 32 = the candidate bounds are final (the launch is part of the tracking loop, behind its fence): read them before the wait.
 __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, int iter, int next_level, int nblocks1, int mode, float sigma_override) {
-  pdl_enter();
+  pdl_launch();
+  int pre_base = 0, pre_ncand = 0;
+  const int pre_have = (mode & 32) ? 1 : 0;
+  if (pre_have) {
+    const int* __restrict__ cb = od.cand_base;
+    pre_base = cb[level];
+    pre_ncand = cb[level + 1] - pre_base;
+  }
+  pdl_wait();
   __shared__ Iter2Shared sh;
   GNState* gn = od.gn;
   if ((mode & 4) && gn->break_level == level) {
@@ -919,7 +947,7 @@ __global__ void __launch_bounds__(IT2_THREADS) k_iter2(OdomDev od, int level, in
     if (blockIdx.x == 0 && threadIdx.x == 0 && next_level >= 0 && next_level != level) gn_prepare_warp(gn, next_level);
     return;
   }
-  const bool brk = iter2_rows<IT2_THREADS>(od, sh, level, iter, next_level, nblocks1, mode, sigma_override, blockIdx.x, gridDim.x);
+  const bool brk = iter2_rows<IT2_THREADS>(od, sh, level, iter, next_level, nblocks1, mode, sigma_override, blockIdx.x, gridDim.x, pre_have, pre_base, pre_ncand);
   // every CTA takes a ticket (also on `break`, so the accumulators of k_iter1 get re-armed exactly once)
   if (!last_block_done(od.counter)) return;
   iter2_final<IT2_THREADS>(od, sh, level, iter, next_level, mode, gridDim.x, brk);
@@ -1568,7 +1596,7 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
     const int nb1 = red_blocks(ctx, npx, 4, IT1_THREADS, IT1_CTAS_PER_SM);
     EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, lv, rgb ? 1 : 0, icp ? 1 : 0, 1, prefetch);
     const int nb2 = iter2_blocks(ctx, npx, rgb, icp ? nb1 : 0);
-    EF_LAUNCH(ctx, k_iter2, nb2, IT2_THREADS, 0, od, lv, sched_iter[s], next_lv, nb1, (rgb ? 1 | 8 : 0) | (icp ? 2 : 0) | 4, 0.f);
+    EF_LAUNCH(ctx, k_iter2, nb2, IT2_THREADS, 0, od, lv, sched_iter[s], next_lv, nb1, (rgb ? 1 | 8 : 0) | (icp ? 2 : 0) | 4 | (prefetch ? 32 : 0), 0.f);
   }
   ef_stage(ctx, 5);
   if (so3)

@@ -529,6 +529,7 @@ int launch_sobel(EfContext* ctx, int which) {
   int rc = run_scan(ctx, flags, &od.gn->flat_n, nullptr, flat, offsets, &od.gn->cand_base[NUM_PYRS]);
   if (rc) return rc;
   EF_LAUNCH(ctx, k_cand_scatter, flat_blocks(ctx, flat), 256, 0, a, (const uint8_t*)flags, (const int*)offsets, od.cand, od.gn);
+  ctx->maps_dirty[which] = true;  // k_iter1 / k_iter2 read the list ahead of their dependency wait: fence before the next one
   EF_CHECK_LAST();
   return 0;
 }

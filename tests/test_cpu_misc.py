@@ -280,10 +280,12 @@ def test_every_kernel_waits_on_its_predecessor():
                 continue  # declaration
             body = re.sub(r"//[^\n]*\n|/\*.*?\*/", "", src[k + 1:k + 2600], flags=re.S).lstrip()  # comments may precede it
             head = src[m.start():m.start() + 200]
-            if body.startswith("pdl_launch();") and "k_iter1(" in head:
-                # the one kernel with a prologue ahead of its wait (live-map prefetch); the wait must precede the first read of
-                # anything the Gauss-Newton loop writes (the device state block od.gn)
-                assert "pdl_wait();" in body and body.index("pdl_wait();") < body.index("od.gn"), "k_iter1 reads state before its wait"
+            if body.startswith("pdl_launch();") and ("k_iter1(" in head or "k_iter2(" in head):
+                # the two kernels with a prologue ahead of their wait (live maps / candidate list, final before the loop starts); the
+                # wait must precede the first read of anything the Gauss-Newton loop writes (the device state block od.gn, the
+                # per-iteration terms, the partials)
+                pre = body[:body.index("pdl_wait();")]
+                assert "od.gn" not in pre and "od.terms" not in pre and "od.partials" not in pre, "reads loop state before its wait"
             else:
                 assert body.startswith("pdl_enter();"), (os.path.basename(path), head.split("\n")[0])
             n += 1

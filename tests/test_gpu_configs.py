@@ -57,8 +57,9 @@ def test_icl_nuim_intrinsics(K):
         m_p, m_o = ctx.map_download(), f.map()
         n = min(len(m_p), len(m_o))  # (a handful of borderline new surfels may differ; the run_both count check bounds it)
         k = int(0.9 * n)             # the order-preserving prefix that cannot have shifted
-        # six frames of fusion: a surfel whose association flipped once (acos / exp one ulp apart) differs from then on
-        assert np.isclose(m_p[:k], m_o[:k], rtol=1e-4, atol=1e-5, equal_nan=True).all(axis=1).mean() > 0.99
+        # six frames of fusion: a surfel whose association flipped once (acos / exp one ulp apart) differs from then on; every
+        # fused position carries the frame poses' difference (held to 2e-5 above), hence the absolute term
+        assert np.isclose(m_p[:k], m_o[:k], rtol=1e-4, atol=5e-5, equal_nan=True).all(axis=1).mean() > 0.99
         assert np.isclose(m_p[:k, :3], m_o[:k, :3], rtol=0, atol=2e-3).all(axis=1).mean() > 0.995
     finally:
         ctx.close()
