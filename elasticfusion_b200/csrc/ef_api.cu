@@ -315,6 +315,8 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
     // cluster size (16 default, 8, or 0 = off), EF_GN_CLUSTER_LEVELS = how many levels from the top of the pyramid (default 1: the 160x120
     // level; measured 313 / 322 / 446 us for the whole loop with 1 / 2 / 3 levels against 338 without -- 16 SMs are too few for the
     // dense pass of the finer levels)
+    e = getenv("EF_FUSED_MODEL");
+    ctx->fused_model_side = !(e && e[0] == '0');
     e = getenv("EF_GN_CLUSTER");
     ctx->gn_cluster = odom_cluster_size(e ? atoi(e) : 16);
     e = getenv("EF_GN_CLUSTER_LEVELS");

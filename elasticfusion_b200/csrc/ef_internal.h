@@ -212,6 +212,7 @@ struct EfContext {
   bool pdl;  // programmatic dependent launch on every kernel (default on; EF_NO_PDL=1 disables)
   bool it1_prefetch;   // k_iter1 loads its first round of live-map pixels before griddepcontrol.wait (EF_IT1_PREFETCH=0 disables)
   int it2_max_blocks;  // cap on k_iter2's grid (EF_IT2_MAXBLOCKS; default MAX_RGB_BLOCKS)
+  bool fused_model_side;  // model pyramids of a frame in 3 launches (k_model_level0 / _down) instead of 6; EF_FUSED_MODEL=0 disables
   int gn_cluster;         // CTAs of the cluster that runs the coarse-level Gauss-Newton iterations (0: two-kernel path everywhere)
   int gn_cluster_levels;  // pyramid levels, from the coarsest, whose iterations run in that cluster
   bool plain_next;     // the next ef_launch omits the programmatic-serialisation attribute (EF_PLAIN_NEXT)

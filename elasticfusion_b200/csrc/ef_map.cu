@@ -805,7 +805,9 @@ struct CcShared {
 constexpr int CC_WORDS = CC_ITEMS * (CC_THREADS / 32);  // keep-mask words per tile, in (item slab k, warp) order
 
 // ctl[0] tile dispenser, ctl[1] exit tickets, ctl[2] first tile that moves (0xffffffff: none)
-__global__ void __launch_bounds__(CC_THREADS, 4) k_clean_flags(CleanArgs a, const MapPose* __restrict__ mp, const float4* __restrict__ pos_conf,
+constexpr int CF_THREADS = CC_TILE;  // one surfel per thread: the window test is a chain of ~5 dependent gathers, so two surfels per
+                                     // thread would double the latency of a small map's pass (27 -> 14 us at 270 k surfels)
+__global__ void __launch_bounds__(CF_THREADS, 2) k_clean_flags(CleanArgs a, const MapPose* __restrict__ mp, const float4* __restrict__ pos_conf,
                                                                const float4* __restrict__ color_time, const float4* __restrict__ norm_rad,
                                                                const int* __restrict__ count, const float4* __restrict__ new_pos,
                                                                const float4* __restrict__ new_col, const float4* __restrict__ new_nr,
@@ -820,22 +822,19 @@ __global__ void __launch_bounds__(CC_THREADS, 4) k_clean_flags(CleanArgs a, cons
     const int n_in = min(CC_TILE, total - g0);
     // a tile moves when it holds new surfels (they have to be appended), lost one of its own, or a graph deforms the map
     bool moves = (g0 + n_in > n_old) || a.n_nodes > 0;
-    // item index k * CC_THREADS + tid: coalesced, and (k, warp, lane) = map order for the ballots
-#pragma unroll
-    for (int k = 0; k < CC_ITEMS; ++k) {
-      const int idx = k * CC_THREADS + tid, g = g0 + idx;
-      bool keep = false;
-      if (idx < n_in) {
-        const bool is_old = g < n_old;
-        const float4 pos = is_old ? pos_conf[g] : new_pos[g - n_old];
-        float4 col = is_old ? color_time[g] : new_col[g - n_old];
-        keep = clean_test(a, mp, pos, col, is_old ? norm_rad + g : new_nr + (g - n_old));
-      }
-      const unsigned int ballot = __ballot_sync(0xffffffffu, keep);
-      const unsigned int valid = __ballot_sync(0xffffffffu, idx < n_in);
-      if (lane == 0) keep_mask[(size_t)t * CC_WORDS + k * (CC_THREADS / 32) + wid] = ballot;
-      moves = moves || ballot != valid;
+    // thread = item of the tile: warp w holds items 32 w .. 32 w + 31, i.e. keep-mask word w in k_clean_move's (slab, warp) order
+    const int g = g0 + tid;
+    bool keep = false;
+    if (tid < n_in) {
+      const bool is_old = g < n_old;
+      const float4 pos = is_old ? pos_conf[g] : new_pos[g - n_old];
+      float4 col = is_old ? color_time[g] : new_col[g - n_old];
+      keep = clean_test(a, mp, pos, col, is_old ? norm_rad + g : new_nr + (g - n_old));
     }
+    const unsigned int ballot = __ballot_sync(0xffffffffu, keep);
+    const unsigned int valid = __ballot_sync(0xffffffffu, tid < n_in);
+    if (lane == 0) keep_mask[(size_t)t * CC_WORDS + wid] = ballot;
+    moves = moves || ballot != valid;
     if (moves && lane == 0) atomicMin(ctl + 2, (unsigned int)t);
   }
 }
@@ -1518,7 +1517,10 @@ int map_clean_async(EfContext* ctx, int time, float conf_threshold, int time_del
   size_t nb = (size_t)ctx->num_sms * 4;
   if (nb > tiles) nb = tiles;
   if (nb < 1) nb = 1;
-  EF_LAUNCH(ctx, k_clean_flags, (int)nb, CC_THREADS, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos, m.new_col, m.new_nr,
+  size_t nbf = (size_t)ctx->num_sms * 2;
+  if (nbf > tiles) nbf = tiles;
+  if (nbf < 1) nbf = 1;
+  EF_LAUNCH(ctx, k_clean_flags, (int)nbf, CF_THREADS, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos, m.new_col, m.new_nr,
             m.new_count, m.keep_mask, m.clean_ctl);
   if (n_nodes > 0)
     EF_LAUNCH(ctx, k_clean_move<true>, (int)nb, CC_THREADS, sizeof(CcShared), a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.new_pos,

@@ -319,6 +319,85 @@ __global__ void k_pyr_down_depth_image(const float* __restrict__ d0, float* __re
   }
 }
 
+// The model side of a frame (frameToModel.initICPModel + initRGBModel, ElasticFusion.cpp:302-322) in three launches instead of six:
+// level 0 = k_copy_maps + k_depth_intensity_l0 in one pass over the predicted textures (the depth IS the vertex z just loaded);
+// each coarser level = k_resize_maps + k_pyr_down_depth_image for the same output pixel. Same arithmetic, same outputs; the
+// separate kernels remain for the stage API and the trackers that initialise only one half.
+__global__ void k_model_level0(const float4* __restrict__ vtxA, const float4* __restrict__ nrmA, const float4* __restrict__ vtxB,
+                               const float4* __restrict__ nrmB, const uchar4* __restrict__ rgbaA, const uchar4* __restrict__ rgbaB,
+                               const int* __restrict__ dense_flag, int forceB_rgb, int rows, int cols, float cutoff, float4* __restrict__ vmaps_tmp,
+                               float* __restrict__ vmap, float* __restrict__ nmap, float* __restrict__ depth, uint8_t* __restrict__ image) {
+  pdl_enter();
+  const size_t n = (size_t)rows * cols;
+  const bool useB = dense_flag && (*dense_flag == 0);
+  const float4* __restrict__ vtx = useB ? vtxB : vtxA;
+  const float4* __restrict__ nrm = useB ? nrmB : nrmA;
+  const uchar4* __restrict__ rgba = (forceB_rgb || useB) ? rgbaB : rgbaA;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+    const float4 vs = vtx[p];
+    const float4 ns = nrm[p];
+    const uchar4 s = rgba[p];
+    vmaps_tmp[p] = vs;
+    f3 vd = mk3(qnan(), qnan(), qnan()), nd = vd;
+    if (!(vs.z == 0)) {
+      vd = mk3(vs.x, vs.y, vs.z);
+      nd = mk3(ns.x, ns.y, ns.z);
+    }
+    vmap[p] = vd.x;
+    vmap[p + n] = vd.y;
+    vmap[p + 2 * n] = vd.z;
+    nmap[p] = nd.x;
+    nmap[p + n] = nd.y;
+    nmap[p + 2 * n] = nd.z;
+    depth[p] = (vs.z > cutoff || vs.z <= 0) ? qnan() : vs.z;
+    image[p] = (uint8_t)__float2int_rz((float)s.x * 0.114f + (float)s.y * 0.299f + (float)s.z * 0.587f);
+  }
+}
+
+__global__ void k_model_level_down(const float* __restrict__ vin, const float* __restrict__ nin, const float* __restrict__ d0,
+                                   const uint8_t* __restrict__ i0, int srows, int scols, float* __restrict__ vout, float* __restrict__ nout,
+                                   float* __restrict__ d1, uint8_t* __restrict__ i1) {
+  pdl_enter();
+  const int drows = srows / 2, dcols = scols / 2;
+  const size_t splane = (size_t)srows * scols, dplane = (size_t)drows * dcols;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < drows * dcols; t += gridDim.x * blockDim.x) {
+    const int y = t / dcols, x = t - y * dcols;
+    const int xs = x * 2, ys = y * 2;
+    const size_t q = (size_t)t;
+    // resizeVMap + resizeNMap (cudafuncs.cu:413-490): 2x2 box average, any NaN -> NaN, normals renormalised
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const float* in = which ? nin : vin;
+      float* out = which ? nout : vout;
+      const float x00 = in[(size_t)(ys + 0) * scols + xs + 0], x01 = in[(size_t)(ys + 0) * scols + xs + 1];
+      const float x10 = in[(size_t)(ys + 1) * scols + xs + 0], x11 = in[(size_t)(ys + 1) * scols + xs + 1];
+      if (isnan(x00) || isnan(x01) || isnan(x10) || isnan(x11)) {
+        out[q] = qnan();
+        out[q + dplane] = qnan();
+        out[q + 2 * dplane] = qnan();
+        continue;
+      }
+      f3 n;
+      n.x = (x00 + x01 + x10 + x11) / 4;
+      const float* iy = in + splane;
+      n.y = (iy[(size_t)(ys + 0) * scols + xs + 0] + iy[(size_t)(ys + 0) * scols + xs + 1] + iy[(size_t)(ys + 1) * scols + xs + 0] +
+             iy[(size_t)(ys + 1) * scols + xs + 1]) / 4;
+      const float* iz = in + 2 * splane;
+      n.z = (iz[(size_t)(ys + 0) * scols + xs + 0] + iz[(size_t)(ys + 0) * scols + xs + 1] + iz[(size_t)(ys + 1) * scols + xs + 0] +
+             iz[(size_t)(ys + 1) * scols + xs + 1]) / 4;
+      if (which) n = normalized(n);
+      out[q] = n.x;
+      out[q + dplane] = n.y;
+      out[q + 2 * dplane] = n.z;
+    }
+    // pyrDownGaussF + pyrDownUcharGauss for the same output pixel
+    auto f0 = [&](int yy, int xx) { return d0[(size_t)yy * scols + xx]; };
+    d1[t] = pyr_down_f_at(f0, srows, scols, x, y);
+    auto g0 = [&](int yy, int xx) { return (int)i0[(size_t)yy * scols + xx]; };
+    i1[t] = pyr_down_u8_at(g0, srows, scols, x, y);
+  }
+}
+
 // computeDerivativeImages / applyKernel (cudafuncs.cu:612-668) for all three levels in one launch, fused with the
 // pose-independent gates of computeRgbResidual (reduce.cu:641-660): a pixel is a photometric *candidate* when
 // j < cols-5, i < rows-1, its 4x4 neighbourhood of the live image is non-zero, its gradient magnitude passes minScale and
@@ -500,6 +579,19 @@ int odom_populate(EfContext* ctx, int which, const uint8_t* rgba, float** destDe
 int map_select_model_inputs(EfContext* ctx, const float**, const float**, const uint8_t**) {
   OdomDev& od = ctx->odom[0];
   Textures& t = ctx->tex;
+  if (ctx->fused_model_side) {
+    const size_t n = (size_t)od.width * od.height;
+    EF_LAUNCH(ctx, k_model_level0, flat_blocks(ctx, n), 256, 0, (const float4*)t.vertex, (const float4*)t.normal, (const float4*)t.fill_vertex,
+              (const float4*)t.fill_normal, (const uchar4*)t.image, (const uchar4*)t.fill_image, (const int*)ctx->map.dense_flag,
+              ctx->frame_to_frame_rgb ? 1 : 0, od.height, od.width, od.maxDepthRGB, (float4*)od.vmaps_tmp, od.vmap_c_prev[0], od.nmap_c_prev[0],
+              od.lastDepth[0], od.lastImage[0]);
+    for (int i = 0; i + 1 < NUM_PYRS; ++i)
+      EF_LAUNCH(ctx, k_model_level_down, flat_blocks(ctx, (size_t)od.rows[i + 1] * od.cols[i + 1] * 2), 128, 0, (const float*)od.vmap_c_prev[i],
+                (const float*)od.nmap_c_prev[i], (const float*)od.lastDepth[i], (const uint8_t*)od.lastImage[i], od.rows[i], od.cols[i],
+                od.vmap_c_prev[i + 1], od.nmap_c_prev[i + 1], od.lastDepth[i + 1], od.lastImage[i + 1]);
+    EF_CHECK_LAST();
+    return 0;
+  }
   int rc = odom_init_icp_model(ctx, 0, (const float*)t.vertex, (const float*)t.normal, (const float*)t.fill_vertex, (const float*)t.fill_normal,
                                ctx->map.dense_flag, false);
   if (rc) return rc;
