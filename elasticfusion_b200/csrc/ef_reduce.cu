@@ -124,8 +124,10 @@ __device__ void gn_begin_body(GNState* gn, int rgbOnly, float icpWeight, int so3
 // possibly on the look-ahead stream) into the tracker's trace (a few hundred words: one or two per thread, so the copy is
 // one memory round trip instead of a serial chain).
 constexpr int GN_BEGIN_THREADS = 256;
+__device__ void gn_seed_body(GNState* gn, int first_level, const So3State* s);
+// first_level >= 0: thread 0 also seeds the SE(3) loop (resultRt, first warp matrices): one launch instead of two.
 __global__ void __launch_bounds__(GN_BEGIN_THREADS) k_gn_begin(GNState* gn, int rgbOnly, float icpWeight, int so3, const So3State* s,
-                                                               EfSolveTrace* trace) {
+                                                               EfSolveTrace* trace, int first_level) {
   pdl_enter();
   if (blockIdx.x != 0) return;
   if (threadIdx.x == 0) {
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(GN_BEGIN_THREADS) k_gn_begin(GNState* gn, int 
       gn->lastSO3Count = s->lastSO3Count;
       gn->trace_n = trace ? s->trace_n : 0;
     }
+    if (first_level >= 0) gn_seed_body(gn, first_level, s);
   }
   if (so3 && trace) {
     const int words = s->trace_n * (int)(sizeof(EfSolveTrace) / 4);
@@ -160,12 +163,6 @@ __device__ void gn_seed_body(GNState* gn, int first_level, const So3State* s) {
   }
   gn_prepare_warp(gn, first_level);
 }
-__global__ void k_gn_seed(GNState* gn, int first_level, const So3State* s) {
-  pdl_enter();
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  gn_seed_body(gn, first_level, s);
-}
-
 // end of getIncrementalTransformation (RGBDOdometry.cpp:555-570) + velocity weighting (ElasticFusion.cpp:369-383)
 __global__ void k_gn_finish(GNState* gn, float weightMultiplier, int have_track, MapPose* map_pose) {
   pdl_enter();
@@ -1025,7 +1022,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) k_gn_cluster(OdomDev od, GnSche
   const int rank = (int)cluster_rank(), C = (int)cluster_size();
   GcShared* lead = cluster_map(&sh, 0u);
 
-  // parameters of the first iteration (k_gn_begin / k_gn_seed or the previous launch left them in the global state)
+  // parameters of the first iteration (k_gn_begin or the previous launch left them in the global state)
   if (tid < 9) {
     sh.Pl.Mcp[tid] = gn->Mcp[tid];
     sh.Pl.krkinv[tid] = gn->krkinv[tid];
@@ -1573,10 +1570,10 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
   // has completed, so k_iter1 may read the live maps ahead of its dependency wait (see k_iter1).
   const int prefetch = ctx->it1_prefetch ? 1 : 0;
   if (prefetch) EF_PLAIN_NEXT(ctx);
-  EF_LAUNCH(ctx, k_gn_begin, 1, GN_BEGIN_THREADS, 0, od.gn, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0, (const So3State*)od.so3s, od.trace);
+  EF_LAUNCH(ctx, k_gn_begin, 1, GN_BEGIN_THREADS, 0, od.gn, rgbOnly ? 1 : 0, icpWeight, so3 ? 1 : 0, (const So3State*)od.so3s, od.trace,
+            ns ? sched_level[0] : 0);
   ctx->maps_dirty[which] = false;
   ef_stage(ctx, 4);
-  EF_LAUNCH(ctx, k_gn_seed, 1, 32, 0, od.gn, ns ? sched_level[0] : 0, (const So3State*)od.so3s);
   // the coarse levels (ctx->gn_cluster_levels of them, from the top of the pyramid) run inside one cluster launch
   int s0 = 0;
   if (ctx->gn_cluster > 0 && ns > 0) {
