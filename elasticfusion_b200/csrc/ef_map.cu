@@ -1398,6 +1398,23 @@ int run_scan(EfContext* ctx, const uint8_t* flags, const int* n_a, const int* n_
   return 0;
 }
 
+// epoch / tile states / dispenser of the shared look-back machinery for a scan that is fused into another kernel
+int scan_begin(EfContext* ctx, size_t max_items, int tile_items, unsigned long long** state, unsigned int** counter, unsigned int* epoch, int* blocks) {
+  MapDev& m = ctx->map;
+  MapBuffers& B = mb(ctx);
+  const size_t tiles = (max_items + tile_items - 1) / tile_items + 1;
+  if (++B.scan_epoch >= (1u << 30)) {
+    CU(cudaMemsetAsync(m.scan_tile_state, 0, B.scan_state_bytes, ctx->stream));
+    B.scan_epoch = 1;
+  }
+  const size_t nb = tiles < (size_t)ctx->num_sms * 4 ? tiles : (size_t)ctx->num_sms * 4;
+  *state = (unsigned long long*)m.scan_tile_state;
+  *counter = m.scan_counter;
+  *epoch = B.scan_epoch;
+  *blocks = (int)nb;
+  return 0;
+}
+
 // T == nullptr: use the tracker's device-resident pose
 int map_update_pose_async(EfContext* ctx, const double* T_host) {
   const double* src = ctx->odom[0].gn->T_wc;
