@@ -517,6 +517,46 @@ __device__ __forceinline__ void fuse_measurement(const FuseArgs& a, const MapPos
   nr = make_float4(ng.x, ng.y, ng.z, get_radius(vPos_f.z, vNormLocal.z, ifx, ify));
 }
 
+// one associated pixel q of the quarter grid: a new surfel goes to new_*[k_new]; the pixel that owns a matched surfel's winner slot
+// fuses its measurement into it (update.vert:49-84)
+__device__ __forceinline__ void fuse_update_item(const FuseArgs& a, const MapPose* __restrict__ mp, float weighting, int cnt, const Quarter& Q, int q,
+                                                 uint32_t as, int k_new, uint32_t* __restrict__ pending, float4* __restrict__ pos_conf,
+                                                 float4* __restrict__ color_time, float4* __restrict__ norm_rad, float4* __restrict__ new_pos,
+                                                 float4* __restrict__ new_col, float4* __restrict__ new_nr) {
+  const int i = 2 * (q / Q.nj) + Q.p, j = 2 * (q % Q.nj) + Q.p;
+  const uint32_t d = (uint32_t)i * a.rows + j;
+  float4 mpos, mcol, mnr;
+  if (as == ASSOC_NEW) {
+    fuse_measurement(a, mp, weighting, i, j, mpos, mcol, mnr);
+    mcol.w = -2.f;
+    new_pos[k_new] = mpos;
+    new_col[k_new] = mcol;
+    new_nr[k_new] = mnr;
+    return;
+  }
+  if ((int)as >= cnt || pending[as] != d) return;
+  pending[as] = 0xffffffffu;  // re-arm the slot: exactly one pixel owns it
+  fuse_measurement(a, mp, weighting, i, j, mpos, mcol, mnr);
+  const float4 s_pos = pos_conf[as], s_col = color_time[as], s_nr = norm_rad[as];
+  const float c_k = s_pos.w, aw = mpos.w;
+  if (mnr.w < (1.0f + 0.5f) * s_nr.w) {
+    const float ck_a = c_k + aw;
+    pos_conf[as] = make_float4(((c_k * s_pos.x) + (aw * mpos.x)) / ck_a, ((c_k * s_pos.y) + (aw * mpos.y)) / ck_a,
+                               ((c_k * s_pos.z) + (aw * mpos.z)) / ck_a, ck_a);
+    const f3 oldCol = decode_color(s_col.x), newCol = decode_color(mcol.x);
+    const f3 avg = mk3(((c_k * oldCol.x) + (aw * newCol.x)) / ck_a, ((c_k * oldCol.y) + (aw * newCol.y)) / ck_a,
+                       ((c_k * oldCol.z) + (aw * newCol.z)) / ck_a);
+    color_time[as] = make_float4(encode_color(avg), s_col.y, s_col.z, (float)a.time);
+    f3 nn = mk3(((c_k * s_nr.x) + (aw * mnr.x)) / ck_a, ((c_k * s_nr.y) + (aw * mnr.y)) / ck_a, ((c_k * s_nr.z) + (aw * mnr.z)) / ck_a);
+    const float rr = ((c_k * s_nr.w) + (aw * mnr.w)) / ck_a;
+    nn = normalized(nn);
+    norm_rad[as] = make_float4(nn.x, nn.y, nn.z, rr);
+  } else {
+    pos_conf[as] = make_float4(s_pos.x, s_pos.y, s_pos.z, c_k + aw);
+    color_time[as] = make_float4(s_col.x, s_col.y, s_col.z, (float)a.time);
+  }
+}
+
 __global__ void k_fuse_update(FuseArgs a, const MapPose* __restrict__ mp, const GNState* __restrict__ gn, const int* __restrict__ count,
                               const uint32_t* __restrict__ assoc, uint32_t* __restrict__ pending, const int* __restrict__ new_off,
                               const int* __restrict__ new_total, float4* __restrict__ pos_conf, float4* __restrict__ color_time,
@@ -531,40 +571,102 @@ __global__ void k_fuse_update(FuseArgs a, const MapPose* __restrict__ mp, const 
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
     const uint32_t as = assoc[q];
     if (as == ASSOC_NONE) continue;
-    const int i = 2 * (q / Q.nj) + Q.p, j = 2 * (q % Q.nj) + Q.p;
-    const uint32_t d = (uint32_t)i * a.rows + j;
-    float4 mpos, mcol, mnr;
-    if (as == ASSOC_NEW) {
-      fuse_measurement(a, mp, weighting, i, j, mpos, mcol, mnr);
-      mcol.w = -2.f;
-      const int k = new_off[q];
-      new_pos[k] = mpos;
-      new_col[k] = mcol;
-      new_nr[k] = mnr;
-      continue;
+    fuse_update_item(a, mp, weighting, cnt, Q, q, as, as == ASSOC_NEW ? new_off[q] : 0, pending, pos_conf, color_time, norm_rad, new_pos, new_col, new_nr);
+  }
+}
+
+// k_fuse_update with the ordered numbering of the new surfels (the transform-feedback order of data.vert's draw) computed in the
+// same launch: single-pass decoupled look-back over tiles of 512 quarter-grid pixels, protocol of k_scan_flags. Replaces
+// k_set_int + k_scan_flags + k_fuse_update.
+constexpr int FU_THREADS = 256, FU_ITEMS = 2, FU_TILE = FU_THREADS * FU_ITEMS;  // (2 pixels per thread: the per-pixel work is a chain of loads)
+constexpr int FU_NCNT = FU_ITEMS * (FU_THREADS / 32);
+__global__ void __launch_bounds__(FU_THREADS) k_fuse_update_compact(FuseArgs a, const MapPose* __restrict__ mp, const GNState* __restrict__ gn,
+                                                                    const int* __restrict__ count, const uint32_t* __restrict__ assoc,
+                                                                    uint32_t* __restrict__ pending, float4* __restrict__ pos_conf,
+                                                                    float4* __restrict__ color_time, float4* __restrict__ norm_rad,
+                                                                    float4* __restrict__ new_pos, float4* __restrict__ new_col,
+                                                                    float4* __restrict__ new_nr, int* __restrict__ new_count,
+                                                                    unsigned long long* state, unsigned int* counter, unsigned int epoch) {
+  pdl_enter();
+  const Quarter Q = quarter_of(a.time, a.rows, a.cols);
+  const int nq = Q.ni * Q.nj;
+  const int cnt = *count;
+  const float weighting = gn->weighting;
+  const unsigned long long tag = (unsigned long long)epoch << 34;
+  const int num_tiles = (nq + FU_TILE - 1) / FU_TILE;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  __shared__ int s_cnt[FU_ITEMS * (FU_THREADS / 32)], s_excl[FU_ITEMS * (FU_THREADS / 32)];
+  __shared__ int s_tile, s_prefix;
+  while (true) {
+    if (tid == 0) s_tile = (int)atomicAdd(counter, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= num_tiles) {
+      if (tid == 0 && atomicAdd(counter + 1, 1u) == gridDim.x - 1) {
+        counter[0] = 0u;
+        counter[1] = 0u;
+      }
+      return;
     }
-    if ((int)as >= cnt || pending[as] != d) continue;
-    pending[as] = 0xffffffffu;  // re-arm the slot: exactly one pixel owns it
-    fuse_measurement(a, mp, weighting, i, j, mpos, mcol, mnr);
-    // update.vert:49-84
-    const float4 s_pos = pos_conf[as], s_col = color_time[as], s_nr = norm_rad[as];
-    const float c_k = s_pos.w, aw = mpos.w;
-    if (mnr.w < (1.0f + 0.5f) * s_nr.w) {
-      const float ck_a = c_k + aw;
-      pos_conf[as] = make_float4(((c_k * s_pos.x) + (aw * mpos.x)) / ck_a, ((c_k * s_pos.y) + (aw * mpos.y)) / ck_a,
-                                 ((c_k * s_pos.z) + (aw * mpos.z)) / ck_a, ck_a);
-      const f3 oldCol = decode_color(s_col.x), newCol = decode_color(mcol.x);
-      const f3 avg = mk3(((c_k * oldCol.x) + (aw * newCol.x)) / ck_a, ((c_k * oldCol.y) + (aw * newCol.y)) / ck_a,
-                         ((c_k * oldCol.z) + (aw * newCol.z)) / ck_a);
-      color_time[as] = make_float4(encode_color(avg), s_col.y, s_col.z, (float)a.time);
-      f3 nn = mk3(((c_k * s_nr.x) + (aw * mnr.x)) / ck_a, ((c_k * s_nr.y) + (aw * mnr.y)) / ck_a, ((c_k * s_nr.z) + (aw * mnr.z)) / ck_a);
-      const float rr = ((c_k * s_nr.w) + (aw * mnr.w)) / ck_a;
-      nn = normalized(nn);
-      norm_rad[as] = make_float4(nn.x, nn.y, nn.z, rr);
-    } else {
-      pos_conf[as] = make_float4(s_pos.x, s_pos.y, s_pos.z, c_k + aw);
-      color_time[as] = make_float4(s_col.x, s_col.y, s_col.z, (float)a.time);
+    uint32_t as[FU_ITEMS];
+    unsigned int ballots[FU_ITEMS];
+#pragma unroll
+    for (int k = 0; k < FU_ITEMS; ++k) {
+      const int q = tile * FU_TILE + k * FU_THREADS + tid;
+      as[k] = (q < nq) ? assoc[q] : ASSOC_NONE;
+      ballots[k] = __ballot_sync(0xffffffffu, as[k] == ASSOC_NEW);
+      if (lane == 0) s_cnt[k * (FU_THREADS / 32) + wid] = __popc(ballots[k]);
     }
+    __syncthreads();
+    if (wid == 0) {
+      static_assert(FU_NCNT <= 32, "one count per lane");
+      const int c = (lane < FU_NCNT) ? s_cnt[lane] : 0;
+      int incl = c;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+      }
+      if (lane < FU_NCNT) s_excl[lane] = incl - c;
+      const int aggregate = __shfl_sync(0xffffffffu, incl, 31);
+      volatile unsigned long long* vstate = state;
+      int prefix = 0;
+      if (tile == 0) {
+        if (lane == 0) vstate[0] = tag | (2ull << 32) | (unsigned int)aggregate;
+      } else {
+        if (lane == 0) vstate[tile] = tag | (1ull << 32) | (unsigned int)aggregate;
+        int look = tile - 1;
+        while (true) {
+          const int idx = look - lane;
+          const unsigned long long w = (idx >= 0) ? vstate[idx] : (tag | (2ull << 32));
+          const unsigned int st = ((w >> 34) == (unsigned long long)epoch) ? ((unsigned int)(w >> 32) & 3u) : 0u;
+          if (__any_sync(0xffffffffu, st == 0)) continue;
+          const unsigned int m2 = __ballot_sync(0xffffffffu, st == 2);
+          const int first2 = m2 ? (__ffs(m2) - 1) : 32;
+          int val = (lane <= first2) ? (int)(unsigned int)(w & 0xffffffffull) : 0;
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
+          prefix += val;
+          if (m2) break;
+          look -= 32;
+        }
+        if (lane == 0) vstate[tile] = tag | (2ull << 32) | (unsigned int)(prefix + aggregate);
+      }
+      if (lane == 0) {
+        s_prefix = prefix;
+        if (tile == num_tiles - 1) *new_count = prefix + aggregate;
+      }
+    }
+    __syncthreads();
+    const int prefix = s_prefix;
+#pragma unroll
+    for (int k = 0; k < FU_ITEMS; ++k) {
+      if (as[k] == ASSOC_NONE) continue;
+      const int q = tile * FU_TILE + k * FU_THREADS + tid;
+      const int k_new = prefix + s_excl[k * (FU_THREADS / 32) + wid] + __popc(ballots[k] & ((1u << lane) - 1u));
+      fuse_update_item(a, mp, weighting, cnt, Q, q, as[k], k_new, pending, pos_conf, color_time, norm_rad, new_pos, new_col, new_nr);
+    }
+    __syncthreads();
   }
 }
 
@@ -1494,6 +1596,17 @@ int map_fuse_async(EfContext* ctx, int time, float max_depth, float weighting) {
   const int nq = Q.ni * Q.nj;
   (void)n;
   EF_LAUNCH(ctx, k_fuse_associate, sblocks(ctx, nq, 16, 128), 128, 0, a, m.count, m.assoc_id, m.pending, m.flags);
+  if (ctx->fused_model_side) {  // (EF_FUSED_MODEL=0: the three-launch version below)
+    unsigned long long* state;
+    unsigned int *counter, epoch;
+    int nb;
+    int rc = scan_begin(ctx, (size_t)nq, FU_TILE, &state, &counter, &epoch, &nb);  // (tile states: the array is sized for tiles of 512)
+    if (rc) return rc;
+    EF_LAUNCH(ctx, k_fuse_update_compact, nb, FU_THREADS, 0, a, m.pose, (const GNState*)ctx->odom[0].gn, m.count, m.assoc_id, m.pending, m.pos_conf,
+              m.color_time, m.norm_rad, m.new_pos, m.new_col, m.new_nr, m.new_count, state, counter, epoch);
+    LAST();
+    return 0;
+  }
   EF_LAUNCH(ctx, k_set_int, 1, 32, 0, m.new_count, nq);
   int rc = run_scan(ctx, m.flags, m.new_count, nullptr, nq, B.offsets, B.totals + 2);
   if (rc) return rc;

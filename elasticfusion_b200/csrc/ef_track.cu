@@ -465,11 +465,12 @@ __global__ void k_cand_scatter(SobelArgs a, const uint8_t* __restrict__ flags, c
   }
 }
 
-// k_sobel_cand + the ordered compaction + k_cand_scatter in ONE launch (single-pass decoupled look-back over tiles of 2048 flat
+// k_sobel_cand + the ordered compaction + k_cand_scatter in ONE launch (single-pass decoupled look-back over tiles of 512 flat
 // pixels, the same protocol as k_scan_flags: persistent CTAs draw tiles from a dispenser, epoch-tagged tile states, self re-arming
 // counters): derivative images, the pose-independent gates, the candidate records in pixel order and the per-level bounds. The
 // flag and offset arrays of the three-launch version (one byte + one int per pixel, written and read back) do not exist here.
-constexpr int SC_THREADS = 256, SC_ITEMS = 8, SC_TILE = SC_THREADS * SC_ITEMS;
+constexpr int SC_THREADS = 256, SC_ITEMS = 2, SC_TILE = SC_THREADS * SC_ITEMS;  // (8 pixels per thread measured 5 us slower than three launches)
+constexpr int SC_NCNT = SC_ITEMS * (SC_THREADS / 32);
 __global__ void __launch_bounds__(SC_THREADS) k_sobel_cand_compact(SobelArgs a, int4* __restrict__ cand, GNState* gn, unsigned long long* state,
                                                                    unsigned int* counter, unsigned int epoch) {
   pdl_enter();
@@ -536,16 +537,16 @@ __global__ void __launch_bounds__(SC_THREADS) k_sobel_cand_compact(SobelArgs a, 
     }
     __syncthreads();
     if (wid == 0) {
-      // exclusive scan of the 64 (slab, warp) counts, two per lane, then the decoupled look-back
-      const int c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
-      int incl = c0 + c1;
+      // exclusive scan of the (slab, warp) counts, one per lane, then the decoupled look-back
+      static_assert(SC_NCNT <= 32, "one count per lane");
+      const int c = (lane < SC_NCNT) ? s_cnt[lane] : 0;
+      int incl = c;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, off);
         if (lane >= off) incl += t;
       }
-      s_excl[2 * lane] = incl - c0 - c1;
-      s_excl[2 * lane + 1] = incl - c1;
+      if (lane < SC_NCNT) s_excl[lane] = incl - c;
       const int aggregate = __shfl_sync(0xffffffffu, incl, 31);
       volatile unsigned long long* vstate = state;
       int prefix = 0;
