@@ -575,101 +575,6 @@ __global__ void k_fuse_update(FuseArgs a, const MapPose* __restrict__ mp, const 
   }
 }
 
-// k_fuse_update with the ordered numbering of the new surfels (the transform-feedback order of data.vert's draw) computed in the
-// same launch: single-pass decoupled look-back over tiles of 512 quarter-grid pixels, protocol of k_scan_flags. Replaces
-// k_set_int + k_scan_flags + k_fuse_update.
-constexpr int FU_THREADS = 256, FU_ITEMS = 2, FU_TILE = FU_THREADS * FU_ITEMS;  // (2 pixels per thread: the per-pixel work is a chain of loads)
-constexpr int FU_NCNT = FU_ITEMS * (FU_THREADS / 32);
-__global__ void __launch_bounds__(FU_THREADS) k_fuse_update_compact(FuseArgs a, const MapPose* __restrict__ mp, const GNState* __restrict__ gn,
-                                                                    const int* __restrict__ count, const uint32_t* __restrict__ assoc,
-                                                                    uint32_t* __restrict__ pending, float4* __restrict__ pos_conf,
-                                                                    float4* __restrict__ color_time, float4* __restrict__ norm_rad,
-                                                                    float4* __restrict__ new_pos, float4* __restrict__ new_col,
-                                                                    float4* __restrict__ new_nr, int* __restrict__ new_count,
-                                                                    unsigned long long* state, unsigned int* counter, unsigned int epoch) {
-  pdl_enter();
-  const Quarter Q = quarter_of(a.time, a.rows, a.cols);
-  const int nq = Q.ni * Q.nj;
-  const int cnt = *count;
-  const float weighting = gn->weighting;
-  const unsigned long long tag = (unsigned long long)epoch << 34;
-  const int num_tiles = (nq + FU_TILE - 1) / FU_TILE;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  __shared__ int s_cnt[FU_ITEMS * (FU_THREADS / 32)], s_excl[FU_ITEMS * (FU_THREADS / 32)];
-  __shared__ int s_tile, s_prefix;
-  while (true) {
-    if (tid == 0) s_tile = (int)atomicAdd(counter, 1u);
-    __syncthreads();
-    const int tile = s_tile;
-    if (tile >= num_tiles) {
-      if (tid == 0 && atomicAdd(counter + 1, 1u) == gridDim.x - 1) {
-        counter[0] = 0u;
-        counter[1] = 0u;
-      }
-      return;
-    }
-    uint32_t as[FU_ITEMS];
-    unsigned int ballots[FU_ITEMS];
-#pragma unroll
-    for (int k = 0; k < FU_ITEMS; ++k) {
-      const int q = tile * FU_TILE + k * FU_THREADS + tid;
-      as[k] = (q < nq) ? assoc[q] : ASSOC_NONE;
-      ballots[k] = __ballot_sync(0xffffffffu, as[k] == ASSOC_NEW);
-      if (lane == 0) s_cnt[k * (FU_THREADS / 32) + wid] = __popc(ballots[k]);
-    }
-    __syncthreads();
-    if (wid == 0) {
-      static_assert(FU_NCNT <= 32, "one count per lane");
-      const int c = (lane < FU_NCNT) ? s_cnt[lane] : 0;
-      int incl = c;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += t;
-      }
-      if (lane < FU_NCNT) s_excl[lane] = incl - c;
-      const int aggregate = __shfl_sync(0xffffffffu, incl, 31);
-      volatile unsigned long long* vstate = state;
-      int prefix = 0;
-      if (tile == 0) {
-        if (lane == 0) vstate[0] = tag | (2ull << 32) | (unsigned int)aggregate;
-      } else {
-        if (lane == 0) vstate[tile] = tag | (1ull << 32) | (unsigned int)aggregate;
-        int look = tile - 1;
-        while (true) {
-          const int idx = look - lane;
-          const unsigned long long w = (idx >= 0) ? vstate[idx] : (tag | (2ull << 32));
-          const unsigned int st = ((w >> 34) == (unsigned long long)epoch) ? ((unsigned int)(w >> 32) & 3u) : 0u;
-          if (__any_sync(0xffffffffu, st == 0)) continue;
-          const unsigned int m2 = __ballot_sync(0xffffffffu, st == 2);
-          const int first2 = m2 ? (__ffs(m2) - 1) : 32;
-          int val = (lane <= first2) ? (int)(unsigned int)(w & 0xffffffffull) : 0;
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
-          prefix += val;
-          if (m2) break;
-          look -= 32;
-        }
-        if (lane == 0) vstate[tile] = tag | (2ull << 32) | (unsigned int)(prefix + aggregate);
-      }
-      if (lane == 0) {
-        s_prefix = prefix;
-        if (tile == num_tiles - 1) *new_count = prefix + aggregate;
-      }
-    }
-    __syncthreads();
-    const int prefix = s_prefix;
-#pragma unroll
-    for (int k = 0; k < FU_ITEMS; ++k) {
-      if (as[k] == ASSOC_NONE) continue;
-      const int q = tile * FU_TILE + k * FU_THREADS + tid;
-      const int k_new = prefix + s_excl[k * (FU_THREADS / 32) + wid] + __popc(ballots[k] & ((1u << lane) - 1u));
-      fuse_update_item(a, mp, weighting, cnt, Q, q, as[k], k_new, pending, pos_conf, color_time, norm_rad, new_pos, new_col, new_nr);
-    }
-    __syncthreads();
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // clean: copy_unstable.vert/.geom without deformation graph (GlobalModel.cpp:527-671)
 // ---------------------------------------------------------------------------------------------------------------
@@ -1500,23 +1405,6 @@ int run_scan(EfContext* ctx, const uint8_t* flags, const int* n_a, const int* n_
   return 0;
 }
 
-// epoch / tile states / dispenser of the shared look-back machinery for a scan that is fused into another kernel
-int scan_begin(EfContext* ctx, size_t max_items, int tile_items, unsigned long long** state, unsigned int** counter, unsigned int* epoch, int* blocks) {
-  MapDev& m = ctx->map;
-  MapBuffers& B = mb(ctx);
-  const size_t tiles = (max_items + tile_items - 1) / tile_items + 1;
-  if (++B.scan_epoch >= (1u << 30)) {
-    CU(cudaMemsetAsync(m.scan_tile_state, 0, B.scan_state_bytes, ctx->stream));
-    B.scan_epoch = 1;
-  }
-  const size_t nb = tiles < (size_t)ctx->num_sms * 4 ? tiles : (size_t)ctx->num_sms * 4;
-  *state = (unsigned long long*)m.scan_tile_state;
-  *counter = m.scan_counter;
-  *epoch = B.scan_epoch;
-  *blocks = (int)nb;
-  return 0;
-}
-
 // T == nullptr: use the tracker's device-resident pose
 int map_update_pose_async(EfContext* ctx, const double* T_host) {
   const double* src = ctx->odom[0].gn->T_wc;
@@ -1596,17 +1484,6 @@ int map_fuse_async(EfContext* ctx, int time, float max_depth, float weighting) {
   const int nq = Q.ni * Q.nj;
   (void)n;
   EF_LAUNCH(ctx, k_fuse_associate, sblocks(ctx, nq, 16, 128), 128, 0, a, m.count, m.assoc_id, m.pending, m.flags);
-  if (ctx->fused_model_side) {  // (EF_FUSED_MODEL=0: the three-launch version below)
-    unsigned long long* state;
-    unsigned int *counter, epoch;
-    int nb;
-    int rc = scan_begin(ctx, (size_t)nq, FU_TILE, &state, &counter, &epoch, &nb);  // (tile states: the array is sized for tiles of 512)
-    if (rc) return rc;
-    EF_LAUNCH(ctx, k_fuse_update_compact, nb, FU_THREADS, 0, a, m.pose, (const GNState*)ctx->odom[0].gn, m.count, m.assoc_id, m.pending, m.pos_conf,
-              m.color_time, m.norm_rad, m.new_pos, m.new_col, m.new_nr, m.new_count, state, counter, epoch);
-    LAST();
-    return 0;
-  }
   EF_LAUNCH(ctx, k_set_int, 1, 32, 0, m.new_count, nq);
   int rc = run_scan(ctx, m.flags, m.new_count, nullptr, nq, B.offsets, B.totals + 2);
   if (rc) return rc;

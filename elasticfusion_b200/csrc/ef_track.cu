@@ -465,134 +465,6 @@ __global__ void k_cand_scatter(SobelArgs a, const uint8_t* __restrict__ flags, c
   }
 }
 
-// k_sobel_cand + the ordered compaction + k_cand_scatter in ONE launch (single-pass decoupled look-back over tiles of 512 flat
-// pixels, the same protocol as k_scan_flags: persistent CTAs draw tiles from a dispenser, epoch-tagged tile states, self re-arming
-// counters): derivative images, the pose-independent gates, the candidate records in pixel order and the per-level bounds. The
-// flag and offset arrays of the three-launch version (one byte + one int per pixel, written and read back) do not exist here.
-constexpr int SC_THREADS = 256, SC_ITEMS = 2, SC_TILE = SC_THREADS * SC_ITEMS;  // (8 pixels per thread measured 5 us slower than three launches)
-constexpr int SC_NCNT = SC_ITEMS * (SC_THREADS / 32);
-__global__ void __launch_bounds__(SC_THREADS) k_sobel_cand_compact(SobelArgs a, int4* __restrict__ cand, GNState* gn, unsigned long long* state,
-                                                                   unsigned int* counter, unsigned int epoch) {
-  pdl_enter();
-  const float gsx[9] = {(float)0.52201, (float)0.00000, (float)-0.52201, (float)0.79451, (float)-0.00000,
-                        (float)-0.79451, (float)0.52201, (float)0.00000, (float)-0.52201};
-  const float gsy[9] = {(float)0.52201, (float)0.79451, (float)0.52201, (float)0.00000, (float)0.00000,
-                        (float)0.00000, (float)-0.52201, (float)-0.79451, (float)-0.52201};
-  const unsigned long long tag = (unsigned long long)epoch << 34;
-  const int total = a.start[NUM_PYRS];
-  const int num_tiles = (total + SC_TILE - 1) / SC_TILE;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  __shared__ int s_cnt[SC_ITEMS * (SC_THREADS / 32)], s_excl[SC_ITEMS * (SC_THREADS / 32)];
-  __shared__ int s_tile, s_prefix;
-  while (true) {
-    if (tid == 0) s_tile = (int)atomicAdd(counter, 1u);
-    __syncthreads();
-    const int tile = s_tile;
-    if (tile >= num_tiles) {
-      if (tid == 0 && atomicAdd(counter + 1, 1u) == gridDim.x - 1) {
-        counter[0] = 0u;  // every CTA has drawn its terminating ticket: re-arm for the next scan
-        counter[1] = 0u;
-      }
-      return;
-    }
-    // item k of this thread is flat pixel tile * SC_TILE + k * SC_THREADS + tid: coalesced, and (k, warp, lane) = pixel order
-    unsigned int ballots[SC_ITEMS];
-    int grad[SC_ITEMS];
-#pragma unroll
-    for (int k = 0; k < SC_ITEMS; ++k) {
-      const int f = tile * SC_TILE + k * SC_THREADS + tid;
-      bool ok = false;
-      grad[k] = 0;
-      if (f < total) {
-        const int lv = (f >= a.start[2]) ? 2 : (f >= a.start[1] ? 1 : 0);
-        const int rows = a.rows[lv], cols = a.cols[lv];
-        const int p = f - a.start[lv];
-        const uint8_t* __restrict__ src = a.src[lv];
-        const int y = p / cols, x = p - y * cols;
-        float dxVal = 0, dyVal = 0;
-        int kernelIndex = 8;
-        for (int j = max(y - 1, 0); j <= min(y + 1, rows - 1); j++)
-          for (int i = max(x - 1, 0); i <= min(x + 1, cols - 1); i++) {
-            const float sv = (float)src[(size_t)j * cols + i];
-            dxVal += sv * gsx[kernelIndex];
-            dyVal += sv * gsy[kernelIndex];
-            --kernelIndex;
-          }
-        const int valx = (int16_t)__float2int_rz(dxVal), valy = (int16_t)__float2int_rz(dyVal);
-        a.dx[lv][p] = (int16_t)valx;
-        a.dy[lv][p] = (int16_t)valy;
-        grad[k] = ((int)(uint16_t)(int16_t)valx) | (((int)(uint16_t)(int16_t)valy) << 16);
-        ok = (x < cols - 5 && y < rows - 1);
-        if (ok) {
-          const float mTwo = (float)((valx * valx) + (valy * valy));
-          ok = (mTwo >= a.minScale[lv]) && !isnan(a.depth[lv][p]);
-        }
-        if (ok) {
-          for (int u = max(y - 2, 0); u < min(y + 2, rows); u++)
-            for (int v = max(x - 2, 0); v < min(x + 2, cols); v++) ok = ok && (src[(size_t)u * cols + v] > 0);
-        }
-      }
-      ballots[k] = __ballot_sync(0xffffffffu, ok);
-      if (lane == 0) s_cnt[k * (SC_THREADS / 32) + wid] = __popc(ballots[k]);
-    }
-    __syncthreads();
-    if (wid == 0) {
-      // exclusive scan of the (slab, warp) counts, one per lane, then the decoupled look-back
-      static_assert(SC_NCNT <= 32, "one count per lane");
-      const int c = (lane < SC_NCNT) ? s_cnt[lane] : 0;
-      int incl = c;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += t;
-      }
-      if (lane < SC_NCNT) s_excl[lane] = incl - c;
-      const int aggregate = __shfl_sync(0xffffffffu, incl, 31);
-      volatile unsigned long long* vstate = state;
-      int prefix = 0;
-      if (tile == 0) {
-        if (lane == 0) vstate[0] = tag | (2ull << 32) | (unsigned int)aggregate;
-      } else {
-        if (lane == 0) vstate[tile] = tag | (1ull << 32) | (unsigned int)aggregate;
-        int look = tile - 1;
-        while (true) {
-          const int idx = look - lane;
-          const unsigned long long w = (idx >= 0) ? vstate[idx] : (tag | (2ull << 32));
-          const unsigned int st = ((w >> 34) == (unsigned long long)epoch) ? ((unsigned int)(w >> 32) & 3u) : 0u;
-          if (__any_sync(0xffffffffu, st == 0)) continue;  // a predecessor has not published yet: re-read
-          const unsigned int m2 = __ballot_sync(0xffffffffu, st == 2);
-          const int first2 = m2 ? (__ffs(m2) - 1) : 32;
-          int val = (lane <= first2) ? (int)(unsigned int)(w & 0xffffffffull) : 0;
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
-          prefix += val;
-          if (m2) break;
-          look -= 32;
-        }
-        if (lane == 0) vstate[tile] = tag | (2ull << 32) | (unsigned int)(prefix + aggregate);
-      }
-      if (lane == 0) {
-        s_prefix = prefix;
-        if (tile == num_tiles - 1) gn->cand_base[NUM_PYRS] = prefix + aggregate;
-      }
-    }
-    __syncthreads();
-    const int prefix = s_prefix;
-#pragma unroll
-    for (int k = 0; k < SC_ITEMS; ++k) {
-      const int f = tile * SC_TILE + k * SC_THREADS + tid;
-      if (f >= total) continue;
-      const int lv = (f >= a.start[2]) ? 2 : (f >= a.start[1] ? 1 : 0);
-      const int o = prefix + s_excl[k * (SC_THREADS / 32) + wid] + __popc(ballots[k] & ((1u << lane) - 1u));
-      if (f == a.start[lv]) gn->cand_base[lv] = o;  // exclusive prefix at the first pixel of the level
-      if (!((ballots[k] >> lane) & 1u)) continue;
-      const int p = f - a.start[lv];
-      cand[o] = make_int4(p, __float_as_int(a.depth[lv][p]), grad[k], (int)a.src[lv][p]);
-    }
-    __syncthreads();
-  }
-}
-
 // =============================================================================================
 // host side: RGBDOdometry mirror
 // =============================================================================================
@@ -617,7 +489,6 @@ inline int flat_blocks(const EfContext* ctx, size_t n) {
 namespace ef {
 int run_scan(EfContext* ctx, const uint8_t* flags, const int* n_a, const int* n_b, size_t max_items, int* offsets, int* total);
 void scan_scratch(EfContext* ctx, uint8_t** flags, int** offsets);
-int scan_begin(EfContext* ctx, size_t max_items, int tile_items, unsigned long long** state, unsigned int** counter, unsigned int* epoch, int* blocks);
 
 int odom_init_icp_depth(EfContext* ctx, int which, const uint16_t* depth_dev, float cutoff) {
   OdomDev& od = ctx->odom[which];
@@ -743,17 +614,6 @@ int launch_sobel(EfContext* ctx, int which) {
   }
   a.start[NUM_PYRS] = od.level_start[NUM_PYRS];
   const size_t flat = (size_t)od.level_start[NUM_PYRS];
-  if (ctx->fused_model_side) {  // (EF_FUSED_MODEL=0 falls back to the three-launch version of this as well)
-    unsigned long long* state;
-    unsigned int *counter, epoch;
-    int nb;
-    int rc = scan_begin(ctx, flat, SC_TILE, &state, &counter, &epoch, &nb);
-    if (rc) return rc;
-    EF_LAUNCH(ctx, k_sobel_cand_compact, nb, SC_THREADS, 0, a, od.cand, od.gn, state, counter, epoch);
-    ctx->maps_dirty[which] = true;  // k_iter1 / k_iter2 read the list ahead of their dependency wait: fence before the next one
-    EF_CHECK_LAST();
-    return 0;
-  }
   uint8_t* flags;
   int* offsets;
   scan_scratch(ctx, &flags, &offsets);
