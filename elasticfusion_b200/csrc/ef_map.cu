@@ -321,32 +321,56 @@ __global__ void k_init_scatter(const uint8_t* __restrict__ rgb, const float* __r
 // ---------------------------------------------------------------------------------------------------------------
 // index map: index_map.vert/.frag (IndexMap.cpp:190-258)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_index_scatter(const float4* __restrict__ pos_conf, const float4* __restrict__ color_time, const int* __restrict__ count,
+__global__ void __launch_bounds__(256, 5) k_index_scatter(const float4* __restrict__ pos_conf, const float4* __restrict__ color_time, const int* __restrict__ count,
                                 const MapPose* __restrict__ mp, int time, float max_depth, int time_delta, int rows, int cols, Cam c,
                                 unsigned long long* __restrict__ zbuf) {
   pdl_enter();
   const int n = *count;
   const float fcols = (float)cols, frows = (float)rows;
-  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
-    const float4 pc = pos_conf[id];
-    const float last_time = color_time[id].w;  // fetched with the position: one memory round trip per surfel, not two
-    const f3 h = xform(mp->t_inv, mk3(pc.x, pc.y, pc.z));
-    if (h.z > max_depth || h.z < 0) continue;
-    if ((float)time - last_time > (float)time_delta) continue;
-    const float xn = ((((c.fx * h.x) / h.z) + c.cx) - (fcols * 0.5f)) / (fcols * 0.5f);
-    const float yn = ((((c.fy * h.y) / h.z) + c.cy) - (frows * 0.5f)) / (frows * 0.5f);
-    const float zn = h.z / max_depth;
-    if (!(xn >= -1.f && xn <= 1.f && yn >= -1.f && yn <= 1.f && zn >= -1.f && zn <= 1.f)) continue;
-    const float xw = (xn + 1.0f) * (fcols * 0.5f);
-    const float yw = (yn + 1.0f) * (frows * 0.5f);
-    const int px = point_pixel(xw), py = point_pixel(yw);
-    if (px < 0 || py < 0 || px >= cols || py >= rows) continue;
-    const unsigned int d24 = depth24(0.5f * zn + 0.5f);
-    if (d24 >= 16777215u) continue;
-    const unsigned long long key = ((unsigned long long)d24 << 32) | (unsigned int)id;
-    unsigned long long* slot = &zbuf[(size_t)py * cols + px];
-    if (__ldcg(slot) <= key) continue;  // cannot win (the slot only ever decreases): no atomic
-    atomicMin(slot, key);
+  // Two surfels per thread and round, in three phases -- 4 loads, 2 projections + 2 z-buffer reads, <= 2 atomics -- so that a
+  // thread has independent requests in flight instead of a chain of three (one surfel at a time: 40 us for 5 M surfels,
+  // long-scoreboard 20 per issue at 39 % of the DRAM roof). One resident wave of 5 CTAs per SM (<= 51 registers); a small map
+  // still gives every thread at most one round.
+  constexpr int U = 2;
+  const int stride = gridDim.x * blockDim.x;
+  for (int base = blockIdx.x * blockDim.x + threadIdx.x; base < n; base += U * stride) {
+    float4 pc[U];
+    float last_time[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int id = base + u * stride;
+      if (id < n) {
+        pc[u] = pos_conf[id];
+        last_time[u] = color_time[id].w;
+      }
+    }
+    unsigned long long key[U], cur[U];
+    unsigned long long* slot[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int id = base + u * stride;
+      slot[u] = nullptr;
+      if (id >= n) continue;
+      const f3 h = xform(mp->t_inv, mk3(pc[u].x, pc[u].y, pc[u].z));
+      if (h.z > max_depth || h.z < 0) continue;
+      if ((float)time - last_time[u] > (float)time_delta) continue;
+      const float xn = ((((c.fx * h.x) / h.z) + c.cx) - (fcols * 0.5f)) / (fcols * 0.5f);
+      const float yn = ((((c.fy * h.y) / h.z) + c.cy) - (frows * 0.5f)) / (frows * 0.5f);
+      const float zn = h.z / max_depth;
+      if (!(xn >= -1.f && xn <= 1.f && yn >= -1.f && yn <= 1.f && zn >= -1.f && zn <= 1.f)) continue;
+      const float xw = (xn + 1.0f) * (fcols * 0.5f);
+      const float yw = (yn + 1.0f) * (frows * 0.5f);
+      const int px = point_pixel(xw), py = point_pixel(yw);
+      if (px < 0 || py < 0 || px >= cols || py >= rows) continue;
+      const unsigned int d24 = depth24(0.5f * zn + 0.5f);
+      if (d24 >= 16777215u) continue;
+      key[u] = ((unsigned long long)d24 << 32) | (unsigned int)id;
+      slot[u] = &zbuf[(size_t)py * cols + px];
+      cur[u] = __ldcg(slot[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (slot[u] && cur[u] > key[u]) atomicMin(slot[u], key[u]);  // (a slot only ever decreases: one that cannot win sends no atomic)
   }
 }
 
@@ -824,6 +848,17 @@ __global__ void __launch_bounds__(CF_THREADS, 2) k_clean_flags(CleanArgs a, cons
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n_old = *count, total = n_old + *new_count;
   const int num_tiles = (total + CC_TILE - 1) / CC_TILE;
+  // (the next tile's position / colour-time records are requested before this tile is tested: two rounds in flight)
+  auto fetch = [&](int t, float4& pos, float4& col) {
+    const int g = t * CC_TILE + tid;
+    if (t < num_tiles && g < total) {
+      const bool is_old = g < n_old;
+      pos = is_old ? pos_conf[g] : new_pos[g - n_old];
+      col = is_old ? color_time[g] : new_col[g - n_old];
+    }
+  };
+  float4 pos_next = make_float4(0.f, 0.f, 0.f, 0.f), col_next = pos_next;
+  fetch(blockIdx.x, pos_next, col_next);
   for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
     const int g0 = t * CC_TILE;
     const int n_in = min(CC_TILE, total - g0);
@@ -831,11 +866,12 @@ __global__ void __launch_bounds__(CF_THREADS, 2) k_clean_flags(CleanArgs a, cons
     bool moves = (g0 + n_in > n_old) || a.n_nodes > 0;
     // thread = item of the tile: warp w holds items 32 w .. 32 w + 31, i.e. keep-mask word w in k_clean_move's (slab, warp) order
     const int g = g0 + tid;
+    const float4 pos = pos_next;
+    float4 col = col_next;
+    fetch(t + gridDim.x, pos_next, col_next);
     bool keep = false;
     if (tid < n_in) {
       const bool is_old = g < n_old;
-      const float4 pos = is_old ? pos_conf[g] : new_pos[g - n_old];
-      float4 col = is_old ? color_time[g] : new_col[g - n_old];
       keep = clean_test(a, mp, pos, col, is_old ? norm_rad + g : new_nr + (g - n_old));
     }
     const unsigned int ballot = __ballot_sync(0xffffffffu, keep);
@@ -1094,7 +1130,7 @@ struct SplatWarp {
   int start[33];   // exclusive prefix of the fragment counts
 };
 
-__global__ void __launch_bounds__(SPLAT_THREADS) k_splat_scatter(RayArgs a, const MapPose* __restrict__ mp, const float4* __restrict__ pos_conf,
+__global__ void __launch_bounds__(SPLAT_THREADS, 4) k_splat_scatter(RayArgs a, const MapPose* __restrict__ mp, const float4* __restrict__ pos_conf,
                                                                  const float4* __restrict__ color_time, const float4* __restrict__ norm_rad,
                                                                  const int* __restrict__ count, unsigned long long* __restrict__ zbuf) {
   pdl_enter();
@@ -1103,11 +1139,26 @@ __global__ void __launch_bounds__(SPLAT_THREADS) k_splat_scatter(RayArgs a, cons
   SplatWarp& W = sw_all[wid];
   const int n = *count;
   const int gw = blockIdx.x * (SPLAT_THREADS / 32) + wid, nw = gridDim.x * (SPLAT_THREADS / 32);
+  // (the next round's position / colour-time records are requested before this round is rasterised: most surfels of a large
+  // map are rejected right after the load, so the loop is a chain of round trips unless two rounds are in flight)
+  float4 pc_next = make_float4(0.f, 0.f, 0.f, 0.f), ct_next = pc_next;
+  if (gw * 32 + lane < n) {
+    pc_next = pos_conf[gw * 32 + lane];
+    ct_next = color_time[gw * 32 + lane];
+  }
   for (int base = gw * 32; base < n; base += nw * 32) {
     const int id = base + lane;
+    const float4 pc_cur = pc_next, ct_cur = ct_next;
+    {
+      const long long nid = (long long)base + (long long)nw * 32 + lane;
+      if (nid < n) {
+        pc_next = pos_conf[nid];
+        ct_next = color_time[nid];
+      }
+    }
     Splat sp;
     int x0 = 0, y0 = 0, bw = 0, nfrag = 0;
-    if (id < n && splat_vertex(a, mp, pos_conf[id], color_time[id], norm_rad, id, sp)) {
+    if (id < n && splat_vertex(a, mp, pc_cur, ct_cur, norm_rad, id, sp)) {
       int x1, y1;
       sprite_range(sp.xw, sp.size, x0, x1);
       sprite_range(sp.yw, sp.size, y0, y1);
@@ -1445,7 +1496,7 @@ int map_predict_indices_async(EfContext* ctx, int time, float max_depth, int tim
   const int n = m.rows * m.cols;
   const int cap_guess = ctx->host_count > 0 ? ctx->host_count : m.capacity;
   (void)cap_guess;
-  EF_LAUNCH(ctx, k_index_scatter, ctx->num_sms * 8, 256, 0, m.pos_conf, m.color_time, m.count, m.pose, time, max_depth, time_delta, m.rows,
+  EF_LAUNCH(ctx, k_index_scatter, ctx->num_sms * 5, 256, 0, m.pos_conf, m.color_time, m.count, m.pose, time, max_depth, time_delta, m.rows,
             m.cols, cam_of(ctx), m.zbuf);
   EF_LAUNCH(ctx, k_index_resolve, sblocks(ctx, n), 256, 0, m.pos_conf, m.color_time, m.norm_rad, m.pose, n, m.zbuf, ctx->tex.index,
             ctx->tex.vert_conf, ctx->tex.color_time, ctx->tex.norm_rad);
@@ -1553,7 +1604,7 @@ int map_raycast_async(EfContext* ctx, float max_depth, float conf_threshold, int
   a.time = time;
   a.max_time = max_time;
   a.time_delta = time_delta;
-  EF_LAUNCH(ctx, k_splat_scatter, ctx->num_sms * 8, SPLAT_THREADS, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.zbuf);
+  EF_LAUNCH(ctx, k_splat_scatter, ctx->num_sms * 4, SPLAT_THREADS, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.count, m.zbuf);
   Textures& t = ctx->tex;
   if (mode == 0)
     EF_LAUNCH(ctx, k_splat_resolve, sblocks(ctx, n), 256, 0, a, m.pose, m.pos_conf, m.color_time, m.norm_rad, m.zbuf, t.image, t.vertex, t.normal,
