@@ -37,7 +37,7 @@ int rgb_to_rgba(EfContext* ctx, const uint8_t* rgb, uint8_t* rgba);
 
 int map_initialise_async(EfContext* ctx);
 int map_update_pose_async(EfContext* ctx, const double* T_host_or_null);
-int map_predict_indices_async(EfContext* ctx, int time_or_neg, float max_depth, int time_delta);
+int map_predict_indices_async(EfContext* ctx, int time_or_neg, float max_depth, int time_delta, int vis_mode = 0);
 int map_fuse_async(EfContext* ctx, int time_or_neg, float max_depth, float weighting_or_neg);
 int map_clean_async(EfContext* ctx, int time_or_neg, float conf_threshold, int time_delta, float max_depth, int n_nodes = 0, bool is_fern = false);
 int map_set_graph(EfContext* ctx, const float* nodes16, int n_nodes);
@@ -315,6 +315,9 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
     // cluster size (16 default, 8, or 0 = off), EF_GN_CLUSTER_LEVELS = how many levels from the top of the pyramid (default 1: the 160x120
     // level; measured 313 / 322 / 446 us for the whole loop with 1 / 2 / 3 levels against 338 without -- 16 SMs are too few for the
     // dense pass of the finer levels)
+    e = getenv("EF_VISIBLE_LIST");
+    ctx->visible_list = !(e && e[0] == '0');
+    ctx->vis_pending = false;
     e = getenv("EF_FUSED_MODEL");
     ctx->fused_model_side = !(e && e[0] == '0');
     e = getenv("EF_GN_CLUSTER");
@@ -1127,11 +1130,11 @@ static int frame_begin_device(EfContext* ctx, const uint8_t* rgb_dev, const uint
 static int frame_end_device(EfContext* ctx, int n_nodes, bool fern_accepted) {
   if (!ctx->frame_open) return EF_ESTATE;
   if (ctx->tick > 1 && !ctx->rgb_only) {
-    RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta));
+    RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta, 1));
     ef_stage(ctx, 7);
     RC(map_fuse_async(ctx, ctx->tick, ctx->max_depth_processed, -1.0f));
     ef_stage(ctx, 8);
-    RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta));
+    RC(map_predict_indices_async(ctx, ctx->tick, ctx->max_depth_processed, ctx->cfg.time_delta, 2));
     ef_stage(ctx, 9);
     if (n_nodes > 0 && !fern_accepted)  // ElasticFusion.cpp:559-569: the time-stamp refresh of deformed surfels reads this depth
       RC(map_raycast_async(ctx, ctx->max_depth_processed, ctx->confidence, ctx->tick, ctx->tick - ctx->cfg.time_delta, 65535, 2, false));

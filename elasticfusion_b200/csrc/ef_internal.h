@@ -143,6 +143,8 @@ struct MapDev {
   // scan scratch
   int* scan_tile_state;   // decoupled look-back
   unsigned int* scan_counter;
+  uint32_t* vis_list;        // surfels that reached the z-buffer in the frame's first index-map pass (k_index_scatter<1>)
+  int* vis_count;
   unsigned int* clean_ctl;   // [0] tile dispenser, [1] exit tickets, [2] first tile that moves (k_clean_flags -> k_clean_move)
   uint32_t* keep_mask;       // one warp ballot per 32 surfels: the clean test's verdicts
   uint8_t* flags;         // capacity + W*H
@@ -212,6 +214,8 @@ struct EfContext {
   bool pdl;  // programmatic dependent launch on every kernel (default on; EF_NO_PDL=1 disables)
   bool it1_prefetch;   // k_iter1 loads its first round of live-map pixels before griddepcontrol.wait (EF_IT1_PREFETCH=0 disables)
   int it2_max_blocks;  // cap on k_iter2's grid (EF_IT2_MAXBLOCKS; default MAX_RGB_BLOCKS)
+  bool vis_pending;       // the first pass of a frame has filled the visible list and the second has not consumed it yet
+  bool visible_list;      // second index-map pass of a frame visits only the surfels the first one rasterised; EF_VISIBLE_LIST=0 disables
   bool fused_model_side;  // model pyramids of a frame in 3 launches (k_model_level0 / _down) instead of 6; EF_FUSED_MODEL=0 disables
   int gn_cluster;         // CTAs of the cluster that runs the coarse-level Gauss-Newton iterations (0: two-kernel path everywhere)
   int gn_cluster_levels;  // pyramid levels, from the coarsest, whose iterations run in that cluster

@@ -321,36 +321,53 @@ __global__ void k_init_scatter(const uint8_t* __restrict__ rgb, const float* __r
 // ---------------------------------------------------------------------------------------------------------------
 // index map: index_map.vert/.frag (IndexMap.cpp:190-258)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 5) k_index_scatter(const float4* __restrict__ pos_conf, const float4* __restrict__ color_time, const int* __restrict__ count,
-                                const MapPose* __restrict__ mp, int time, float max_depth, int time_delta, int rows, int cols, Cam c,
-                                unsigned long long* __restrict__ zbuf) {
+// MODE 0: every surfel of the map. MODE 1: the same, and every surfel that reaches the z-buffer stage is appended to `vis`
+// (unordered; warp-aggregated). MODE 2: only the surfels listed in `vis` are visited.
+// The frame loop renders the index map twice with identical arguments, before and after fuse (IndexMap::predictIndices,
+// ElasticFusion.cpp:536-556). Fuse only writes surfels it found THROUGH the first index map, i.e. surfels in `vis`; every other
+// surfel is bit-for-bit what it was and fails (or cannot win differently in) the second pass exactly as it did in the first, and
+// new surfels join the map only in clean. So the second pass over `vis` -- each entry re-tested with its updated state --
+// produces the identical index map while reading the in-view part of the map instead of all of it.
+template <int MODE>
+__global__ void __launch_bounds__(256, 5) k_index_scatter(const float4* __restrict__ pos_conf, const float4* __restrict__ color_time,
+                                                          const int* __restrict__ count, const MapPose* __restrict__ mp, int time, float max_depth,
+                                                          int time_delta, int rows, int cols, Cam c, unsigned long long* __restrict__ zbuf,
+                                                          uint32_t* __restrict__ vis, int* __restrict__ vis_count, int vis_capacity) {
   pdl_enter();
-  const int n = *count;
+  const int n_map = *count;
+  const int n = (MODE == 2) ? min(*vis_count, vis_capacity) : n_map;
   const float fcols = (float)cols, frows = (float)rows;
   // Two surfels per thread and round, in three phases -- 4 loads, 2 projections + 2 z-buffer reads, <= 2 atomics -- so that a
   // thread has independent requests in flight instead of a chain of three (one surfel at a time: 40 us for 5 M surfels,
   // long-scoreboard 20 per issue at 39 % of the DRAM roof). One resident wave of 5 CTAs per SM (<= 51 registers); a small map
-  // still gives every thread at most one round.
+  // still gives every thread at most one round. The loop bound is warp-uniform (the append below votes with the full warp).
   constexpr int U = 2;
+  const int lane = threadIdx.x & 31;
   const int stride = gridDim.x * blockDim.x;
-  for (int base = blockIdx.x * blockDim.x + threadIdx.x; base < n; base += U * stride) {
+  for (int wbase = blockIdx.x * blockDim.x + threadIdx.x - lane; wbase < n; wbase += U * stride) {
     float4 pc[U];
     float last_time[U];
+    int ids[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int id = base + u * stride;
-      if (id < n) {
-        pc[u] = pos_conf[id];
-        last_time[u] = color_time[id].w;
+      const int i = wbase + lane + u * stride;
+      ids[u] = -1;
+      if (i < n) {
+        const int id = (MODE == 2) ? (int)vis[i] : i;
+        if (id < n_map) {
+          ids[u] = id;
+          pc[u] = pos_conf[id];
+          last_time[u] = color_time[id].w;
+        }
       }
     }
     unsigned long long key[U], cur[U];
     unsigned long long* slot[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int id = base + u * stride;
+      const int id = ids[u];
       slot[u] = nullptr;
-      if (id >= n) continue;
+      if (id < 0) continue;
       const f3 h = xform(mp->t_inv, mk3(pc[u].x, pc[u].y, pc[u].z));
       if (h.z > max_depth || h.z < 0) continue;
       if ((float)time - last_time[u] > (float)time_delta) continue;
@@ -369,16 +386,27 @@ __global__ void __launch_bounds__(256, 5) k_index_scatter(const float4* __restri
       cur[u] = __ldcg(slot[u]);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+    for (int u = 0; u < U; ++u) {
+      if (MODE == 1) {
+        const unsigned int m = __ballot_sync(0xffffffffu, slot[u] != nullptr);
+        if (m) {
+          int at = 0;
+          if (lane == 0) at = atomicAdd(vis_count, __popc(m));
+          at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+          if (slot[u] && at < vis_capacity) vis[at] = (uint32_t)ids[u];
+        }
+      }
       if (slot[u] && cur[u] > key[u]) atomicMin(slot[u], key[u]);  // (a slot only ever decreases: one that cannot win sends no atomic)
+    }
   }
 }
 
 __global__ void k_index_resolve(const float4* __restrict__ pos_conf, const float4* __restrict__ color_time, const float4* __restrict__ norm_rad,
                                 const MapPose* __restrict__ mp, int n_px, unsigned long long* __restrict__ zbuf,
                                 uint32_t* __restrict__ index, float4* __restrict__ vert_conf, float4* __restrict__ col_time,
-                                float4* __restrict__ nrm_rad) {
+                                float4* __restrict__ nrm_rad, int* __restrict__ reset_count) {
   pdl_enter();
+  if (reset_count && blockIdx.x == 0 && threadIdx.x == 0) *reset_count = 0;  // the visible list has been consumed: re-arm it
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_px; p += gridDim.x * blockDim.x) {
     const unsigned long long key = zbuf[p];
     zbuf[p] = kEmptyKey;  // the resolve pass leaves the z-buffer cleared for the next scatter (no memset between passes)
@@ -1409,6 +1437,9 @@ int alloc_map(EfContext* ctx) {
   m.scan_tile_state = reinterpret_cast<int*>(st);
   CU(ctx_alloc(ctx, &m.scan_counter, 4));
   CU(ctx_alloc(ctx, &m.clean_ctl, 4));
+  CU(ctx_alloc(ctx, &m.vis_list, cap));
+  CU(ctx_alloc(ctx, &m.vis_count, 4));
+  CU(cudaMemsetAsync(m.vis_count, 0, 16, ctx->stream));
   CU(ctx_alloc(ctx, &m.keep_mask, ((max_items + CC_TILE - 1) / CC_TILE) * CC_WORDS));
   CU(ctx_alloc(ctx, &m.flags, 2 * n));
   CU(ctx_alloc(ctx, &B->offsets, 2 * n));
@@ -1491,15 +1522,28 @@ int map_initialise_async(EfContext* ctx) {
   return 0;
 }
 
-int map_predict_indices_async(EfContext* ctx, int time, float max_depth, int time_delta) {
+// vis_mode 0: plain (stage API). 1: also record the surfels that reach the z-buffer (first pass of a frame). 2: visit only those
+// (second pass of the frame, same arguments, only fuse in between) and re-arm the list.
+int map_predict_indices_async(EfContext* ctx, int time, float max_depth, int time_delta, int vis_mode) {
   MapDev& m = ctx->map;
   const int n = m.rows * m.cols;
-  const int cap_guess = ctx->host_count > 0 ? ctx->host_count : m.capacity;
-  (void)cap_guess;
-  EF_LAUNCH(ctx, k_index_scatter, ctx->num_sms * 5, 256, 0, m.pos_conf, m.color_time, m.count, m.pose, time, max_depth, time_delta, m.rows,
-            m.cols, cam_of(ctx), m.zbuf);
+  if (!ctx->visible_list) vis_mode = 0;
+  const int grid = ctx->num_sms * 5;
+  if (vis_mode == 1 && ctx->vis_pending) CU(cudaMemsetAsync(m.vis_count, 0, 4, ctx->stream));  // (a frame that failed between its two passes)
+  if (vis_mode == 2 && !ctx->vis_pending) vis_mode = 0;
+  if (vis_mode == 1) ctx->vis_pending = true;
+  if (vis_mode == 2) ctx->vis_pending = false;
+  if (vis_mode == 1)
+    EF_LAUNCH(ctx, k_index_scatter<1>, grid, 256, 0, m.pos_conf, m.color_time, m.count, m.pose, time, max_depth, time_delta, m.rows, m.cols,
+              cam_of(ctx), m.zbuf, m.vis_list, m.vis_count, m.capacity);
+  else if (vis_mode == 2)
+    EF_LAUNCH(ctx, k_index_scatter<2>, grid, 256, 0, m.pos_conf, m.color_time, m.count, m.pose, time, max_depth, time_delta, m.rows, m.cols,
+              cam_of(ctx), m.zbuf, m.vis_list, m.vis_count, m.capacity);
+  else
+    EF_LAUNCH(ctx, k_index_scatter<0>, grid, 256, 0, m.pos_conf, m.color_time, m.count, m.pose, time, max_depth, time_delta, m.rows, m.cols,
+              cam_of(ctx), m.zbuf, (uint32_t*)nullptr, (int*)nullptr, 0);
   EF_LAUNCH(ctx, k_index_resolve, sblocks(ctx, n), 256, 0, m.pos_conf, m.color_time, m.norm_rad, m.pose, n, m.zbuf, ctx->tex.index,
-            ctx->tex.vert_conf, ctx->tex.color_time, ctx->tex.norm_rad);
+            ctx->tex.vert_conf, ctx->tex.color_time, ctx->tex.norm_rad, vis_mode == 2 ? m.vis_count : (int*)nullptr);
   LAST();
   return 0;
 }

@@ -510,6 +510,35 @@ def test_icp_only_registration_at_one_eighth_resolution(K):
     assert abs(float(sp["lastICPError"]) - so["lastICPError"]) <= 1e-3 * so["lastICPError"] and float(sp["lastICPError"]) < 3e-4
 
 
+def test_visible_list_second_index_pass_is_exact(monkeypatch, frames, K):
+    """The frame's second index-map pass visits only the surfels the first one rasterised (ef_map.cu: k_index_scatter<1> / <2>).
+    Bit-identical poses, maps and index / vertex-confidence images against visiting the whole map both times, over frames in
+    which surfels are fused, added and culled; also with a finite time window."""
+
+    def run(env, **cfg):
+        monkeypatch.delenv("EF_VISIBLE_LIST", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = make_ctx(K, **cfg)
+        try:
+            out = []
+            for i in range(8):
+                ctx.process_frame(frames[i][0], frames[i][1], i * 33333)
+                out.append((ctx.get_pose().copy(), ctx.map_count()))
+            return out, ctx.map_download(), ctx.download("INDEX").copy(), ctx.download("VERT_CONF").copy()
+        finally:
+            ctx.close()
+
+    for cfg in (dict(), dict(time_delta=3, confidence=2.0)):
+        a = run({"EF_VISIBLE_LIST": "0"}, **cfg)
+        b = run({}, **cfg)
+        for (Ta, ca), (Tb, cb) in zip(a[0], b[0]):
+            assert np.array_equal(Ta, Tb) and ca == cb
+        assert_same(a[1], b[1], "map")
+        assert_same(a[2], b[2], "index map")
+        assert_same(a[3], b[3], "index map vertices")
+
+
 def test_cluster_and_two_kernel_gauss_newton_agree(monkeypatch):
     """k_gn_cluster (the coarse-level iterations inside one thread-block cluster, partial sums through distributed shared
     memory) against the two-kernel path (k_iter1 + k_iter2): same iteration records; the systems differ by the regrouping of
