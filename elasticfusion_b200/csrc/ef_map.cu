@@ -340,17 +340,18 @@ __global__ void __launch_bounds__(256, 5) k_index_scatter(const float4* __restri
   // Two surfels per thread and round, in three phases -- 4 loads, 2 projections + 2 z-buffer reads, <= 2 atomics -- so that a
   // thread has independent requests in flight instead of a chain of three (one surfel at a time: 40 us for 5 M surfels,
   // long-scoreboard 20 per issue at 39 % of the DRAM roof). One resident wave of 5 CTAs per SM (<= 51 registers); a small map
-  // still gives every thread at most one round. The loop bound is warp-uniform (the append below votes with the full warp).
+  // still gives every thread at most one round.
   constexpr int U = 2;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int stride = gridDim.x * blockDim.x;
-  for (int wbase = blockIdx.x * blockDim.x + threadIdx.x - lane; wbase < n; wbase += U * stride) {
+  __shared__ int s_vis[256 / 32 + 1];
+  for (int bbase = blockIdx.x * blockDim.x; bbase < n; bbase += U * stride) {  // (CTA-uniform bound: the append below synchronises)
     float4 pc[U];
     float last_time[U];
     int ids[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int i = wbase + lane + u * stride;
+      const int i = bbase + threadIdx.x + u * stride;
       ids[u] = -1;
       if (i < n) {
         const int id = (MODE == 2) ? (int)vis[i] : i;
@@ -388,13 +389,23 @@ __global__ void __launch_bounds__(256, 5) k_index_scatter(const float4* __restri
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (MODE == 1) {
+        // one atomic per CTA and round (one per warp put 8 k of them on a single address for a small map: +6 us)
         const unsigned int m = __ballot_sync(0xffffffffu, slot[u] != nullptr);
-        if (m) {
-          int at = 0;
-          if (lane == 0) at = atomicAdd(vis_count, __popc(m));
-          at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
-          if (slot[u] && at < vis_capacity) vis[at] = (uint32_t)ids[u];
+        if (lane == 0) s_vis[wid] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          int tot = 0;
+          for (int w = 0; w < 256 / 32; ++w) {
+            const int cw = s_vis[w];
+            s_vis[w] = tot;
+            tot += cw;
+          }
+          s_vis[256 / 32] = tot ? atomicAdd(vis_count, tot) : 0;
         }
+        __syncthreads();
+        const int at = s_vis[256 / 32] + s_vis[wid] + __popc(m & ((1u << lane) - 1u));
+        if (slot[u] && at < vis_capacity) vis[at] = (uint32_t)ids[u];
+        __syncthreads();
       }
       if (slot[u] && cur[u] > key[u]) atomicMin(slot[u], key[u]);  // (a slot only ever decreases: one that cannot win sends no atomic)
     }

@@ -2,7 +2,7 @@
 # visible-list index pass: full GPU tests, large-map bench A/B
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-timeout 1200 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider > gpurun_out/r02_pytest_vis.txt 2>&1
+timeout 1200 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider -k "visible or pipeline or predict_indices or gl_golden or fuse or sequence" > gpurun_out/r02_pytest_vis.txt 2>&1
 tail -n 4 gpurun_out/r02_pytest_vis.txt
 for cfg in "EF_DUMMY=1" "EF_VISIBLE_LIST=0"; do
   echo "== $cfg"
