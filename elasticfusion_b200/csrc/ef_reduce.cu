@@ -1325,16 +1325,14 @@ __device__ __forceinline__ void so3_gradient(const uint8_t* img, int cols, int x
 }
 
 // per-CTA partial of one SO3 step (11 floats into od.partials[vb])
+// rows of one SO3 step accumulated by this thread: pixels vb * THREADS + tid, stride nvb * THREADS
 template <int THREADS>
-__device__ __forceinline__ void so3_partial(const OdomDev& od, int vb, int nvb, float* sred) {
-  const So3State* gn = od.so3s;
+__device__ __forceinline__ void so3_rows(const OdomDev& od, const m33& imageBasis, const m33& kinv, const m33& krlr, int vb, int nvb, float (&acc)[11]) {
   const int level = 2;
   const int rows = od.rows[level], cols = od.cols[level];
   const int N = rows * cols;
-  const m33 imageBasis = load_m33(gn->imageBasis), kinv = load_m33(gn->kinv), krlr = load_m33(gn->krlr);
   const uint8_t* lastImage = od.lastNextImage[level];
   const uint8_t* nextImage = od.nextImage[level];
-  float acc[11];
 #pragma unroll
   for (int k = 0; k < 11; ++k) acc[k] = 0.f;
   for (int k = vb * THREADS + threadIdx.x; k < N; k += nvb * THREADS) {
@@ -1372,6 +1370,13 @@ __device__ __forceinline__ void so3_partial(const OdomDev& od, int vb, int nvb, 
       acc[10] += 1.0f;
     }
   }
+}
+
+template <int THREADS>
+__device__ __forceinline__ void so3_partial(const OdomDev& od, int vb, int nvb, float* sred) {
+  const So3State* gn = od.so3s;
+  float acc[11];
+  so3_rows<THREADS>(od, load_m33(gn->imageBasis), load_m33(gn->kinv), load_m33(gn->krlr), vb, nvb, acc);
   block_reduce_sum<11, THREADS>(acc, sred);
   if (threadIdx.x < 11) od.so3_partials[(size_t)vb * PARTIAL_STRIDE + threadIdx.x] = acc[0];
 }
@@ -1448,6 +1453,78 @@ __global__ void __launch_bounds__(RED_THREADS) k_so3_step(OdomDev od, int iter, 
   so3_finish(od, iter);
 }
 
+// The whole SO(3) pre-alignment loop (k_so3_begin + up to 10 x k_so3_step) in one launch of one cluster: same protocol as
+// k_gn_cluster -- per-CTA 11-term partials into the leader's shared memory, the leader sums them in rank order in double, its
+// thread 0 runs the unchanged solve / convergence logic (so3_finish) and publishes the next iteration's three matrices and the
+// exit flag through its shared memory. 160x120 pixels of work per iteration; the ten-launch version pays a kernel boundary and a
+// gpu-scope ticket for each, also for the iterations after convergence (47 us in total, on the critical path of every caller that
+// does not use look-ahead).
+struct So3Shared {
+  float slots[GC_MAX_CL][16];
+  float P[28];   // imageBasis 9, kinv 9, krlr 9, done flag
+  float Pl[28];
+  float sred[32 * (GC_THREADS / 32)];
+};
+__global__ void __launch_bounds__(GC_THREADS, 1) k_so3_cluster(OdomDev od) {
+  pdl_enter();
+  __shared__ So3Shared sh;
+  So3State* st = od.so3s;
+  const int tid = threadIdx.x;
+  const int rank = (int)cluster_rank(), C = (int)cluster_size();
+  So3Shared* lead = cluster_map(&sh, 0u);
+  if (rank == 0 && tid == 0) {
+    // start of the SO(3) loop (RGBDOdometry.cpp:284-303), k_so3_begin's body
+    const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int k = 0; k < 9; ++k) {
+      st->resultR[k] = I3[k];
+      st->lastResultR[k] = I3[k];
+      st->R_lr[k] = (float)I3[k];
+    }
+    st->so3_lastError = FLT_MAX / 2;
+    st->so3_lastCount = FLT_MAX / 2;
+    st->so3_done = 0;
+    st->trace_n = 0;
+    so3_prepare(st, od.gn);
+    for (int k = 0; k < 9; ++k) {
+      sh.P[k] = st->imageBasis[k];
+      sh.P[9 + k] = st->kinv[k];
+      sh.P[18 + k] = st->krlr[k];
+    }
+    sh.P[27] = 0.f;
+  }
+  __syncthreads();
+  cluster_sync_all();
+  for (int iter = 0; iter < SO3_MAX_ITER; ++iter) {
+    if (tid < 28) sh.Pl[tid] = lead->P[tid];
+    __syncthreads();
+    if (sh.Pl[27] != 0.f) break;  // converged or diverging: the rest of the loop is skipped (uniform over the cluster)
+    float acc[11];
+    so3_rows<GC_THREADS>(od, load_m33(sh.Pl), load_m33(sh.Pl + 9), load_m33(sh.Pl + 18), rank, C, acc);
+    block_reduce_sum<11, GC_THREADS>(acc, sh.sred);
+    if (tid < 11) lead->slots[rank][tid] = acc[0];
+    cluster_sync_all();
+    if (rank == 0) {
+      if (tid < 11) {
+        double t = 0;
+        for (int r = 0; r < C; ++r) t += (double)sh.slots[r][tid];
+        st->sum_so3[tid] = (float)t;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        so3_finish(od, iter);
+        for (int k = 0; k < 9; ++k) {
+          sh.P[k] = st->imageBasis[k];
+          sh.P[9 + k] = st->kinv[k];
+          sh.P[18 + k] = st->krlr[k];
+        }
+        sh.P[27] = st->so3_done ? 1.f : 0.f;
+      }
+    }
+    cluster_sync_all();
+  }
+  cluster_sync_all();  // nobody leaves while a peer may still read its shared memory
+}
+
 namespace {
 
 inline int red_blocks(const EfContext* ctx, int n_items, int per_thread, int threads, int ctas_per_sm) {
@@ -1509,6 +1586,7 @@ static void ef_launch_cluster(EfContext* ctx, void (*kernel)(KArgs...), int clus
 int odom_cluster_size(int want) {
   if (want <= 0) return 0;
   cudaFuncSetAttribute(k_gn_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute(k_so3_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   for (int c = want > 8 ? 16 : 8; c >= 8; c >>= 1) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(c);
@@ -1529,6 +1607,11 @@ int odom_cluster_size(int want) {
 
 int odom_so3_async(EfContext* ctx, int which) {
   OdomDev& od = ctx->odom[which];
+  if (ctx->gn_cluster > 0 && ctx->so3_cluster) {
+    ef_launch_cluster(ctx, k_so3_cluster, ctx->gn_cluster, GC_THREADS, od);
+    EF_CHECK_LAST();
+    return 0;
+  }
   EF_LAUNCH(ctx, k_so3_begin, 1, 32, 0, od.so3s, (const GNState*)od.gn);
   const int nb = red_blocks(ctx, od.rows[2] * od.cols[2], 1, RED_THREADS, 2);
   for (int i = 0; i < SO3_MAX_ITER; ++i) EF_LAUNCH(ctx, k_so3_step, nb, RED_THREADS, 0, od, i, 1);
