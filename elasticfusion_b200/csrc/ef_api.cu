@@ -322,8 +322,6 @@ extern "C" int ef_create(const EfConfig* cfg, void* stream, EfContext** out) {
     ctx->fused_model_side = !(e && e[0] == '0');
     e = getenv("EF_GN_CLUSTER");
     ctx->gn_cluster = odom_cluster_size(e ? atoi(e) : 16);
-    e = getenv("EF_IT2_CLUSTER");
-    ctx->it2_cluster = !(e && e[0] == '0') && odom_cluster_size(8) > 0;
     e = getenv("EF_SO3_CLUSTER");
     ctx->so3_cluster = !(e && e[0] == '0');
     e = getenv("EF_GN_CLUSTER_LEVELS");

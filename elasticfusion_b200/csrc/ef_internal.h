@@ -218,7 +218,6 @@ struct EfContext {
   bool visible_list;      // second index-map pass of a frame visits only the surfels the first one rasterised; EF_VISIBLE_LIST=0 disables
   bool fused_model_side;  // model pyramids of a frame in 3 launches (k_model_level0 / _down) instead of 6; EF_FUSED_MODEL=0 disables
   int gn_cluster;         // CTAs of the cluster that runs the coarse-level Gauss-Newton iterations (0: two-kernel path everywhere)
-  bool it2_cluster;       // k_iter2 in clusters of 8 CTAs that pre-add their partial rows through DSMEM (k_iter2c); EF_IT2_CLUSTER=0 disables
   bool so3_cluster;       // the SO(3) pre-alignment loop in one cluster launch (k_so3_cluster); EF_SO3_CLUSTER=0: k_so3_begin + 10 x k_so3_step
   int gn_cluster_levels;  // pyramid levels, from the coarsest, whose iterations run in that cluster
   bool plain_next;     // the next ef_launch omits the programmatic-serialisation attribute (EF_PLAIN_NEXT)

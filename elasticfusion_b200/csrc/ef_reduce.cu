@@ -753,8 +753,7 @@ struct Iter2Shared {
 // the dense-pass partials and the photometric rows over its candidates. Returns the rgbOnly `break` decision.
 template <int THREADS>
 __device__ __forceinline__ bool iter2_rows(const OdomDev& od, Iter2Shared& sh, int level, int iter, int next_level, int nblocks1, int mode,
-                                           float sigma_override, int vb, int nvb, int pre_have = 0, int pre_base = 0, int pre_ncand = 0,
-                                           double* dst_icp = nullptr, float* dst_rgb = nullptr /* 32 values each; default: this CTA's global rows */) {
+                                           float sigma_override, int vb, int nvb, int pre_have = 0, int pre_base = 0, int pre_ncand = 0) {
   GnScratch& S = sh.S;
   GNState* gn = od.gn;
   const bool do_rgb = mode & 1, do_icp = mode & 2, solve = mode & 4, have_res = mode & 8;
@@ -827,7 +826,7 @@ __device__ __forceinline__ bool iter2_rows(const OdomDev& od, Iter2Shared& sh, i
   const bool brk = sh.brk != 0;
 
   if (!brk) {
-    if (do_icp && threadIdx.x < 32) (dst_icp ? dst_icp : od.partials2 + vb * 32)[threadIdx.x] = presum;
+    if (do_icp && threadIdx.x < 32) od.partials2[vb * 32 + threadIdx.x] = presum;
     if (do_rgb) {
       const float sigma = sh.sigma;
       float lfx, lfy, lcx, lcy;
@@ -841,7 +840,7 @@ __device__ __forceinline__ bool iter2_rows(const OdomDev& od, Iter2Shared& sh, i
         if (t.x != -1) rgb_accumulate(t, sigma, lfx, lfy, lcx, lcy, od.sobelScale, acc);
       }
       block_reduce_sum<29, THREADS>(acc, sh.sred);
-      if (threadIdx.x < 32) (dst_rgb ? dst_rgb : od.partials_rgb + vb * 32)[threadIdx.x] = (threadIdx.x < 29) ? acc[0] : 0.f;
+      if (threadIdx.x < 29) od.partials_rgb[vb * 32 + threadIdx.x] = acc[0];
     }
   }
   EF_STAMP(gn, 10, stamp && vb == 0);
@@ -1454,65 +1453,6 @@ __global__ void __launch_bounds__(RED_THREADS) k_so3_step(OdomDev od, int iter, 
   so3_finish(od, iter);
 }
 
-// k_iter2 in clusters of IT2_CL CTAs: the per-CTA partial rows (pre-summed geometric partials, photometric partial) go into the
-// cluster leader's shared memory, one cluster barrier later the leader adds them in rank order and only the leaders write a row
-// and take the ticket. The CTA that finishes the iteration then sums 19 rows instead of 150 (its 2.5 us of loads were the largest
-// piece of every iteration's serial tail) and 19 tickets queue on the counter instead of 150.
-constexpr int IT2_CL = 8;
-__device__ __forceinline__ bool last_of_n_done(unsigned int* counter, unsigned int n) {
-  __shared__ bool is_last_n;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int t = atomicAdd(counter, 1u);
-    is_last_n = (t == n - 1);
-    if (is_last_n) __threadfence();
-  }
-  __syncthreads();
-  return is_last_n;
-}
-__global__ void __launch_bounds__(IT2_THREADS) k_iter2c(OdomDev od, int level, int iter, int next_level, int nblocks1, int mode, float sigma_override) {
-  pdl_launch();
-  int pre_base = 0, pre_ncand = 0;
-  const int pre_have = (mode & 32) ? 1 : 0;
-  if (pre_have) {
-    const int* __restrict__ cb = od.cand_base;
-    pre_base = cb[level];
-    pre_ncand = cb[level + 1] - pre_base;
-  }
-  pdl_wait();
-  __shared__ Iter2Shared sh;
-  __shared__ double c_icp[IT2_CL][32];
-  __shared__ float c_rgb[IT2_CL][32];
-  GNState* gn = od.gn;
-  if ((mode & 4) && gn->break_level == level) {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && next_level >= 0 && next_level != level) gn_prepare_warp(gn, next_level);
-    return;  // (every CTA of every cluster takes this branch: no barrier is left waiting)
-  }
-  const int rank = (int)cluster_rank(), CL = (int)cluster_size();
-  const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
-  double(*l_icp)[32] = cluster_map(c_icp, 0u);
-  float(*l_rgb)[32] = cluster_map(c_rgb, 0u);
-  const bool brk = iter2_rows<IT2_THREADS>(od, sh, level, iter, next_level, nblocks1, mode, sigma_override, blockIdx.x, gridDim.x, pre_have, pre_base,
-                                           pre_ncand, &l_icp[rank][0], &l_rgb[rank][0]);
-  cluster_sync_all();
-  if (rank != 0) return;
-  if (!brk) {
-    const int t = threadIdx.x;
-    if ((mode & 2) && t < 32) {
-      double a = 0;
-      for (int r = 0; r < CL; ++r) a += c_icp[r][t];
-      od.partials2[cid * 32 + t] = a;
-    } else if ((mode & 1) && t >= 32 && t < 64) {
-      double a = 0;
-      for (int r = 0; r < CL; ++r) a += (double)c_rgb[r][t - 32];
-      od.partials_rgb[cid * 32 + t - 32] = (float)a;
-    }
-  }
-  if (!last_of_n_done(od.counter, (unsigned int)ncl)) return;
-  iter2_final<IT2_THREADS>(od, sh, level, iter, next_level, mode, ncl, brk);
-}
-
 // The whole SO(3) pre-alignment loop (k_so3_begin + up to 10 x k_so3_step) in one launch of one cluster: same protocol as
 // k_gn_cluster -- per-CTA 11-term partials into the leader's shared memory, the leader sums them in rank order in double, its
 // thread 0 runs the unchanged solve / convergence logic (so3_finish) and publishes the next iteration's three matrices and the
@@ -1642,28 +1582,6 @@ static void ef_launch_cluster(EfContext* ctx, void (*kernel)(KArgs...), int clus
   ctx->launches++;
 }
 
-// `grid` CTAs in clusters of `cluster`
-template <typename... KArgs, typename... Args>
-static void ef_launch_cluster_grid(EfContext* ctx, void (*kernel)(KArgs...), int grid, int cluster, int block, Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(block);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = (ctx->pdl && !ctx->plain_next) ? 2 : 1;
-  ctx->plain_next = false;
-  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-  ctx->launches++;
-}
-
 // Largest cluster (16, else 8) of k_gn_cluster the device can co-schedule; 0 when clusters are unavailable. Called once per context.
 int odom_cluster_size(int want) {
   if (want <= 0) return 0;
@@ -1753,14 +1671,8 @@ int odom_track_async(EfContext* ctx, int which, bool rgbOnly, float icpWeight, b
     const int next_lv = (s + 1 < ns) ? sched_level[s + 1] : -1;
     const int nb1 = red_blocks(ctx, npx, 4, IT1_THREADS, IT1_CTAS_PER_SM);
     EF_LAUNCH(ctx, k_iter1, nb1, IT1_THREADS, 0, od, lv, rgb ? 1 : 0, icp ? 1 : 0, 1, prefetch);
-    int nb2 = iter2_blocks(ctx, npx, rgb, icp ? nb1 : 0);
-    const int mode2 = (rgb ? 1 | 8 : 0) | (icp ? 2 : 0) | 4 | (prefetch ? 32 : 0);
-    if (ctx->it2_cluster) {
-      nb2 = (nb2 + IT2_CL - 1) / IT2_CL * IT2_CL;  // whole clusters (a CTA without candidates still pre-sums its share of rows)
-      ef_launch_cluster_grid(ctx, k_iter2c, nb2, IT2_CL, IT2_THREADS, od, lv, sched_iter[s], next_lv, nb1, mode2, 0.f);
-    } else {
-      EF_LAUNCH(ctx, k_iter2, nb2, IT2_THREADS, 0, od, lv, sched_iter[s], next_lv, nb1, mode2, 0.f);
-    }
+    const int nb2 = iter2_blocks(ctx, npx, rgb, icp ? nb1 : 0);
+    EF_LAUNCH(ctx, k_iter2, nb2, IT2_THREADS, 0, od, lv, sched_iter[s], next_lv, nb1, (rgb ? 1 | 8 : 0) | (icp ? 2 : 0) | 4 | (prefetch ? 32 : 0), 0.f);
   }
   ef_stage(ctx, 5);
   if (so3)

@@ -7,7 +7,7 @@ export PYTHONUNBUFFERED=1
 timeout 1200 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider > gpurun_out/r02_pytest_final.txt 2>&1
 tail -n 6 gpurun_out/r02_pytest_final.txt
 rm -f gpurun_out/r02_stage_times_final.txt
-for cfg in "EF_DUMMY=1" "EF_IT2_CLUSTER=0" "EF_SO3_CLUSTER=0" "EF_FUSED_MODEL=0" "EF_VISIBLE_LIST=0" "EF_GN_CLUSTER=0" "EF_IT1_PREFETCH=0"; do
+for cfg in "EF_DUMMY=1" "EF_SO3_CLUSTER=0" "EF_FUSED_MODEL=0" "EF_VISIBLE_LIST=0" "EF_GN_CLUSTER=0" "EF_IT1_PREFETCH=0" "EF_NO_PDL=1"; do
   echo "== stage times: $cfg" | tee -a gpurun_out/r02_stage_times_final.txt
   env $cfg timeout 300 python scripts/stage_times.py 60 2>&1 | tail -13 | tee -a gpurun_out/r02_stage_times_final.txt
 done

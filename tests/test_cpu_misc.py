@@ -280,7 +280,7 @@ def test_every_kernel_waits_on_its_predecessor():
                 continue  # declaration
             body = re.sub(r"//[^\n]*\n|/\*.*?\*/", "", src[k + 1:k + 2600], flags=re.S).lstrip()  # comments may precede it
             head = src[m.start():m.start() + 200]
-            if body.startswith("pdl_launch();") and ("k_iter1(" in head or "k_iter2(" in head or "k_iter2c(" in head):
+            if body.startswith("pdl_launch();") and ("k_iter1(" in head or "k_iter2(" in head):
                 # the two kernels with a prologue ahead of their wait (live maps / candidate list, final before the loop starts); the
                 # wait must precede the first read of anything the Gauss-Newton loop writes (the device state block od.gn, the
                 # per-iteration terms, the partials)

