@@ -80,7 +80,6 @@ struct Arena {
   }
 };
 
-Arena* arena_of(EfContext* ctx);
 
 struct CtxExtra {
   Arena arena;

@@ -509,7 +509,7 @@ __device__ __forceinline__ void iter1_body(const OdomDev& od, int level, int do_
   // smaller than the grid still occupies every SM evenly
   const int gid = (wid * nvb + vb) * 32 + lane, gstride = nvb * THREADS;
 
-  const bool stamp = (vb == 0 && threadIdx.x == 0 && level == 0);
+  [[maybe_unused]] const bool stamp = (vb == 0 && threadIdx.x == 0 && level == 0);
   EF_STAMP(gn, 0, stamp);
   unsigned int cnt = 0, sig = 0;
   const bool vec = (cols & 3) == 0;
@@ -758,7 +758,7 @@ __device__ __forceinline__ bool iter2_rows(const OdomDev& od, Iter2Shared& sh, i
   GNState* gn = od.gn;
   const bool do_rgb = mode & 1, do_icp = mode & 2, solve = mode & 4, have_res = mode & 8;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const bool stamp = (threadIdx.x == 0 && level == 0);
+  [[maybe_unused]] const bool stamp = (threadIdx.x == 0 && level == 0);
   EF_STAMP(gn, 8, stamp && vb == 0);
 
   // issue the loads that do not depend on sigma first: this CTA's candidate terms and its share of the dense partials
@@ -855,7 +855,7 @@ __device__ __forceinline__ void iter2_final(const OdomDev& od, Iter2Shared& sh, 
   GNState* gn = od.gn;
   const bool do_rgb = mode & 1, do_icp = mode & 2, solve = mode & 4;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const bool stamp = (threadIdx.x == 0 && level == 0);
+  [[maybe_unused]] const bool stamp = (threadIdx.x == 0 && level == 0);
   EF_STAMP(gn, 11, stamp);
   if (threadIdx.x == 0) {
     *od.counter = 0;
