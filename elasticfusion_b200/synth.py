@@ -73,8 +73,8 @@ def trajectory(n: int, seed: int = 42, speed: float = 1.0) -> np.ndarray:
 
 def corner_trajectory(n: int, seed: int = 42, speed: float = 1.0) -> np.ndarray:
     """(n,4,4) camera-to-room poses looking DOWN into a floor corner of the room from ~1.5 m: three mutually orthogonal planes
-    fill the image, all of them inside the 3 m depth cut-off, so the geometric term alone constrains all six degrees of
-    freedom (the default trajectory sees two walls beyond the cut-off for most of its pixels: point-to-plane ICP slides along
+    are in view (the floor on a few per cent of the pixels at the extremes of the sway), inside the 3 m depth cut-off over the
+    first ~100 / speed frames, so the geometric term alone constrains all six degrees of freedom (the default trajectory sees two walls beyond the cut-off for most of its pixels: point-to-plane ICP slides along
     them and only the photometric term holds the pose). Same Lissajous sway, <= ~1 cm and <= ~0.5 deg per frame at speed 1."""
     rng = np.random.RandomState(seed)
     ph = rng.uniform(0, 2 * np.pi, size=6)

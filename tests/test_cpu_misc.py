@@ -97,6 +97,21 @@ def test_render_is_consistent_with_ground_truth_pose(small_K):
     assert fr[0][0].min() >= 1  # no zero intensities (nextImage > 0 gate)
 
 
+def test_corner_views_show_three_plane_orientations_inside_the_cutoff(small_K):
+    """synth.corner_trajectory over the stretches the ICP-only registration tests use (Ferns: seed 17, speed 3, 16 frames; 1/8
+    resolution: seed 5, speed 1, 12 frames): three mutually orthogonal planes in every view, each on >= 4 % of the pixels, all
+    depths inside the 3 m cut-off. (With fewer plane orientations in range, point-to-plane ICP slides -- on the oracle as well.)"""
+    from elasticfusion_b200 import synth
+
+    for seed, speed, n in ((17, 3.0, 16), (5, 1.0, 12)):
+        for i, T in enumerate(synth.corner_trajectory(n, seed=seed, speed=speed)):
+            _, depth, _, n_c = synth.render(T, small_K)
+            assert depth.min() > 300 and depth.max() < 3000, (seed, i, depth.min(), depth.max())
+            n_room = np.rint(n_c.reshape(-1, 3) @ T[:3, :3].T).astype(int)  # camera-frame normals back to the room's axes
+            axes, counts = np.unique(np.abs(n_room), axis=0, return_counts=True)
+            assert len(axes) == 3 and counts.min() > 0.04 * depth.size, (seed, i, axes, counts)
+
+
 # ---------------------------------------------------------------- analytic KATs of the oracle
 def test_icp_converges_to_ground_truth_on_exact_maps(small_K):
     """Planar room, noise-free float vertex/normal maps: the point-plane system has zero residual at the true pose, so
